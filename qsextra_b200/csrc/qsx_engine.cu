@@ -199,6 +199,7 @@ __device__ void emit(const double2* s, const EvolveParams& k, int inst, int slot
         double2* dst = reinterpret_cast<double2*>(a.out_snap) + ((size_t)inst * a.n_emit + slot) * k.E;
         for (int e = threadIdx.x; e < k.E; e += blockDim.x) dst[e] = s[e];
     }
+    __syncthreads();      // the next pass overwrites sigma
 }
 
 __global__ void evolve_generic_kernel(const EvolveParams k) {

@@ -1,0 +1,79 @@
+"""ctypes binding of ``libqsx.so`` (C ABI declared in ``include/qsx.h``).
+
+The shared library is built in-tree by ``qsextra_b200/csrc/build.py`` (``__graft_entry__.build()``).  There is no
+CPU fallback: ``load()`` raises if the library is missing, and every compute call raises ``QsxError`` with the
+library's message when it fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libqsx.so')
+ABI_VERSION = 1
+
+EXPORTS = ('qsx_abi_version', 'qsx_last_error', 'qsx_device_info', 'qsx_evolve_workspace_bytes', 'qsx_evolve',
+           'qsx_apply_dipole', 'qsx_fp64_peak')
+
+
+class QsxError(RuntimeError):
+    pass
+
+
+class QsxOp(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ('type', 'i0', 'i1', 'i2', 'i3', 'i4', 'p', 'reserved')]
+
+
+class QsxBlock(C.Structure):
+    _fields_ = [('n_sites', C.c_int32), ('n_bits', C.c_int32), ('nA', C.c_int32), ('nB', C.c_int32),
+                ('cfgA', C.c_void_p), ('cfgB', C.c_void_p), ('rankA', C.c_void_p), ('rankB', C.c_void_p)]
+
+
+class QsxEvolveArgs(C.Structure):
+    _fields_ = [('block', QsxBlock),
+                ('n_ops', C.c_int32), ('ops', C.c_void_p),
+                ('param_stride', C.c_int32), ('params', C.c_void_p),
+                ('n_inst', C.c_int32), ('inst_set', C.c_void_p), ('inst_src', C.c_void_p),
+                ('sigma_in', C.c_void_p),
+                ('n_steps', C.c_int32), ('n_emit', C.c_int32), ('emit_steps', C.c_void_p),
+                ('n_obs', C.c_int32), ('obs_ptr', C.c_void_p), ('obs_idx', C.c_void_p), ('obs_w', C.c_void_p),
+                ('out_obs', C.c_void_p), ('obs_real', C.c_int32),
+                ('out_snap', C.c_void_p), ('workspace', C.c_void_p), ('threads', C.c_int32)]
+
+
+_lib = None
+
+
+def load():
+    """Load libqsx.so once; raise (never fall back) when it is absent or has the wrong ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise QsxError('CUDA extension {} is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                       '(there is no CPU fallback)'.format(LIB_PATH))
+    lib = C.CDLL(LIB_PATH)
+    lib.qsx_abi_version.restype = C.c_int32
+    lib.qsx_last_error.restype = C.c_char_p
+    lib.qsx_device_info.argtypes = [C.POINTER(C.c_int32)] * 3
+    lib.qsx_device_info.restype = C.c_int32
+    lib.qsx_evolve_workspace_bytes.argtypes = [C.POINTER(QsxEvolveArgs)]
+    lib.qsx_evolve_workspace_bytes.restype = C.c_int64
+    lib.qsx_evolve.argtypes = [C.POINTER(QsxEvolveArgs), C.c_void_p]
+    lib.qsx_evolve.restype = C.c_int32
+    lib.qsx_apply_dipole.argtypes = [C.POINTER(QsxBlock), C.POINTER(QsxBlock), C.c_int32, C.c_void_p, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.qsx_apply_dipole.restype = C.c_int32
+    lib.qsx_fp64_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
+    lib.qsx_fp64_peak.restype = C.c_int32
+    if lib.qsx_abi_version() != ABI_VERSION:
+        raise QsxError('libqsx.so ABI {} != expected {}'.format(lib.qsx_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc < 0:
+        raise QsxError('libqsx: {} (code {})'.format(load().qsx_last_error().decode(), rc))
+    return rc

@@ -1,0 +1,514 @@
+"""Host-side compiler: system parameters -> step program of the CUDA engine (``qsx_op`` list + angle tables).
+
+Mirrors what the reference builds with Qiskit objects in ``qevolve.py``:
+
+  :74-105   system block           Z_i (-eps_i/2), then X_iX_j, Y_iY_j (J_ij/2) for i<j, Lie/Suzuki product formula
+  :107-195  pseudomode operators   Gray-coded a, a^dagger, a + a^dagger, a^dagger a as Pauli sums
+  :197-253  mode evolution, exciton-mode coupling g (a + a^dagger) (I - Z_e)/2
+  :255-290  step assembly order    system block; for k: for i: [mode(i,k), coupling(i,k)]
+  :292-348  collisions             rzx + reset (dephasing)  |  sqrt(rate/dt)(a sigma+ + a^dagger sigma-) + reset
+  :362-428  dt / Trotter_number / step-count logic
+
+but in the engine's vocabulary (include/qsx.h): Pauli strings are (xmask, zmask) pairs, Z-type rotations are
+merged into diagonal tables, X_iX_j/Y_iY_j pairs into exciton hops, X_m / X_m Z_e pairs into rotations
+conditioned on the site occupation, and the 2-level collision + reset into an amplitude-damping channel.
+All parameters carry a leading batch axis so one compile serves many parameter sets of the same structure.
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .sectors import Block
+
+OP_DIAG, OP_HOP, OP_PROT, OP_AD, OP_RESET = 0, 1, 2, 3, 4
+
+
+# ---------------------------------------------------------------------------------------------
+# batched system parameters
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class SystemBatch:
+    """Parameters of B systems that share one structure (N, pseudomode levels)."""
+    energies: np.ndarray                    # [B, N]
+    couplings: np.ndarray                   # [B, N, N]
+    dipole_moments: np.ndarray              # [B, N]
+    omega: np.ndarray | None = None         # [B, W]
+    coupl_ep: np.ndarray | None = None      # [B, W]
+    levels: tuple[int, ...] | None = None   # W entries
+
+    @property
+    def batch(self) -> int:
+        return self.energies.shape[0]
+
+    @property
+    def n_sites(self) -> int:
+        return self.energies.shape[1]
+
+    @property
+    def chromophore(self) -> bool:
+        return self.levels is not None
+
+    @property
+    def n_modes(self) -> int:
+        return len(self.levels) if self.levels is not None else 0
+
+    @classmethod
+    def from_systems(cls, systems) -> "SystemBatch":
+        systems = list(systems)
+        first = systems[0]
+        md = getattr(first, 'mode_dict', None)
+        kw = dict(energies=np.array([np.asarray(s.e_el, dtype=float) for s in systems]),
+                  couplings=np.array([np.asarray(s.coupl_el, dtype=float) for s in systems]),
+                  dipole_moments=np.array([np.asarray(s.dipole_moments, dtype=float) for s in systems]))
+        if md is not None:
+            levels = tuple(int(d) for d in md['lvl_mode'])
+            for s in systems:
+                if s.mode_dict is None or tuple(int(d) for d in s.mode_dict['lvl_mode']) != levels:
+                    raise ValueError('all systems of a batch must have the same pseudomode levels')
+            kw.update(levels=levels,
+                      omega=np.array([np.asarray(s.mode_dict['omega_mode'], dtype=float) for s in systems]),
+                      coupl_ep=np.array([np.asarray(s.mode_dict['coupl_ep'], dtype=float) for s in systems]))
+        return cls(**kw)
+
+
+def mode_register_size(d_k: int) -> int:
+    """Qubits of a d_k-level pseudomode register (qevolve.py:28-35)."""
+    nq = np.log2(d_k)
+    return int(np.ceil(nq)) if abs(np.round(nq) - nq) > 1e-10 else int(np.round(nq))
+
+
+@dataclass
+class BitLayout:
+    """Positions of pseudomode qubits (and the optional collision ancilla) inside ``bits``; same order as the
+    reference's registers mode(0,0), mode(0,1), ..., mode(N-1,W-1) (qevolve.py:25-37)."""
+    mode: dict
+    ancilla: int | None
+    n_bits: int
+
+    @classmethod
+    def build(cls, n_sites: int, levels, with_ancilla: bool) -> "BitLayout":
+        mode, nxt = {}, 0
+        for i in range(n_sites):
+            for k, d in enumerate(levels or ()):
+                q = mode_register_size(d)
+                mode[(i, k)] = list(range(nxt, nxt + q))
+                nxt += q
+        anc = nxt if with_ancilla else None
+        return cls(mode, anc, nxt + (1 if with_ancilla else 0))
+
+
+# ---------------------------------------------------------------------------------------------
+# Pauli sums of the Gray-coded ladder operators  (qevolve.py:107-195)
+# ---------------------------------------------------------------------------------------------
+def _projector_terms(u: int, v: int, nq: int):
+    """Pauli expansion of |u><v| on nq qubits as [(xmask, zmask, coeff)], highest qubit varying slowest and
+    (I|X) before (Z|Y) on every qubit -- the enumeration order of the reference's itertools.product."""
+    per_qubit = []
+    for q in range(nq - 1, -1, -1):
+        uq, vq = (u >> q) & 1, (v >> q) & 1
+        bit = 1 << q
+        if uq == vq:
+            per_qubit.append([(0, 0, 0.5), (0, bit, 0.5 if uq == 0 else -0.5)])
+        else:
+            per_qubit.append([(bit, 0, 0.5), (bit, bit, 0.5j if uq == 0 else -0.5j)])
+    out = []
+    for combo in itertools.product(*per_qubit):
+        x = z = 0
+        coeff = 1.0
+        first = True
+        for cx, cz, cc in combo:
+            x |= cx
+            z |= cz
+            coeff = cc if first else coeff * cc
+            first = False
+        out.append((x, z, coeff))
+    return out
+
+
+def mode_operator_terms(d_k: int):
+    """Ordered {(xmask, zmask): coeff} of a, a^dagger, a + a^dagger and a^dagger a; level l sits on the basis
+    state whose bits are Gray(l) = l ^ (l >> 1)."""
+    nq = mode_register_size(d_k)
+    gray = [l ^ (l >> 1) for l in range(1 << nq)]
+
+    def accumulate(target, u, v, weight):
+        for x, z, c in _projector_terms(u, v, nq):
+            value = weight * c
+            key = (x, z)
+            target[key] = target[key] + value if key in target else value
+
+    a, adag, num = {}, {}, {}
+    for l in range(1, d_k):
+        accumulate(a, gray[l - 1], gray[l], np.sqrt(l))
+    for l in range(d_k - 1):
+        accumulate(adag, gray[l + 1], gray[l], np.sqrt(l + 1))
+    for l in range(d_k):
+        accumulate(num, gray[l], gray[l], l)
+    a_plus_adag = {k: a[k] + adag[k] for k in a if a[k] != -adag[k]}
+    return a, adag, a_plus_adag, num
+
+
+# ---------------------------------------------------------------------------------------------
+# literal term list of one propagation step
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class Rot:
+    """exp(-i angle P), P = (Pauli on system qubits xs/zs) x (Pauli on bits xb/zb); angle has shape [B]."""
+    xs: int
+    zs: int
+    xb: int
+    zb: int
+    angle: np.ndarray
+
+
+@dataclass
+class Dephase:
+    site: int
+    phi: np.ndarray
+
+
+@dataclass
+class Damp:
+    bit: int
+    phi: np.ndarray
+
+
+@dataclass
+class Reset:
+    bit: int
+
+
+def product_formula(terms, time, order):
+    """[(masks..., coeff[B])] -> [(masks..., angle[B])] in application order.  Order 1 = Lie-Trotter; even orders =
+    Suzuki as synthesised by Qiskit 1.0 (order 2: half steps of terms[1:] reversed, full first term, mirrored;
+    order 2k by the 1/(4 - 4^(1/(2k-1))) recursion); odd orders > 1 are rejected like Qiskit does."""
+    if order == 1:
+        return [(m, c * time) for m, c in terms]
+    if order % 2 == 1:
+        raise ValueError('Suzuki product formulae are symmetric and therefore only defined for even orders.')
+
+    def recurse(o, t):
+        if o == 2:
+            halves = [(m, c * t / 2) for m, c in reversed(terms[1:])]
+            return halves + [(terms[0][0], terms[0][1] * t)] + halves[::-1]
+        p = 1 / (4 - 4 ** (1 / (o - 1)))
+        outer = recurse(o - 2, p * t)
+        return outer + outer + recurse(o - 2, (1 - 4 * p) * t) + outer + outer
+    return recurse(order, time)
+
+
+def _simplify(terms):
+    """SparsePauliOp.simplify(): sum duplicates in first-appearance order, drop |c| <= 1e-8."""
+    order, sums = [], {}
+    for key, c in terms:
+        if key not in sums:
+            order.append(key)
+            sums[key] = 0j
+        sums[key] = sums[key] + c
+    return [(k, sums[k]) for k in order if not np.isclose(sums[k], 0, atol=1e-8, rtol=1e-5)]
+
+
+def _place(mask: int, positions: list[int]) -> int:
+    out = 0
+    for j, pos in enumerate(positions):
+        if (mask >> j) & 1:
+            out |= 1 << pos
+    return out
+
+
+def step_terms(batch: SystemBatch, layout: BitLayout, dt: float, dt_trotter: float, trotter_number: int,
+               order: int, coll_rates):
+    """One propagation step as a list of Rot / Dephase / Damp / Reset in the reference's order
+    (Trotter_number Trotter steps, then one collision round, qevolve.py:419-422).
+
+    ``coll_rates``: None, [B] (excitonic) or [B, W] (chromophore)."""
+    n, B = batch.n_sites, batch.batch
+    eps, J = batch.energies, batch.couplings
+
+    # system block (qevolve.py:84-101); a term exists if the parameter is non-zero for any member of the batch
+    sys_terms = []
+    for i in range(n):
+        if np.any(eps[:, i] != 0.):
+            sys_terms.append(((0, 1 << i, 0, 0), -eps[:, i] / 2))
+    for i in range(n):
+        for j in range(i + 1, n):
+            if np.any(J[:, i, j] != 0.):
+                pair = (1 << i) | (1 << j)
+                sys_terms.append(((pair, 0, 0, 0), J[:, i, j] / 2))           # X_i X_j
+                sys_terms.append(((pair, pair, 0, 0), J[:, i, j] / 2))        # Y_i Y_j
+    trotter = [Rot(*m, a) for m, a in product_formula(sys_terms, dt_trotter, order)] if sys_terms else []
+
+    if batch.chromophore:
+        for k, d_k in enumerate(batch.levels):                                 # qevolve.py:272-289
+            _, _, a_plus_adag, num = mode_operator_terms(d_k)
+            omega, g = batch.omega[:, k], batch.coupl_ep[:, k]
+            mode_rot, int_rot = [], []
+            if np.any(omega != 0):
+                terms = [((x, z), omega * np.real(c)) for (x, z), c in num.items()]
+                mode_rot = product_formula(terms, dt_trotter, order)
+            if np.any(g != 0):
+                both = [((x, z, zs), c * cz) for (x, z), c in a_plus_adag.items() for zs, cz in ((0, 0.5), (1, -0.5))]
+                terms = [(key, g * np.real(c)) for key, c in _simplify(both)]
+                int_rot = product_formula(terms, dt_trotter, order)
+            for i in range(n):
+                pos = layout.mode[(i, k)]
+                for (x, z), ang in mode_rot:
+                    trotter.append(Rot(0, 0, _place(x, pos), _place(z, pos), ang))
+                for (x, z, zs), ang in int_rot:
+                    trotter.append(Rot(0, (1 << i) if zs else 0, _place(x, pos), _place(z, pos), ang))
+
+    ops = trotter * trotter_number
+    if coll_rates is None:
+        return ops
+    rates = np.asarray(coll_rates, dtype=float)
+    if not batch.chromophore:                                                  # qevolve.py:302-304
+        phi = np.sqrt(rates.reshape(B)) * np.sqrt(dt)                          # rzx angle / 2
+        return ops + [Dephase(i, phi) for i in range(n)]
+    rates = rates.reshape(B, batch.n_modes)
+    for k, d_k in enumerate(batch.levels):                                     # qevolve.py:328-347
+        if not np.any(rates[:, k] != 0):
+            continue
+        pos0 = layout.mode[(0, k)]
+        if len(pos0) == 1:
+            # exp(-i phi/2 XX) exp(-i phi/2 YY) on (mode, ancilla |0>) + reset  ==  amplitude damping, phi = sqrt(rate dt)
+            phi = dt * np.sqrt(rates[:, k] / dt)
+            ops += [Damp(layout.mode[(i, k)][0], phi) for i in range(n)]
+            continue
+        a, adag, _, _ = mode_operator_terms(d_k)
+        # ancilla is the LOW qubit of the reference's gate; here it is its own bit: keys (x_mode, z_mode, x_anc, z_anc)
+        both = [((x, z, 1, za), c * ca) for (x, z), c in a.items() for za, ca in ((0, 0.5), (1, -0.5j))]
+        both += [((x, z, 1, za), c * ca) for (x, z), c in adag.items() for za, ca in ((0, 0.5), (1, 0.5j))]
+        scale = np.sqrt(rates[:, k] / dt)
+        terms = [(key, scale * np.real(c)) for key, c in _simplify(both)]
+        rots = product_formula(terms, dt, order)
+        anc = 1 << layout.ancilla
+        for i in range(n):
+            pos = layout.mode[(i, k)]
+            for (x, z, xa, za), ang in rots:
+                ops.append(Rot(0, 0, _place(x, pos) | (anc if xa else 0), _place(z, pos) | (anc if za else 0), ang))
+            ops.append(Reset(layout.ancilla))
+    return ops
+
+
+# ---------------------------------------------------------------------------------------------
+# lowering to engine operations
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class _Diag:
+    zterms: list = field(default_factory=list)      # (zs, zb, angle[B])
+    deph: list = field(default_factory=list)        # (site, phi[B])
+
+
+@dataclass
+class _Hop:
+    i: int
+    j: int
+    xx: np.ndarray
+    yy: np.ndarray
+
+
+@dataclass
+class _Prot:
+    xb: int
+    zb: int
+    site: int                                        # -1: unconditioned
+    plain: np.ndarray                                # summed angle of the terms without Z_site
+    signed: np.ndarray                               # summed angle of the terms with Z_site
+
+
+def _popcount(v: int) -> int:
+    return bin(v).count('1')
+
+
+def _z_commutes(op, zs: int, zb: int) -> bool:
+    """Does exp(-i th Z^zs Z^zb) commute with ``op`` (as maps on sigma)?"""
+    if isinstance(op, _Hop):
+        return _popcount(zs & ((1 << op.i) | (1 << op.j))) % 2 == 0
+    if isinstance(op, _Prot):
+        return _popcount(zb & op.xb) % 2 == 0
+    return True                                      # Damp / Reset commute with Z on their own bit; _Diag trivially
+
+
+def _deph_commutes(op, site: int) -> bool:
+    if isinstance(op, _Hop):
+        return site not in (op.i, op.j)
+    return True
+
+
+def lower(terms, n_sites: int):
+    """Literal terms -> [_Diag | _Hop | _Prot | Damp | Reset], preserving the result exactly up to rounding:
+    Z-type terms move back to the nearest diagonal table they commute with, adjacent XX/YY of one pair fuse into a
+    hop, adjacent rotations with the same bit-Pauli fuse into one rotation conditioned on a site's occupation."""
+    ops = []
+
+    def add_diagonal(commutes, store):
+        j = len(ops)
+        while j > 0 and not isinstance(ops[j - 1], _Diag) and commutes(ops[j - 1]):
+            j -= 1
+        if j > 0 and isinstance(ops[j - 1], _Diag):
+            store(ops[j - 1])
+        else:
+            d = _Diag()
+            store(d)
+            ops.insert(j, d)
+
+    for t in terms:
+        if isinstance(t, Dephase):
+            add_diagonal(lambda op: _deph_commutes(op, t.site), lambda d: d.deph.append((t.site, t.phi)))
+        elif isinstance(t, (Damp, Reset)):
+            ops.append(t)
+        elif t.xs == 0 and t.xb == 0:
+            if t.zs == 0 and t.zb == 0:
+                continue                              # identity term: global phase
+            add_diagonal(lambda op: _z_commutes(op, t.zs, t.zb), lambda d: d.zterms.append((t.zs, t.zb, t.angle)))
+        elif t.xb == 0:
+            if _popcount(t.xs) != 2 or t.zs not in (0, t.xs):
+                raise NotImplementedError('system-qubit rotation outside the XX/YY family')
+            i, j = [q for q in range(n_sites) if (t.xs >> q) & 1]
+            last = ops[-1] if ops else None
+            if not (isinstance(last, _Hop) and (last.i, last.j) == (i, j)):
+                last = _Hop(i, j, np.zeros_like(t.angle), np.zeros_like(t.angle))
+                ops.append(last)
+            if t.zs == 0:
+                last.xx = last.xx + t.angle
+            else:
+                last.yy = last.yy + t.angle
+        else:
+            if t.xs != 0 or _popcount(t.zs) > 1:
+                raise NotImplementedError('rotation coupling bits to more than a Z on one site')
+            site = [q for q in range(n_sites) if (t.zs >> q) & 1][0] if t.zs else -1
+            last = ops[-1] if ops else None
+            fusable = (isinstance(last, _Prot) and (last.xb, last.zb) == (t.xb, t.zb)
+                       and (site == -1 or last.site in (-1, site)))
+            if not fusable:
+                last = _Prot(t.xb, t.zb, -1, np.zeros_like(t.angle), np.zeros_like(t.angle))
+                ops.append(last)
+            if site == -1:
+                last.plain = last.plain + t.angle
+            else:
+                last.site = site
+                last.signed = last.signed + t.angle
+    for op in ops:
+        if isinstance(op, _Hop) and not np.array_equal(op.xx, op.yy):
+            raise NotImplementedError('XX and YY angles differ: the step does not conserve the exciton number')
+    return ops
+
+
+# ---------------------------------------------------------------------------------------------
+# step program bound to a sector block
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class BoundProgram:
+    block: Block
+    ops: np.ndarray          # [n_ops, 8] int32 (qsx_op)
+    params: np.ndarray       # [B, stride] float64
+    labels: list             # human-readable op names, for reports
+
+
+class StepProgram:
+    """One propagation step of ``qevolve`` for a batch of parameter sets, independent of the sector."""
+
+    def __init__(self, batch: SystemBatch, dt, Trotter_number=1, Trotter_order=1, coll_rates=None,
+                 dt_trotter=None):
+        self.batch = batch
+        self.n_sites = batch.n_sites
+        rates = None if coll_rates is None else np.asarray(coll_rates, dtype=float)
+        needs_ancilla = (rates is not None and batch.chromophore
+                         and any(mode_register_size(d) > 1 and np.any(rates.reshape(batch.batch, -1)[:, k] != 0)
+                                 for k, d in enumerate(batch.levels)))
+        self.layout = BitLayout.build(batch.n_sites, batch.levels, needs_ancilla)
+        self.n_bits = self.layout.n_bits
+        if dt_trotter is None:
+            dt_trotter = dt / Trotter_number
+        self.terms = step_terms(batch, self.layout, dt, dt_trotter, Trotter_number, Trotter_order, rates)
+        self.lowered = lower(self.terms, batch.n_sites)
+
+    def block(self, ka: int, kb: int) -> Block:
+        return Block(self.n_sites, self.n_bits, ka, kb)
+
+    def bind(self, block: Block) -> BoundProgram:
+        """Angle tables and qsx_op array for one (KA, KB) block."""
+        B = self.batch.batch
+        nb = block.n_bits
+        chunks, ops, labels = [], [], []
+        cursor = 0
+
+        def push(arr):                               # arr [B, n] doubles; slots are kept even (16-byte aligned)
+            nonlocal cursor
+            slot = cursor
+            arr = np.ascontiguousarray(arr, dtype=np.float64).reshape(B, -1)
+            if arr.shape[1] % 2:
+                arr = np.concatenate([arr, np.zeros((B, 1))], axis=1)
+            chunks.append(arr)
+            cursor += arr.shape[1]
+            return slot
+
+        def side_table(cfgs, zterms):
+            masks = np.array(cfgs, dtype=np.int64)
+            idx = np.arange(len(cfgs) << nb, dtype=np.int64)
+            cfg_of, bits_of = masks[idx >> nb], idx & ((1 << nb) - 1)
+            phase = np.zeros((B, idx.size))
+            for zs, zb, ang in zterms:
+                par = np.array([_popcount(int(c) & zs) for c in cfg_of]) + np.array([_popcount(int(m) & zb) for m in bits_of])
+                phase += ang[:, None] * (1 - 2 * (par & 1))[None, :]
+            g = np.exp(-1j * phase)
+            return np.stack([g.real, g.imag], axis=-1).reshape(B, -1)
+
+        for op in self.lowered:
+            if isinstance(op, _Diag):
+                slot_a = push(side_table(block.cfg_a, op.zterms))
+                slot_b = push(side_table(block.cfg_b, op.zterms))
+                slot_t = -1
+                if op.deph:
+                    t = np.ones((B, block.n_a, block.n_b))
+                    differs = np.array([[[(ca >> s) & 1 != (cb >> s) & 1 for cb in block.cfg_b] for ca in block.cfg_a]
+                                        for s in range(self.n_sites)])
+                    for site, phi in op.deph:
+                        c, s = np.cos(phi), np.sin(phi)
+                        t = t * np.where(differs[site][None], (c * c - s * s)[:, None, None], 1.0)
+                    slot_t = push(t)
+                ops.append([OP_DIAG, slot_a, slot_b, slot_t, 0, 0, 0, 0])
+                labels.append('diag')
+            elif isinstance(op, _Hop):
+                slot = push(np.stack([np.cos(2 * op.xx), np.sin(2 * op.xx)], axis=1))
+                ops.append([OP_HOP, op.i, op.j, 0, 0, 0, slot, 0])
+                labels.append('hop({},{})'.format(op.i, op.j))
+            elif isinstance(op, _Prot):
+                th0, th1 = op.plain + op.signed, op.plain - op.signed      # Z_site = +1 (empty) / -1 (occupied)
+                skip0 = int(op.site >= 0 and not np.any(th0 != 0))
+                slot = push(np.stack([np.cos(th0), np.sin(th0), np.cos(th1), np.sin(th1)], axis=1))
+                ny = _popcount(op.xb & op.zb) & 3
+                ops.append([OP_PROT, op.xb, op.zb, ny, op.site, skip0, slot, 0])
+                labels.append('prot(x={:b},z={:b},site={})'.format(op.xb, op.zb, op.site))
+            elif isinstance(op, Damp):
+                slot = push(np.stack([np.cos(op.phi), np.sin(op.phi) ** 2], axis=1))
+                ops.append([OP_AD, op.bit, 0, 0, 0, 0, slot, 0])
+                labels.append('damp({})'.format(op.bit))
+            elif isinstance(op, Reset):
+                ops.append([OP_RESET, op.bit, 0, 0, 0, 0, 0, 0])
+                labels.append('reset({})'.format(op.bit))
+        params = np.concatenate(chunks, axis=1) if chunks else np.zeros((B, 2))
+        return BoundProgram(block, np.array(ops, dtype=np.int32).reshape(-1, 8), params, labels)
+
+
+# ---------------------------------------------------------------------------------------------
+# time-grid logic  (qevolve.py:373-391)
+# ---------------------------------------------------------------------------------------------
+def resolve_time_grid(time, dt, Trotter_number):
+    """-> (dt, dt_trotter, Trotter_number, integer step count of every entry of ``time``).
+
+    ``dt is None``: dt = (time[1] - time[0]) / Trotter_number (or time / Trotter_number for a scalar) and the
+    collisions then fire every dt (Trotter_number becomes 1).  Every time must be a multiple of dt within 1e-10,
+    else ``ValueError``."""
+    if dt is None:
+        dt_trotter = (time if np.isscalar(time) else time[1] - time[0]) / Trotter_number
+        dt, Trotter_number = dt_trotter, 1
+    else:
+        dt_trotter = dt / Trotter_number
+    times = [time] if np.isscalar(time) else list(time)
+    if not all(abs(t - np.round(t / dt) * dt) < 1e-10 for t in times):
+        raise ValueError('Entries in time are not multiples of dt_collisions.')
+    return dt, dt_trotter, Trotter_number, np.round(np.array(times) / dt).astype(int)

@@ -1,0 +1,107 @@
+"""Response-function evaluation on the device: the Feynman-pathway sum of ``qspectroscopy`` as a tree of
+batched evolutions.
+
+The reference (qspectroscopy.py:117-183) builds, for every delay-grid point, N**(order+1) site pathways x {1,2,3}
+X/Y circuits, each re-evolved from t = 0.  Because everything is linear in sigma = |ket><bra|:
+
+  * the sum over sites of one interaction is ONE collective operator  sum_s mu_s O_s  (``qsx_apply_dipole``);
+    O = X for the first interaction on a side, else |0><1| if (side == 'k') xor (direction == 'i'), else |1><0|
+    -- the coefficient rules mu, mu/2, +-i mu/2 of :144-174;  ket side: sigma -> O sigma, bra side: sigma -> sigma O;
+  * <X_kb> + i<Y_kb> of the ketbra ancilla (:90-91, :180-183) is the trace of the block after the emission
+    operator (a read-out of ``qsx_evolve``);
+  * chains that share a prefix along t1 -> t2 -> t3 are evolved once: level n evolves every instance produced by
+    level n-1 and snapshots it at each distinct step count of the n-th delay list.
+
+Independent chains are sharded over ranks at the first level that has enough of them; one all-gather assembles
+the signal.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import dist as qdist
+from .program import StepProgram
+from .sectors import Block
+
+
+def interaction_plan(side_seq: str, direction_seq: str):
+    """[(side, kind)] with kind in {'X', 'lower', 'raise'}; the last entry is the emission."""
+    first = {'k': True, 'b': True}
+    plan = []
+    n_int = len(side_seq)
+    for n, (side, direction) in enumerate(zip(side_seq, direction_seq)):
+        if first[side]:
+            kind = 'X'
+            first[side] = False
+        elif n == n_int - 1:
+            kind = 'X'
+        elif (side == 'k') ^ (direction == 'i'):
+            kind = 'lower'
+        else:
+            kind = 'raise'
+        plan.append((side, kind))
+    return plan
+
+
+def response_function(program: StepProgram, mu, side_seq: str, direction_seq: str, step_counts, engine=None):
+    """Signal over the delay grid.  ``step_counts``: one integer list per delay (any order, duplicates allowed).
+    Returns a complex ndarray of shape [len(c) for c in step_counts], identical on every rank."""
+    from .runtime import get_engine
+    eng = engine or get_engine()
+    n_sites = program.n_sites
+    plan = interaction_plan(side_seq, direction_seq)
+    if len(plan) != len(step_counts) + 1:
+        raise ValueError('side_seq must have one more entry than delay_time')
+    shape = [len(c) for c in step_counts]
+    uniq, inverse = [], []
+    for c in step_counts:
+        u, inv = np.unique(np.asarray(c, dtype=np.int64), return_inverse=True)
+        uniq.append(u.astype(np.int32))
+        inverse.append(inv)
+    mu_dev = eng.to_device(np.asarray(mu, dtype=np.float64), torch.float64)
+    rank, size = qdist.world()
+
+    ka = kb = 0
+    block = program.block(0, 0)
+    sigma = torch.zeros((1, block.size), dtype=torch.complex128, device=eng.device)
+    sigma[0, 0] = 1.0                                   # |g><g|, pseudomodes and ancilla in |0>
+    n_global = 1                                        # instances across all ranks at the current level
+    shard_units, rows_per_unit = 0, 1                   # units split over ranks, and rows each has grown into
+    sharded = False
+    zero = False
+    out = None
+    for level, (side, kind) in enumerate(plan[:-1]):
+        # ket side: |1><0| sigma raises the ket sector; bra side: sigma |0><1| raises the bra sector
+        delta = +1 if kind == 'X' or (kind == 'raise') == (side == 'k') else -1
+        nka, nkb = (ka + delta, kb) if side == 'k' else (ka, kb + delta)
+        new_block = Block(n_sites, program.n_bits, nka, nkb)
+        if not new_block.valid():
+            zero = True
+            break
+        if not sharded and size > 1 and n_global >= size:
+            lo, hi = qdist.shard_bounds(n_global, rank, size)
+            sigma = sigma[lo:hi].contiguous()
+            sharded, shard_units = True, n_global
+        sigma = eng.apply_dipole(block, new_block, 0 if side == 'k' else 1, mu_dev, sigma)
+        block, ka, kb = new_block, nka, nkb
+        dev = eng.upload_program(program.bind(block))
+        n_local = sigma.shape[0]
+        emit = uniq[level]
+        if level < len(plan) - 2:
+            _, snap = eng.evolve(dev, sigma, n_local, int(emit.max()), emit, snapshots=True)
+            sigma = snap.reshape(n_local * len(emit), block.size)
+        else:
+            obs = eng.upload_observables(*block.emission_observable(np.asarray(mu, dtype=float)))
+            out, _ = eng.evolve(dev, sigma, n_local, int(emit.max()), emit, obs=obs)
+            out = out.reshape(n_local, len(emit))
+        n_global *= len(emit)
+        if sharded and level < len(plan) - 2:
+            rows_per_unit *= len(emit)
+
+    if zero:
+        return np.zeros(shape, dtype=complex)
+    if sharded:
+        out = qdist.all_gather_rows(out, shard_units, rows_per_unit)
+    table = out.cpu().numpy().reshape([len(u) for u in uniq])
+    return table[np.ix_(*inverse)].reshape(shape)

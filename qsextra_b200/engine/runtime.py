@@ -1,0 +1,150 @@
+"""Device-side runtime: PyTorch owns memory and streams, ``libqsx.so`` does the arithmetic.
+
+``Engine`` keeps the small per-block tables on the device and turns host-side programs
+(``program.BoundProgram``) into ``qsx_evolve`` / ``qsx_apply_dipole`` calls on the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import cabi
+from .program import BoundProgram
+from .sectors import Block, sector_rank
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class DeviceBlock:
+    """Sector tables of one block resident on the device."""
+
+    def __init__(self, block: Block, device):
+        self.block = block
+        self.cfg_a = torch.tensor(block.cfg_a, dtype=torch.int32, device=device)
+        self.cfg_b = torch.tensor(block.cfg_b, dtype=torch.int32, device=device)
+        self.rank_a = torch.from_numpy(sector_rank(block.n_sites, block.ka).copy()).to(device)
+        self.rank_b = torch.from_numpy(sector_rank(block.n_sites, block.kb).copy()).to(device)
+        self.c = cabi.QsxBlock(block.n_sites, block.n_bits, block.n_a, block.n_b,
+                               self.cfg_a.data_ptr(), self.cfg_b.data_ptr(),
+                               self.rank_a.data_ptr(), self.rank_b.data_ptr())
+
+
+class Engine:
+    """One engine per process/GPU.  Raises when CUDA or the extension is unavailable (no CPU path)."""
+
+    def __init__(self, device=None):
+        self.lib = cabi.load()
+        if not torch.cuda.is_available():
+            raise cabi.QsxError('no CUDA device: the qsextra_b200 engine has no CPU fallback')
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self._blocks: dict[Block, DeviceBlock] = {}
+        self.launches = 0                     # kernels enqueued through this engine (bench bookkeeping)
+        with torch.cuda.device(self.device):
+            sm, smem, cc = C.c_int32(), C.c_int32(), C.c_int32()
+            cabi.check(self.lib.qsx_device_info(C.byref(sm), C.byref(smem), C.byref(cc)))
+        self.sm_count, self.smem_optin, self.cc = sm.value, smem.value, cc.value
+
+    # ---- helpers --------------------------------------------------------------------------
+    def device_block(self, block: Block) -> DeviceBlock:
+        db = self._blocks.get(block)
+        if db is None:
+            db = self._blocks[block] = DeviceBlock(block, self.device)
+        return db
+
+    def to_device(self, array, dtype=None):
+        t = torch.as_tensor(np.ascontiguousarray(array))
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.to(self.device, non_blocking=True)
+
+    def upload_program(self, bound: BoundProgram):
+        """-> dict of device tensors for a bound program (ops + parameter sets)."""
+        return dict(block=self.device_block(bound.block),
+                    ops=self.to_device(bound.ops, torch.int32),
+                    params=self.to_device(bound.params, torch.float64),
+                    n_ops=int(bound.ops.shape[0]), stride=int(bound.params.shape[1]),
+                    n_sets=int(bound.params.shape[0]))
+
+    def upload_observables(self, ptr, idx, w):
+        return dict(n=len(ptr) - 1, ptr=self.to_device(ptr, torch.int32), idx=self.to_device(idx, torch.int32),
+                    w=self.to_device(np.asarray(w, dtype=np.complex128)))
+
+    # ---- kernels ------------------------------------------------------------------------------
+    def evolve(self, prog: dict, sigma_in: torch.Tensor, n_inst: int, n_steps: int, emit_steps, obs: dict | None = None,
+               obs_real: bool = False, snapshots: bool = False, inst_set=None, inst_src=None, threads: int = 0):
+        """Run ``n_inst`` instances for ``n_steps`` steps.  Returns (out_obs | None, out_snap | None):
+        out_obs [n_inst, n_emit, n_obs] (float64 if obs_real else complex128), out_snap [n_inst, n_emit, E] complex128."""
+        blk: DeviceBlock = prog['block']
+        E = blk.block.size
+        emit = emit_steps if isinstance(emit_steps, torch.Tensor) else self.to_device(np.asarray(emit_steps), torch.int32)
+        n_emit = int(emit.numel())
+        assert sigma_in.dtype == torch.complex128 and sigma_in.is_contiguous() and sigma_in.numel() % E == 0
+        out_obs = out_snap = None
+        if obs is not None:
+            out_obs = torch.empty((n_inst, n_emit, obs['n']), dtype=torch.float64 if obs_real else torch.complex128,
+                                  device=self.device)
+        if snapshots:
+            out_snap = torch.empty((n_inst, n_emit, E), dtype=torch.complex128, device=self.device)
+        args = cabi.QsxEvolveArgs()
+        args.block = blk.c
+        args.n_ops, args.ops = prog['n_ops'], prog['ops'].data_ptr()
+        args.param_stride, args.params = prog['stride'], prog['params'].data_ptr()
+        args.n_inst = n_inst
+        args.inst_set = None if inst_set is None else inst_set.data_ptr()
+        args.inst_src = None if inst_src is None else inst_src.data_ptr()
+        args.sigma_in = sigma_in.data_ptr()
+        args.n_steps, args.n_emit, args.emit_steps = int(n_steps), n_emit, emit.data_ptr()
+        if obs is not None:
+            args.n_obs, args.obs_ptr, args.obs_idx, args.obs_w = obs['n'], obs['ptr'].data_ptr(), obs['idx'].data_ptr(), obs['w'].data_ptr()
+            args.out_obs = out_obs.data_ptr()
+        args.obs_real = int(obs_real)
+        args.out_snap = None if out_snap is None else out_snap.data_ptr()
+        args.threads = threads
+        with torch.cuda.device(self.device):
+            ws_bytes = self.lib.qsx_evolve_workspace_bytes(C.byref(args))
+            cabi.check(ws_bytes)
+            workspace = None
+            if ws_bytes > 0:
+                workspace = torch.empty(ws_bytes // 8, dtype=torch.float64, device=self.device)
+                args.workspace = workspace.data_ptr()
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            cabi.check(self.lib.qsx_evolve(C.byref(args), C.c_void_p(stream)))
+        if n_inst > 0 and n_emit > 0:
+            self.launches += 1
+        return out_obs, out_snap
+
+    def apply_dipole(self, in_block: Block, out_block: Block, side: int, mu: torch.Tensor, sigma_in: torch.Tensor):
+        """Collective dipole operator on a batch of blocks: [n, E_in] -> [n, E_out]."""
+        n_inst = sigma_in.numel() // in_block.size
+        out = torch.empty((n_inst, out_block.size), dtype=torch.complex128, device=self.device)
+        bi, bo = self.device_block(in_block), self.device_block(out_block)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            cabi.check(self.lib.qsx_apply_dipole(C.byref(bi.c), C.byref(bo.c), side, C.c_void_p(mu.data_ptr()), n_inst,
+                                                 C.c_void_p(sigma_in.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                 C.c_void_p(stream)))
+        if n_inst > 0:
+            self.launches += 1
+        return out
+
+    def fp64_peak(self, repeats: int = 5) -> float:
+        """Measured DFMA throughput of the CUDA cores (TFLOP/s) -- the FP64 roofline denominator."""
+        out = C.c_double()
+        with torch.cuda.device(self.device):
+            cabi.check(self.lib.qsx_fp64_peak(repeats, C.byref(out)))
+        return out.value
+
+
+_ENGINE = None
+
+
+def get_engine() -> Engine:
+    """Process-wide engine on the current CUDA device."""
+    global _ENGINE
+    if _ENGINE is None or _ENGINE.device.index != torch.cuda.current_device():
+        _ENGINE = Engine()
+    return _ENGINE

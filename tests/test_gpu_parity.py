@@ -1,0 +1,94 @@
+"""GPU parity: the CUDA path (through the public API and the C ABI) against the golden fixtures produced by the
+unmodified reference, and against the CPU oracle on seeded inputs.  Tolerance: 1e-10 relative (FP64), as
+BASELINE.json's north_star states."""
+import numpy as np
+import pytest
+
+from helpers import build_spectroscopy, build_system, golden_names, load_golden, time_arg
+from oracle import reference_path as R
+from qsextra_b200.qcomo import qevolve, qevolve_batch
+from qsextra_b200.spectroscopy import qspectroscopy
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def close(a, b, scale=None):
+    scale = max(1.0, np.abs(b).max()) if scale is None else scale
+    assert np.abs(np.asarray(a) - np.asarray(b)).max() <= RTOL * scale, np.abs(np.asarray(a) - np.asarray(b)).max()
+
+
+@pytest.mark.parametrize('name', golden_names('qevolve_'))
+def test_qevolve_matches_reference_golden(engine, name):
+    meta, arrays = load_golden(name)
+    system = build_system(meta['system'])
+    kw = dict(meta['kwargs'])
+    t = kw.pop('time')
+    res = qevolve(system, time_arg(t), shots=0, verbose=False, **kw)
+    close(res.distribution, arrays['distribution'])
+    n = system.system_size
+    pops = np.array([[arrays['distribution'][k][[(v >> i) & 1 == 1 for v in range(2 ** n)]].sum() for i in range(n)]
+                     for k in range(len(res.steps))])
+    close(res.populations, pops)
+
+
+@pytest.mark.parametrize('name', golden_names('qspectroscopy_'))
+def test_qspectroscopy_matches_reference_golden(engine, name):
+    meta, arrays = load_golden(name)
+    system = build_system(meta['system'])
+    spec = build_spectroscopy(meta['label'], meta['delay_time'])
+    signal = qspectroscopy(system, spec, shots=0, verbose=False, **dict(meta['kwargs']))
+    assert signal.shape == arrays['signal'].shape
+    close(signal, arrays['signal'], scale=max(1.0, np.abs(arrays['signal']).max()))
+
+
+def test_qevolve_shots_counts(engine):
+    meta, arrays = load_golden('qevolve_ex1_dephasing')
+    system = build_system(meta['system'])
+    kw = dict(meta['kwargs'])
+    t = kw.pop('time')
+    res = qevolve(system, t, shots=20000, verbose=False, **kw)
+    counts = res.get_counts()
+    assert len(counts) == len(t)
+    n = system.system_size
+    for c, p in zip(counts, arrays['distribution']):
+        assert sum(c.values()) == 20000
+        for i in range(n):
+            key = '{:b}'.format(1 << i).zfill(n)
+            assert abs(c.get(key, 0) / 20000 - p[1 << i]) < 5 * np.sqrt(max(p[1 << i] * (1 - p[1 << i]), 1e-4) / 20000)
+
+
+def test_batch_random_parameter_sets_vs_oracle(engine):
+    """C2-shaped workload at test size: non-Markovian dimers with one pseudomode per site, seeded parameters."""
+    from qsextra_b200 import ChromophoreSystem
+    rng = np.random.default_rng(0)
+    B, steps = 6, 40
+    dt = 0.1 / 0.658212
+    systems, rates = [], []
+    for _ in range(B):
+        gam, om = rng.uniform(0.02, 0.1), rng.uniform(0.05, 0.2)
+        s = ChromophoreSystem(energies=rng.uniform(1.4, 1.6, 2).tolist(), couplings=float(rng.uniform(-0.05, 0.05)),
+                              dipole_moments=[1., 1.], frequencies_pseudomode=float(rng.uniform(0.01, 0.2)),
+                              levels_pseudomode=2, couplings_ep=float(np.sqrt(gam * om / 2)))
+        s.set_state('localized excitation', 0)
+        systems.append(s)
+        rates.append([2 * om])
+    time = np.arange(steps + 1) * dt
+    pops = qevolve_batch(systems, time, dt=dt, coll_rates=np.array(rates))
+    assert pops.shape == (B, steps + 1, 2)
+    for b in range(B):
+        ref = R.qevolve_exact(systems[b], time, dt=dt, coll_rates=rates[b])
+        close(pops[b], ref['populations'])
+
+
+def test_trimer_two_excitons_vs_oracle(engine):
+    """ESA on a trimer with pseudomodes touches the two-exciton sector; compare with the operator-form oracle."""
+    from qsextra_b200 import ChromophoreSystem
+    from qsextra_b200.spectroscopy import FeynmanDiagram
+    s = ChromophoreSystem(energies=[1.55, 1.46, 1.50], couplings=[[0, -.01, .004], [-.01, 0, -.008], [.004, -.008, 0]],
+                          dipole_moments=[1., 0.7, -0.4], frequencies_pseudomode=0.02, levels_pseudomode=2,
+                          couplings_ep=0.054)
+    dt = 0.5
+    spec = FeynmanDiagram('esa', [[0., 2., 1.], [1., 0.], [0., 3., 3.]])
+    kw = dict(dt=dt, coll_rates=[0.2])
+    close(qspectroscopy(s, spec, verbose=False, **kw), R.qspectroscopy_operator(s, spec, **kw))
