@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the hot path on B200 (contract: see DESIGN.md "Measurement").
+
+Workload (BASELINE.json configs[1], "C2"): non-Markovian dimers, one 2-level pseudomode per site, 1000 collision
+steps, a batch of 4096 parameter sets PER GPU (weak scaling), populations written after every step
+([4096, 1001, 2] float64).  One bench "step" = one pass of the hot path over that batch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+metric = collision steps per second (whole job).  `value` is timed with CUDA events around the K launches with
+all inputs resident in HBM (L2 flushed between launches, outside the event pairs); `e2e` goes through the public
+API `qevolve_batch` from host arrays to a pinned host result.  `--impl reference` times the CPU oracle port
+(oracle/csrc/qsx_oracle.c, all host cores) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+HBAR = 0.658212
+DT = 0.1 / HBAR
+N_SETS = 4096
+N_STEPS = 1000
+METRIC = 'collision_steps_per_sec'
+UNIT = 'steps/s'
+
+
+def c2_parameters(n_sets, seed=0):
+    """eps~U(1.4,1.6), J~U(-.05,.05), omega~U(.01,.2), Gamma~U(.02,.1), Omega~U(.05,.2),
+    g = sqrt(Gamma Omega / 2), rate = 2 Omega."""
+    rng = np.random.default_rng(seed)
+    eps = rng.uniform(1.4, 1.6, (n_sets, 2))
+    J = rng.uniform(-0.05, 0.05, n_sets)
+    omega = rng.uniform(0.01, 0.2, n_sets)
+    Gamma = rng.uniform(0.02, 0.1, n_sets)
+    Omega = rng.uniform(0.05, 0.2, n_sets)
+    coup = np.zeros((n_sets, 2, 2))
+    coup[:, 0, 1] = coup[:, 1, 0] = J
+    return dict(energies=eps, couplings=coup, dipole_moments=np.ones((n_sets, 2)), omega=omega[:, None],
+                coupl_ep=np.sqrt(Gamma * Omega / 2)[:, None], rates=(2 * Omega)[:, None])
+
+
+def algorithmic_flops_per_step(n_sites=2, n_modes=1, stored_elements=64):
+    """F_step = E (6 n_Z + 12 n_R + 2.5 n_AD) for the d=2 pseudomode step, E = stored elements of
+    the block (1-exciton sector of the dimer: 8 x 8)."""
+    n_z = n_sites + n_sites * n_modes
+    n_r = 2 * (n_sites * (n_sites - 1) // 2) + 2 * n_sites * n_modes
+    n_ad = n_sites * n_modes
+    return stored_elements * (6 * n_z + 12 * n_r + 2.5 * n_ad)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port)
+# ------------------------------------------------------------------------------------------------
+def cpu_systems(params, lo, hi):
+    import warnings
+    from qsextra_b200 import ChromophoreSystem
+    out, rates = [], []
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for b in range(lo, hi):
+            s = ChromophoreSystem(energies=params['energies'][b].tolist(), couplings=float(params['couplings'][b, 0, 1]),
+                                  dipole_moments=[1., 1.], frequencies_pseudomode=float(params['omega'][b, 0]),
+                                  levels_pseudomode=2, couplings_ep=float(params['coupl_ep'][b, 0]))
+            s.set_state('localized excitation', 0)
+            out.append(s)
+            rates.append([float(params['rates'][b, 0])])
+    return out, np.array(rates)
+
+
+def cpu_sample(params, n_sample, n_steps=N_STEPS):
+    """Time the C oracle on the first n_sample parameter sets; -> (steps/s, threads, seconds)."""
+    from oracle import fast
+    systems, rates = cpu_systems(params, 0, n_sample)
+    time_grid = np.arange(n_steps + 1) * DT
+    fast.populations_batch(systems[:2], time_grid[:3], dt=DT, coll_rates=rates[:2])      # load + warm
+    t0 = time.perf_counter()
+    _, threads = fast.populations_batch(systems, time_grid, dt=DT, coll_rates=rates)
+    sec = time.perf_counter() - t0
+    return n_sample * n_steps / sec, threads, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    params = c2_parameters(N_SETS)
+    n_sample = 128
+    cpu_sample(params, 8, 50)
+    for _ in range(args.warmup):
+        cpu_sample(params, 16, 100)
+    t0 = time.perf_counter()
+    threads = 1
+    for _ in range(args.steps):
+        _, threads, _ = cpu_sample(params, n_sample)
+    sec = time.perf_counter() - t0
+    value = args.steps * n_sample * N_STEPS / sec
+    sample = '{} of {} parameter sets x {} steps per bench step (C oracle port, full-space literal gates, OpenMP)'.format(
+        n_sample, N_SETS, N_STEPS)
+    line = dict(impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * sec / args.steps, higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='f64', data='synthetic',
+                config=workload_config(args.gpus),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind='port', sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return dict(workload='C2: qcomo qevolve, non-Markovian dimer, 1 two-level pseudomode/site, {} collision steps, '
+                         '{} parameter sets per GPU, populations after every step'.format(N_STEPS, N_SETS),
+                parameter_sets_per_gpu=N_SETS, collision_steps=N_STEPS, global_parameter_sets=N_SETS * n_gpus,
+                sharding='parameter sets over ranks, no data-path collective',
+                cache='L2 flushed (256 MiB write) between timed launches, outside the event pairs')
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix='.csv')
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.QUERY,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.proc.wait()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for row in open(self.path):
+            f = [x.strip() for x in row.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, f[4:8]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        os.unlink(self.path)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from qsextra_b200.engine.program import StepProgram, SystemBatch
+    from qsextra_b200.engine.runtime import get_engine
+    from qsextra_b200.engine.sectors import population_observables
+    from qsextra_b200.qcomo import qevolve_batch
+
+    eng = get_engine()
+    params = c2_parameters(N_SETS * world)                      # global batch; this rank owns a contiguous slice
+    lo, hi = rank * N_SETS, (rank + 1) * N_SETS
+    batch = SystemBatch(params['energies'][lo:hi], params['couplings'][lo:hi], params['dipole_moments'][lo:hi],
+                        params['omega'][lo:hi], params['coupl_ep'][lo:hi], (2,))
+    program = StepProgram(batch, DT, 1, 1, params['rates'][lo:hi])
+    block = program.block(1, 1)
+    bound = program.bind(block)
+    dev = eng.upload_program(bound)
+    sigma0 = torch.zeros((1, block.size), dtype=torch.complex128, device=eng.device)
+    site0 = (0 << block.n_bits) * block.dim_b + (0 << block.n_bits)    # |cfg 0 (site 0 excited), modes 0>
+    sigma0[0, site0] = 1.0
+    inst_set = torch.arange(N_SETS, dtype=torch.int32, device=eng.device)
+    inst_src = torch.zeros(N_SETS, dtype=torch.int32, device=eng.device)
+    emit = eng.to_device(np.arange(N_STEPS + 1), torch.int32)
+    obs = eng.upload_observables(*population_observables(block))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
+
+    def hot_path():
+        return eng.evolve(dev, sigma0, N_SETS, N_STEPS, emit, obs=obs, obs_real=True, inst_set=inst_set,
+                          inst_src=inst_src)[0]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = None
+    for _ in range(max(args.warmup, 3)):
+        flush.fill_(1)
+        out = hot_path()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = eng.launches
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)
+        starts[i].record()
+        out = hot_path()
+        stops[i].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = eng.launches - launches0
+    clocks = sampler.stop()
+    kernel_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
+    t_dev = torch.tensor([sum(kernel_ms)], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    total_ms = float(t_dev.item())
+    steps_done = args.steps * N_SETS * N_STEPS * world
+    value = steps_done / (total_ms * 1e-3)
+
+    # parity spot-check of what was timed (rank 0, a few parameter sets, against the C oracle)
+    parity = None
+    if rank == 0:
+        from oracle import fast
+        systems, rates = cpu_systems(params, 0, 4)
+        ref, _ = fast.populations_batch(systems, np.arange(N_STEPS + 1) * DT, dt=DT, coll_rates=rates)
+        parity = float(np.abs(out[:4].cpu().numpy() - ref).max())
+
+    # ---- end to end through the public API: host arrays in, pinned host populations out ----------------------
+    pinned = torch.empty((N_SETS, N_STEPS + 1, 2), dtype=torch.float64).pin_memory()
+    host_batch = SystemBatch(np.array(batch.energies), np.array(batch.couplings), np.array(batch.dipole_moments),
+                             np.array(batch.omega), np.array(batch.coupl_ep), (2,))
+    time_grid = np.arange(N_STEPS + 1) * DT
+    world_was = world
+
+    def e2e_once():
+        # per-rank call on this rank's own parameter sets (no gather: weak scaling, independent units)
+        res = qevolve_batch(host_batch, time_grid, dt=DT, coll_rates=params['rates'][lo:hi], device_output=True,
+                            shard=False)
+        pinned.copy_(res, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_once()
+    h2d0 = eng.h2d_bytes
+    barrier()
+    t0 = time.perf_counter()
+    e2e_iters = max(1, min(args.steps, 5))
+    for _ in range(e2e_iters):
+        e2e_once()
+    barrier()
+    e2e_sec = time.perf_counter() - t0
+    h2d = (eng.h2d_bytes - h2d0) // e2e_iters
+    t_e2e = torch.tensor([e2e_sec], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_iters * N_SETS * N_STEPS * world_was / float(t_e2e.item())
+
+    if rank == 0:
+        fp64_peak = eng.fp64_peak(5)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
+        except OSError:
+            pass
+        f_step = algorithmic_flops_per_step(2, 1, block.size)
+        per_launch_flops = f_step * N_SETS * N_STEPS
+        per_launch_ms = float(np.mean(kernel_ms))
+        achieved = per_launch_flops / (per_launch_ms * 1e-3) / 1e12
+        out_bytes = N_SETS * (N_STEPS + 1) * 2 * 8
+        in_bytes = bound.params.nbytes + block.size * 16
+        hbm_peak = peaks.get('hbm_gbs', 6650.0)
+        cpu_value, cpu_threads, cpu_sec = cpu_sample(params, 128)
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=total_ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='f64', data='synthetic', config=workload_config(world),
+                    clocks=clocks, gpu_launches=launches,
+                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(pinned.numel() * 8),
+                             api='qsextra_b200.qcomo.qevolve_batch(SystemBatch of host arrays) -> pinned host tensor'),
+                    roofline=dict(bound='fp64', kernel='evolve_generic_kernel', achieved=achieved, peak=fp64_peak,
+                                  unit='TFLOP/s', frac=achieved / fp64_peak if fp64_peak else None, traffic=None,
+                                  peak_source='qsx_fp64_peak DFMA micro-benchmark measured in this run '
+                                              '(MEASURED_PEAKS.json has no FP64 figure)',
+                                  flops_per_collision_step=f_step, flops_per_launch=per_launch_flops,
+                                  kernel_ms_per_launch=per_launch_ms,
+                                  hbm=dict(achieved=(in_bytes + out_bytes) / (per_launch_ms * 1e-3) / 1e9, peak=hbm_peak,
+                                           unit='GB/s', algorithmic_bytes_per_launch=in_bytes + out_bytes,
+                                           peak_source='MEASURED_PEAKS.json' if peaks else 'fallback')),
+                    cpu_baseline=dict(value=cpu_value, unit=UNIT, cores=cpu_threads, kind='port',
+                                      sample='128 of 4096 parameter sets x 1000 steps, C oracle port '
+                                             '(full-space literal gates, OpenMP), %.1f s' % cpu_sec),
+                    parity_max_abs_err_vs_oracle=parity, wall_s_timed_region=wall)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -43,6 +43,7 @@ class Engine:
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self._blocks: dict[Block, DeviceBlock] = {}
         self.launches = 0                     # kernels enqueued through this engine (bench bookkeeping)
+        self.h2d_bytes = 0                    # bytes copied host -> device through to_device()
         with torch.cuda.device(self.device):
             sm, smem, cc = C.c_int32(), C.c_int32(), C.c_int32()
             cabi.check(self.lib.qsx_device_info(C.byref(sm), C.byref(smem), C.byref(cc)))
@@ -59,6 +60,7 @@ class Engine:
         t = torch.as_tensor(np.ascontiguousarray(array))
         if dtype is not None:
             t = t.to(dtype)
+        self.h2d_bytes += t.numel() * t.element_size()
         return t.to(self.device, non_blocking=True)
 
     def upload_program(self, bound: BoundProgram):

@@ -206,14 +206,15 @@ def qevolve(system: ChromophoreSystem | ExcitonicSystem,
 
 
 def qevolve_batch(systems, time, Trotter_number: int = 1, Trotter_order: int = 1, dt: float = None, coll_rates=None,
-                  initialize_circuit: bool = True, device_output: bool = False):
+                  initialize_circuit: bool = True, device_output: bool = False, shard: bool = True):
     """Population dynamics of MANY parameter sets in one launch (new API; the reference loops ``qevolve``).
 
     ``systems``: list of ExcitonicSystem / ChromophoreSystem with the same structure and state type, or a
     ``SystemBatch`` (then ``initial_state`` is site 0 excited unless ``systems.psi`` is set).
     ``coll_rates``: one value (list) for all, or an array with a leading batch axis.
     Returns populations [B, T, N] for the distinct requested times in ascending order.  Under
-    ``torch.distributed`` the parameter sets are sharded over the ranks and gathered with one collective.
+    ``torch.distributed`` (and ``shard=True``) the parameter sets are sharded over the ranks and gathered with one
+    collective; ``shard=False`` evolves the whole batch on the calling rank.
     """
     if isinstance(systems, SystemBatch):
         batch = systems
@@ -239,7 +240,7 @@ def qevolve_batch(systems, time, Trotter_number: int = 1, Trotter_order: int = 1
     dt, dt_trotter, Trotter_number, counts = resolve_time_grid(time, dt, Trotter_number)
     steps = sorted(set(int(c) for c in counts))
 
-    rank, size = qdist.world()
+    rank, size = qdist.world() if shard else (0, 1)
     lo, hi = qdist.shard_bounds(B, rank, size)
     sub = SystemBatch(batch.energies[lo:hi], batch.couplings[lo:hi], batch.dipole_moments[lo:hi],
                       None if batch.omega is None else batch.omega[lo:hi],
@@ -247,5 +248,5 @@ def qevolve_batch(systems, time, Trotter_number: int = 1, Trotter_order: int = 1
     program = StepProgram(sub, dt, Trotter_number, Trotter_order, None if rates is None else rates[lo:hi],
                           dt_trotter=dt_trotter)
     local = run_populations(sub, psi[lo:hi], program, steps, readout='populations', device_output=True)
-    full = qdist.all_gather_rows(local, B)
+    full = qdist.all_gather_rows(local, B) if size > 1 else local
     return full if device_output else full.cpu().numpy()
