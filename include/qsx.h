@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define QSX_ABI_VERSION 1
+#define QSX_ABI_VERSION 2
 
 enum {
     QSX_OK = 0,
@@ -55,9 +55,7 @@ enum {
      *   (2-level pseudomode collision + reset, qevolve.py:334-347) */
     QSX_OP_AD = 3,
     /* trace out bit i0 and replace it by |0>  (reset, qevolve.py:347) */
-    QSX_OP_RESET = 4,
-    /* fused step of the standard 2-level-pseudomode / Markovian program: reserved */
-    QSX_OP_FUSED = 5
+    QSX_OP_RESET = 4
 };
 
 typedef struct qsx_op {
@@ -66,6 +64,28 @@ typedef struct qsx_op {
     int32_t p;          /* slot (in doubles) into the parameter-set table */
     int32_t reserved;
 } qsx_op;
+
+/* Fused passes.  A pass program is an equivalent regrouping of the step's operations into sweeps over sigma in
+ * which every thread keeps a small tile in registers and applies several operations to it ("passes"):
+ *
+ *  QSX_PASS_CFG   tile = all (cfgA, cfgB) pairs at fixed bits.  f = {tile_off, n_tiles, nA, nB, slot GA, slot GB,
+ *                 slot T_pre, slot T_post, hop_begin, hop_end}; slots are -1 when absent.  Order inside the pass:
+ *                 sigma *= GA conj(GB) T_pre;  hops [hop_begin, hop_end) of `hops`;  sigma *= T_post.
+ *                 tiles[2*t] = element offset of the tile, tiles[2*t+1] = bits_a | bits_b << 16.
+ *                 hops[4*h] = {side (0 ket, 1 bra), p, q, param slot {cos 2th, sin 2th}}: rotate configurations p, q.
+ *  QSX_PASS_MODE  tile = KB (1 or 2) pseudomode bits on both sides.  f = {tile_off, n_tiles, KB, bit0, bit1,
+ *                 rot slot0, rot slot1, damp slot0, damp slot1, skip flags}.  Per bit: X-rotation conditioned on the
+ *                 occupation of the bit's site (QSX_OP_PROT with a one-bit xmask, no zmask), then amplitude damping.
+ *                 tiles[2*t] = element offset, tiles[2*t+1] = occupation flags
+ *                 (bit0: site(bit0) in cfgA, bit1: in cfgB, bit2: site(bit1) in cfgA, bit3: in cfgB).
+ *  QSX_PASS_OP    f = {index into `ops`}: the operation is applied by the generic sweep.
+ */
+enum { QSX_PASS_CFG = 0, QSX_PASS_MODE = 1, QSX_PASS_OP = 2 };
+
+typedef struct qsx_pass {
+    int32_t type;
+    int32_t f[11];
+} qsx_pass;
 
 /* Geometry of one ket x bra sector block. */
 typedef struct qsx_block {
@@ -101,7 +121,13 @@ typedef struct qsx_evolve_args {
     int32_t obs_real;
     double* out_snap;           /* DEVICE [n_inst][n_emit][DA*DB] complex128 snapshots, or NULL */
     double* workspace;          /* DEVICE scratch of qsx_evolve_workspace_bytes() bytes, or NULL */
-    int32_t threads;            /* threads per instance (0 = library default) */
+    int32_t threads;            /* threads per instance (0 = library default); a power of two */
+    int32_t n_passes;           /* 0: apply `ops` one by one; > 0: run the pass program below (same result) */
+    const qsx_pass* passes;     /* DEVICE [n_passes] */
+    int32_t n_tile_ints;        /* length of `tiles` in int32 */
+    const int32_t* tiles;       /* DEVICE tile tables of all passes */
+    int32_t n_hop_ints;         /* length of `hops` in int32 */
+    const int32_t* hops;        /* DEVICE hop entries of all QSX_PASS_CFG passes (p < q) */
 } qsx_evolve_args;
 
 int32_t qsx_abi_version(void);

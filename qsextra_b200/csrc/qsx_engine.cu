@@ -1,9 +1,13 @@
 // qsx_engine.cu -- sm_100a kernels + C ABI (include/qsx.h) of the collision-model / Feynman-pathway engine.
 //
-// Generic path ("interpreter"): one CTA owns one instance.  The ket x bra block sigma lives in shared memory
-// (global scratch when it does not fit), the step program is a list of qsx_op applied in order, each op as a
-// ket-side pass (G sigma) followed by a bra-side pass (sigma G^dagger) or as one joint pass for channels.
-// HBM is touched only when an instance is loaded and when it emits read-outs or snapshots.
+// One TEAM of threads owns one instance: the ket x bra block sigma (complex128) stays in shared memory for the
+// whole evolution (global scratch only when it cannot fit) and HBM is touched when the instance is loaded and when
+// it emits read-outs or snapshots.  Small blocks use sub-warp teams (several instances per warp, __syncwarp only);
+// large blocks use one CTA per instance.  A step is either
+//   * a PASS PROGRAM (qsx_pass): sweeps in which every thread keeps a tile of sigma in registers and applies all
+//     operations that act inside the tile -- the configuration tile (diagonal phases, all exciton hops of both
+//     sides, dephasing) and the pseudomode tile (conditioned X-rotations of both sides + amplitude damping); or
+//   * the plain operation list (qsx_op), one sweep per operation and side (generic fallback, any program).
 //
 // Reference semantics: qsextra/qcomo/evolution/qevolve.py:74-348 (gates), :417-427 (step loop);
 // qsextra/spectroscopy/simulation/qspectroscopy.py:65-80, :142-183 (dipoles, read-out).
@@ -51,81 +55,115 @@ __device__ __forceinline__ double2 mul_ipow(double2 v, int k) {
         default: return make_double2(v.y, -v.x);
     }
 }
+// [x; y] -> [[c, -i s], [-i s, c]] [x; y]  (sgn = +1)   or its conjugate (sgn = -1)
+__device__ __forceinline__ void rot_pair(double2& x, double2& y, double c, double s_signed) {
+    // new_x = c x - i s y ; new_y = c y - i s x   with s_signed = s (ket) or -s (bra)
+    double2 nx = make_double2(fma(c, x.x, s_signed * y.y), fma(c, x.y, -s_signed * y.x));
+    double2 ny = make_double2(fma(c, y.x, s_signed * x.y), fma(c, y.y, -s_signed * x.x));
+    x = nx;
+    y = ny;
+}
 
 struct EvolveParams {
     qsx_evolve_args a;
     int32_t DA, DB, E;
     int32_t use_workspace;
+    int32_t team;            // threads per instance
+    int32_t inst_per_cta;
+    int32_t inst_stride;     // bytes of shared memory per instance (sigma + params)
+    int32_t n_tile_ints, n_hop_ints;
+};
+
+// A team: `n` threads (a power of two) that own one instance.  Sub-warp teams synchronise with __syncwarp
+// (all teams of a warp run the same program in lock-step), CTA teams with __syncthreads.
+template <bool WARP>
+struct Team {
+    int tid, n;
+    unsigned mask;
+    __device__ __forceinline__ void sync() const {
+        if (WARP) __syncwarp(mask);
+        else __syncthreads();
+    }
+};
+
+struct Tables {
+    const qsx_op* ops;
+    const qsx_pass* passes;
+    const int* tiles;
+    const int* hops;
+    const int *cfgA, *cfgB, *rankA, *rankB;
 };
 
 // ------------------------------------------------------------------------------------------------
-// per-op passes; s = sigma (shared or global), P = this instance's parameter set (shared)
+// generic sweeps: one operation at a time (any program)
 // ------------------------------------------------------------------------------------------------
-__device__ void pass_diag(double2* s, const EvolveParams& k, const qsx_op& op, const double* P) {
+template <bool W>
+__device__ void sweep_diag(double2* s, const EvolveParams& k, const qsx_op& op, const double* P, const Team<W>& t) {
     const double2* GA = reinterpret_cast<const double2*>(P + op.i0);
     const double2* GB = reinterpret_cast<const double2*>(P + op.i1);
     const double* T = op.i2 >= 0 ? P + op.i2 : nullptr;
     const int nb = k.a.block.n_bits, nB = k.a.block.nB, DB = k.DB;
-    for (int e = threadIdx.x; e < k.E; e += blockDim.x) {
+    for (int e = t.tid; e < k.E; e += t.n) {
         int a = e / DB, b = e - a * DB;
         double2 w = cmul_conj(GA[a], GB[b]);
         if (T) {
-            double t = T[(a >> nb) * nB + (b >> nb)];
-            w.x *= t;
-            w.y *= t;
+            double tt = T[(a >> nb) * nB + (b >> nb)];
+            w.x *= tt;
+            w.y *= tt;
         }
         s[e] = cmul(s[e], w);
     }
-    __syncthreads();
+    t.sync();
 }
 
-__device__ void pass_hop(double2* s, const EvolveParams& k, const qsx_op& op, const double* P,
-                         const int* cfgA, const int* cfgB, const int* rankA, const int* rankB) {
+template <bool W>
+__device__ void sweep_hop(double2* s, const EvolveParams& k, const qsx_op& op, const double* P, const Tables& tb,
+                          const Team<W>& t) {
     const double c = P[op.p], sn = P[op.p + 1];
-    const int nb = k.a.block.n_bits, DB = k.DB, DA = k.DA;
+    const int nb = k.a.block.n_bits, DB = k.DB;
     const int flip = (1 << op.i0) | (1 << op.i1);
     const int bitsmask = (1 << nb) - 1;
-    // ket side: [x;y] -> [[c,-is],[-is,c]] [x;y]
-    for (int e = threadIdx.x; e < k.E; e += blockDim.x) {
+    for (int e = t.tid; e < k.E; e += t.n) {            // ket side
         int a = e / DB, b = e - a * DB;
-        int cfg = cfgA[a >> nb];
+        int cfg = tb.cfgA[a >> nb];
         if (((cfg >> op.i0) & 1) && !((cfg >> op.i1) & 1)) {
-            int a2 = (rankA[cfg ^ flip] << nb) | (a & bitsmask);
+            int a2 = (tb.rankA[cfg ^ flip] << nb) | (a & bitsmask);
             int e2 = a2 * DB + b;
             double2 x = s[e], y = s[e2];
-            s[e] = axpby(c, x, 0.0, -sn, y);
-            s[e2] = axpby(c, y, 0.0, -sn, x);
+            rot_pair(x, y, c, sn);
+            s[e] = x;
+            s[e2] = y;
         }
     }
-    __syncthreads();
-    // bra side: conj
-    for (int e = threadIdx.x; e < k.E; e += blockDim.x) {
+    t.sync();
+    for (int e = t.tid; e < k.E; e += t.n) {            // bra side (conjugate)
         int a = e / DB, b = e - a * DB;
-        int cfg = cfgB[b >> nb];
+        int cfg = tb.cfgB[b >> nb];
         if (((cfg >> op.i0) & 1) && !((cfg >> op.i1) & 1)) {
-            int b2 = (rankB[cfg ^ flip] << nb) | (b & bitsmask);
+            int b2 = (tb.rankB[cfg ^ flip] << nb) | (b & bitsmask);
             int e2 = a * DB + b2;
             double2 x = s[e], y = s[e2];
-            s[e] = axpby(c, x, 0.0, sn, y);
-            s[e2] = axpby(c, y, 0.0, sn, x);
+            rot_pair(x, y, c, -sn);
+            s[e] = x;
+            s[e2] = y;
         }
     }
-    __syncthreads();
-    (void)DA;
+    t.sync();
 }
 
-__device__ void pass_prot(double2* s, const EvolveParams& k, const qsx_op& op, const double* P,
-                          const int* cfgA, const int* cfgB) {
+template <bool W>
+__device__ void sweep_prot(double2* s, const EvolveParams& k, const qsx_op& op, const double* P, const Tables& tb,
+                           const Team<W>& t) {
     const int xm = op.i0, zm = op.i1, site = op.i3, skip0 = op.i4;
     const int pivot = xm & -xm;
     const int nb = k.a.block.n_bits, DB = k.DB;
     const int upow = (op.i2 + 3) & 3;                 // -i * i^nY = i^(nY+3)
     const double c0 = P[op.p], s0 = P[op.p + 1], c1 = P[op.p + 2], s1 = P[op.p + 3];
     // ket side: new_a = c sig_a + (-i s) P[a,a2] sig_a2,  P[a,a2] = i^nY (-1)^{|a2 & z|}
-    for (int e = threadIdx.x; e < k.E; e += blockDim.x) {
+    for (int e = t.tid; e < k.E; e += t.n) {
         int a = e / DB, b = e - a * DB;
         if (a & pivot) continue;
-        int occ = site >= 0 ? (cfgA[a >> nb] >> site) & 1 : 0;
+        int occ = site >= 0 ? (tb.cfgA[a >> nb] >> site) & 1 : 0;
         if (skip0 && !occ) continue;
         double c = occ ? c1 : c0, sn = occ ? s1 : s0;
         int a2 = a ^ xm, e2 = a2 * DB + b;
@@ -136,13 +174,13 @@ __device__ void pass_prot(double2* s, const EvolveParams& k, const qsx_op& op, c
         s[e] = make_double2(fma(c, x.x, sg_a2 * uy.x), fma(c, x.y, sg_a2 * uy.y));
         s[e2] = make_double2(fma(c, y.x, sg_a * ux.x), fma(c, y.y, sg_a * ux.y));
     }
-    __syncthreads();
+    t.sync();
     // bra side: new_b = c sig_b + conj(-i s P[b,b2]) sig_b2
     const int upow_c = (4 - upow) & 3;
-    for (int e = threadIdx.x; e < k.E; e += blockDim.x) {
+    for (int e = t.tid; e < k.E; e += t.n) {
         int a = e / DB, b = e - a * DB;
         if (b & pivot) continue;
-        int occ = site >= 0 ? (cfgB[b >> nb] >> site) & 1 : 0;
+        int occ = site >= 0 ? (tb.cfgB[b >> nb] >> site) & 1 : 0;
         if (skip0 && !occ) continue;
         double c = occ ? c1 : c0, sn = occ ? s1 : s0;
         int b2 = b ^ xm, e2 = a * DB + b2;
@@ -153,15 +191,16 @@ __device__ void pass_prot(double2* s, const EvolveParams& k, const qsx_op& op, c
         s[e] = make_double2(fma(c, x.x, sg_b2 * uy.x), fma(c, x.y, sg_b2 * uy.y));
         s[e2] = make_double2(fma(c, y.x, sg_b * ux.x), fma(c, y.y, sg_b * ux.y));
     }
-    __syncthreads();
+    t.sync();
 }
 
-__device__ void pass_ad_or_reset(double2* s, const EvolveParams& k, const qsx_op& op, const double* P) {
+template <bool W>
+__device__ void sweep_ad_or_reset(double2* s, const EvolveParams& k, const qsx_op& op, const double* P, const Team<W>& t) {
     const int m = 1 << op.i0, DB = k.DB;
     const bool reset = op.type == QSX_OP_RESET;
     const double c = reset ? 0.0 : P[op.p], s2 = reset ? 1.0 : P[op.p + 1];
     const double cc = c * c;
-    for (int e = threadIdx.x; e < k.E; e += blockDim.x) {
+    for (int e = t.tid; e < k.E; e += t.n) {
         int a = e / DB, b = e - a * DB;
         if ((a & m) || (b & m)) continue;
         int e01 = e + m, e10 = e + m * DB, e11 = e10 + m;
@@ -171,97 +210,376 @@ __device__ void pass_ad_or_reset(double2* s, const EvolveParams& k, const qsx_op
         s[e10] = make_double2(c * v10.x, c * v10.y);
         s[e11] = make_double2(cc * v11.x, cc * v11.y);
     }
-    __syncthreads();
+    t.sync();
 }
 
-__device__ void emit(const double2* s, const EvolveParams& k, int inst, int slot) {
+template <bool W>
+__device__ void sweep_op(double2* s, const EvolveParams& k, const qsx_op& op, const double* P, const Tables& tb,
+                         const Team<W>& t) {
+    switch (op.type) {
+        case QSX_OP_DIAG: sweep_diag(s, k, op, P, t); break;
+        case QSX_OP_HOP: sweep_hop(s, k, op, P, tb, t); break;
+        case QSX_OP_PROT: sweep_prot(s, k, op, P, tb, t); break;
+        case QSX_OP_AD:
+        case QSX_OP_RESET: sweep_ad_or_reset(s, k, op, P, t); break;
+        default: break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused passes
+// ------------------------------------------------------------------------------------------------
+// Configuration tile: v[i][j] = sigma[(i, bits_a), (j, bits_b)], i < TA, j < TB, all register indices static.
+template <int TA, int TB, bool W>
+__device__ void pass_cfg(double2* s, const EvolveParams& k, const qsx_pass& ps, const double* P, const Tables& tb,
+                         const Team<W>& t) {
+    const int nb = k.a.block.n_bits;
+    const int strideB = 1 << nb, strideA = strideB * k.DB;
+    const int* tiles = tb.tiles + ps.f[0];
+    const int n_tiles = ps.f[1];
+    const double2* GA = ps.f[4] >= 0 ? reinterpret_cast<const double2*>(P + ps.f[4]) : nullptr;
+    const double2* GB = ps.f[5] >= 0 ? reinterpret_cast<const double2*>(P + ps.f[5]) : nullptr;
+    const double* Tpre = ps.f[6] >= 0 ? P + ps.f[6] : nullptr;
+    const double* Tpost = ps.f[7] >= 0 ? P + ps.f[7] : nullptr;
+    const int h0 = ps.f[8], h1 = ps.f[9];
+    for (int ti = t.tid; ti < n_tiles; ti += t.n) {
+        const int base = tiles[2 * ti], mm = tiles[2 * ti + 1];
+        const int ma = mm & 0xffff, mb = mm >> 16;
+        double2 v[TA][TB];
+#pragma unroll
+        for (int i = 0; i < TA; ++i)
+#pragma unroll
+            for (int j = 0; j < TB; ++j) v[i][j] = s[base + i * strideA + j * strideB];
+        if (GA) {
+            double2 ga[TA], gb[TB];
+#pragma unroll
+            for (int i = 0; i < TA; ++i) ga[i] = GA[(i << nb) | ma];
+#pragma unroll
+            for (int j = 0; j < TB; ++j) gb[j] = GB[(j << nb) | mb];
+#pragma unroll
+            for (int i = 0; i < TA; ++i)
+#pragma unroll
+                for (int j = 0; j < TB; ++j) {
+                    double2 w = cmul_conj(ga[i], gb[j]);
+                    if (Tpre) {
+                        double tt = Tpre[i * TB + j];
+                        w.x *= tt;
+                        w.y *= tt;
+                    }
+                    v[i][j] = cmul(v[i][j], w);
+                }
+        }
+        for (int h = h0; h < h1; ++h) {
+            const int side = tb.hops[4 * h], p = tb.hops[4 * h + 1], q = tb.hops[4 * h + 2], slot = tb.hops[4 * h + 3];
+            const double c = P[slot], sn = P[slot + 1];
+            if (side == 0) {
+#pragma unroll
+                for (int pp = 0; pp < TA; ++pp)
+#pragma unroll
+                    for (int qq = pp + 1; qq < TA; ++qq)
+                        if (p == pp && q == qq) {
+#pragma unroll
+                            for (int j = 0; j < TB; ++j) rot_pair(v[pp][j], v[qq][j], c, sn);
+                        }
+            } else {
+#pragma unroll
+                for (int pp = 0; pp < TB; ++pp)
+#pragma unroll
+                    for (int qq = pp + 1; qq < TB; ++qq)
+                        if (p == pp && q == qq) {
+#pragma unroll
+                            for (int i = 0; i < TA; ++i) rot_pair(v[i][pp], v[i][qq], c, -sn);
+                        }
+            }
+        }
+        if (Tpost) {
+#pragma unroll
+            for (int i = 0; i < TA; ++i)
+#pragma unroll
+                for (int j = 0; j < TB; ++j) {
+                    double tt = Tpost[i * TB + j];
+                    v[i][j].x *= tt;
+                    v[i][j].y *= tt;
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < TA; ++i)
+#pragma unroll
+            for (int j = 0; j < TB; ++j) s[base + i * strideA + j * strideB] = v[i][j];
+    }
+    t.sync();
+}
+
+// Kernel shape classes keep the register budget of small blocks small: CLS 0: nA, nB <= 2; 1: <= 4; 2: up to 6 x 4.
+template <bool W, int CLS>
+__device__ void pass_cfg_dispatch(double2* s, const EvolveParams& k, const qsx_pass& ps, const double* P,
+                                  const Tables& tb, const Team<W>& t) {
+    const int code = ps.f[2] * 8 + ps.f[3];
+#define QSX_CFG_CASE(A, B) case (A) * 8 + (B): pass_cfg<A, B, W>(s, k, ps, P, tb, t); break;
+    if (CLS == 0) {
+        switch (code) {
+            QSX_CFG_CASE(1, 1) QSX_CFG_CASE(1, 2) QSX_CFG_CASE(2, 1) QSX_CFG_CASE(2, 2)
+            default: break;
+        }
+    } else if (CLS == 1) {
+        switch (code) {
+            QSX_CFG_CASE(1, 1) QSX_CFG_CASE(1, 2) QSX_CFG_CASE(2, 1) QSX_CFG_CASE(2, 2)
+            QSX_CFG_CASE(1, 3) QSX_CFG_CASE(3, 1) QSX_CFG_CASE(3, 3) QSX_CFG_CASE(2, 3) QSX_CFG_CASE(3, 2)
+            QSX_CFG_CASE(1, 4) QSX_CFG_CASE(4, 1) QSX_CFG_CASE(4, 4)
+            default: break;
+        }
+    } else {
+        switch (code) {
+            QSX_CFG_CASE(4, 6) QSX_CFG_CASE(6, 4) QSX_CFG_CASE(1, 6) QSX_CFG_CASE(6, 1)
+            default: break;
+        }
+    }
+#undef QSX_CFG_CASE
+}
+
+// Pseudomode tile: KB bits on both sides; v[ia][ib], ia/ib = values of the tile's bits on the ket/bra side.
+template <int KB, bool W>
+__device__ void pass_mode(double2* s, const EvolveParams& k, const qsx_pass& ps, const double* P, const Tables& tb,
+                          const Team<W>& t) {
+    constexpr int TS = 1 << KB;
+    const int* tiles = tb.tiles + ps.f[0];
+    const int n_tiles = ps.f[1];
+    int off[TS];
+#pragma unroll
+    for (int i = 0; i < TS; ++i) {
+        int o = 0;
+#pragma unroll
+        for (int b = 0; b < KB; ++b)
+            if ((i >> b) & 1) o |= 1 << ps.f[3 + b];
+        off[i] = o;
+    }
+    double rc0[KB], rs0[KB], rc1[KB], rs1[KB], dc[KB], ds[KB];
+    bool has_rot[KB], has_ad[KB], skip0[KB];
+#pragma unroll
+    for (int b = 0; b < KB; ++b) {
+        has_rot[b] = ps.f[5 + b] >= 0;
+        has_ad[b] = ps.f[7 + b] >= 0;
+        skip0[b] = (ps.f[9] >> b) & 1;
+        if (has_rot[b]) {
+            const double* r = P + ps.f[5 + b];
+            rc0[b] = r[0]; rs0[b] = r[1]; rc1[b] = r[2]; rs1[b] = r[3];
+        }
+        if (has_ad[b]) {
+            dc[b] = P[ps.f[7 + b]];
+            ds[b] = P[ps.f[7 + b] + 1];
+        }
+    }
+    for (int ti = t.tid; ti < n_tiles; ti += t.n) {
+        const int base = tiles[2 * ti], flags = tiles[2 * ti + 1];
+        double2 v[TS][TS];
+#pragma unroll
+        for (int ia = 0; ia < TS; ++ia)
+#pragma unroll
+            for (int ib = 0; ib < TS; ++ib) v[ia][ib] = s[base + off[ia] * k.DB + off[ib]];
+#pragma unroll
+        for (int b = 0; b < KB; ++b) {
+            if (has_rot[b]) {
+                const int occ_a = (flags >> (2 * b)) & 1, occ_b = (flags >> (2 * b + 1)) & 1;
+                if (occ_a || !skip0[b]) {                       // ket side: X-rotation of bit b
+                    const double c = occ_a ? rc1[b] : rc0[b], sn = occ_a ? rs1[b] : rs0[b];
+#pragma unroll
+                    for (int ia = 0; ia < TS; ++ia)
+                        if (!((ia >> b) & 1)) {
+#pragma unroll
+                            for (int ib = 0; ib < TS; ++ib) rot_pair(v[ia][ib], v[ia | (1 << b)][ib], c, sn);
+                        }
+                }
+                if (occ_b || !skip0[b]) {                       // bra side (conjugate)
+                    const double c = occ_b ? rc1[b] : rc0[b], sn = occ_b ? rs1[b] : rs0[b];
+#pragma unroll
+                    for (int ib = 0; ib < TS; ++ib)
+                        if (!((ib >> b) & 1)) {
+#pragma unroll
+                            for (int ia = 0; ia < TS; ++ia) rot_pair(v[ia][ib], v[ia][ib | (1 << b)], c, -sn);
+                        }
+                }
+            }
+            if (has_ad[b]) {
+                const double c = dc[b], s2 = ds[b], cc = c * c;
+#pragma unroll
+                for (int ia = 0; ia < TS; ++ia)
+#pragma unroll
+                    for (int ib = 0; ib < TS; ++ib) {
+                        const int ha = (ia >> b) & 1, hb = (ib >> b) & 1;
+                        if (!ha && !hb) {
+                            double2 hi = v[ia | (1 << b)][ib | (1 << b)];
+                            v[ia][ib].x = fma(s2, hi.x, v[ia][ib].x);
+                            v[ia][ib].y = fma(s2, hi.y, v[ia][ib].y);
+                        }
+                    }
+#pragma unroll
+                for (int ia = 0; ia < TS; ++ia)
+#pragma unroll
+                    for (int ib = 0; ib < TS; ++ib) {
+                        const int ha = (ia >> b) & 1, hb = (ib >> b) & 1;
+                        if (ha != hb) {
+                            v[ia][ib].x *= c;
+                            v[ia][ib].y *= c;
+                        } else if (ha && hb) {
+                            v[ia][ib].x *= cc;
+                            v[ia][ib].y *= cc;
+                        }
+                    }
+            }
+        }
+#pragma unroll
+        for (int ia = 0; ia < TS; ++ia)
+#pragma unroll
+            for (int ib = 0; ib < TS; ++ib) s[base + off[ia] * k.DB + off[ib]] = v[ia][ib];
+    }
+    t.sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// read-outs and snapshots
+// ------------------------------------------------------------------------------------------------
+template <bool W>
+__device__ void emit(const double2* s, const EvolveParams& k, int inst, int slot, const Team<W>& t) {
     const qsx_evolve_args& a = k.a;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int o = warp; o < a.n_obs; o += nwarps) {
-        double re = 0.0, im = 0.0;
-        const double2* w = reinterpret_cast<const double2*>(a.obs_w);
-        for (int q = a.obs_ptr[o] + lane; q < a.obs_ptr[o + 1]; q += 32) {
-            double2 v = cmul(w[q], s[a.obs_idx[q]]);
-            re += v.x;
-            im += v.y;
-        }
-        for (int off = 16; off; off >>= 1) {
-            re += __shfl_xor_sync(0xffffffffu, re, off);
-            im += __shfl_xor_sync(0xffffffffu, im, off);
-        }
-        if (lane == 0) {
-            size_t at = ((size_t)inst * a.n_emit + slot) * a.n_obs + o;
-            if (a.obs_real) a.out_obs[at] = re;
-            else reinterpret_cast<double2*>(a.out_obs)[at] = make_double2(re, im);
+    const double2* w = reinterpret_cast<const double2*>(a.obs_w);
+    if (a.n_obs > 0) {
+        // one thread per observable (serial sum) when teams are small; warp-per-observable otherwise
+        if (W) {
+            for (int o = t.tid; o < a.n_obs; o += t.n) {
+                double re = 0.0, im = 0.0;
+                for (int q = a.obs_ptr[o]; q < a.obs_ptr[o + 1]; ++q) {
+                    double2 v = cmul(w[q], s[a.obs_idx[q]]);
+                    re += v.x;
+                    im += v.y;
+                }
+                size_t at = ((size_t)inst * a.n_emit + slot) * a.n_obs + o;
+                if (a.obs_real) a.out_obs[at] = re;
+                else reinterpret_cast<double2*>(a.out_obs)[at] = make_double2(re, im);
+            }
+        } else {
+            const int lane = t.tid & 31, warp = t.tid >> 5, nwarps = t.n >> 5;
+            for (int o = warp; o < a.n_obs; o += nwarps) {
+                double re = 0.0, im = 0.0;
+                for (int q = a.obs_ptr[o] + lane; q < a.obs_ptr[o + 1]; q += 32) {
+                    double2 v = cmul(w[q], s[a.obs_idx[q]]);
+                    re += v.x;
+                    im += v.y;
+                }
+                for (int off = 16; off; off >>= 1) {
+                    re += __shfl_xor_sync(0xffffffffu, re, off);
+                    im += __shfl_xor_sync(0xffffffffu, im, off);
+                }
+                if (lane == 0) {
+                    size_t at = ((size_t)inst * a.n_emit + slot) * a.n_obs + o;
+                    if (a.obs_real) a.out_obs[at] = re;
+                    else reinterpret_cast<double2*>(a.out_obs)[at] = make_double2(re, im);
+                }
+            }
         }
     }
     if (a.out_snap) {
         double2* dst = reinterpret_cast<double2*>(a.out_snap) + ((size_t)inst * a.n_emit + slot) * k.E;
-        for (int e = threadIdx.x; e < k.E; e += blockDim.x) dst[e] = s[e];
+        for (int e = t.tid; e < k.E; e += t.n) dst[e] = s[e];
     }
-    __syncthreads();      // the next pass overwrites sigma
+    t.sync();      // the next sweep overwrites sigma
 }
 
-__global__ void evolve_generic_kernel(const EvolveParams k) {
+// ------------------------------------------------------------------------------------------------
+// the evolution kernel
+// ------------------------------------------------------------------------------------------------
+template <bool W, int CLS, bool WS>
+__global__ void __launch_bounds__(256) evolve_kernel(const EvolveParams k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const qsx_evolve_args& a = k.a;
-    // shared layout: [sigma E complex (unless workspace)] [params] [ops] [cfgA cfgB rankA rankB]
+    // shared layout: [launch tables: ops | passes | tiles | hops | cfgA cfgB rankA rankB] [per instance: sigma | params]
     unsigned char* cur = smem_raw;
-    double2* s;
-    if (k.use_workspace) {
-        s = reinterpret_cast<double2*>(a.workspace) + (size_t)blockIdx.x * k.E;
-    } else {
-        s = reinterpret_cast<double2*>(cur);
-        cur += (size_t)k.E * sizeof(double2);
-    }
-    double* P = reinterpret_cast<double*>(cur);
-    cur += (size_t)((a.param_stride + 1) & ~1) * sizeof(double);
     qsx_op* ops = reinterpret_cast<qsx_op*>(cur);
     cur += (size_t)a.n_ops * sizeof(qsx_op);
+    qsx_pass* passes = reinterpret_cast<qsx_pass*>(cur);
+    cur += (size_t)a.n_passes * sizeof(qsx_pass);
+    int* tiles = reinterpret_cast<int*>(cur);
+    cur += (size_t)k.n_tile_ints * sizeof(int);
+    int* hops = reinterpret_cast<int*>(cur);
+    cur += (size_t)k.n_hop_ints * sizeof(int);
     int* cfgA = reinterpret_cast<int*>(cur);
     int* cfgB = cfgA + a.block.nA;
     int* rankA = cfgB + a.block.nB;
     int* rankB = rankA + (1 << a.block.n_sites);
+    cur = reinterpret_cast<unsigned char*>(rankB + (1 << a.block.n_sites));
+    cur = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cur) + 15) & ~uintptr_t(15));
 
     for (int i = threadIdx.x; i < a.n_ops * (int)(sizeof(qsx_op) / 4); i += blockDim.x)
         reinterpret_cast<int*>(ops)[i] = reinterpret_cast<const int*>(a.ops)[i];
+    for (int i = threadIdx.x; i < a.n_passes * (int)(sizeof(qsx_pass) / 4); i += blockDim.x)
+        reinterpret_cast<int*>(passes)[i] = reinterpret_cast<const int*>(a.passes)[i];
+    for (int i = threadIdx.x; i < k.n_tile_ints; i += blockDim.x) tiles[i] = a.tiles[i];
+    for (int i = threadIdx.x; i < k.n_hop_ints; i += blockDim.x) hops[i] = a.hops[i];
     for (int i = threadIdx.x; i < a.block.nA; i += blockDim.x) cfgA[i] = a.block.cfgA[i];
     for (int i = threadIdx.x; i < a.block.nB; i += blockDim.x) cfgB[i] = a.block.cfgB[i];
     for (int i = threadIdx.x; i < (1 << a.block.n_sites); i += blockDim.x) {
         rankA[i] = a.block.rankA[i];
         rankB[i] = a.block.rankB[i];
     }
+    __syncthreads();
+    Tables tb{ops, passes, tiles, hops, cfgA, cfgB, rankA, rankB};
 
-    for (int inst = blockIdx.x; inst < a.n_inst; inst += gridDim.x) {
-        __syncthreads();
+    const int team_id = threadIdx.x / k.team;
+    Team<W> t;
+    t.tid = threadIdx.x - team_id * k.team;
+    t.n = k.team;
+    t.mask = 0xffffffffu;
+    unsigned char* mine = cur + (size_t)team_id * k.inst_stride;
+    // WS is a template parameter so that, in the common case, the compiler knows sigma is in shared memory (LDS/STS)
+    double2* s;
+    double* P;
+    if (WS) {
+        s = reinterpret_cast<double2*>(a.workspace) + (size_t)blockIdx.x * k.E;
+        P = reinterpret_cast<double*>(mine);
+    } else {
+        s = reinterpret_cast<double2*>(mine);
+        P = reinterpret_cast<double*>(mine + (size_t)k.E * sizeof(double2));
+    }
+
+    for (int inst = blockIdx.x * k.inst_per_cta + team_id;; inst += gridDim.x * k.inst_per_cta) {
+        if (W) {
+            // teams that ran out of instances leave; the others keep synchronising among themselves
+            t.mask = __ballot_sync(t.mask, inst < a.n_inst);
+            if (inst >= a.n_inst) break;
+        } else {
+            if (inst >= a.n_inst) break;      // uniform for the whole CTA (one team per CTA)
+        }
+        t.sync();
         const int set = a.inst_set ? a.inst_set[inst] : 0;
         const int src = a.inst_src ? a.inst_src[inst] : inst;
         const double* Pg = a.params + (size_t)set * a.param_stride;
-        for (int i = threadIdx.x; i < a.param_stride; i += blockDim.x) P[i] = Pg[i];
+        for (int i = t.tid; i < a.param_stride; i += t.n) P[i] = Pg[i];
         const double2* sin = reinterpret_cast<const double2*>(a.sigma_in) + (size_t)src * k.E;
-        for (int e = threadIdx.x; e < k.E; e += blockDim.x) s[e] = sin[e];
-        __syncthreads();
+        for (int e = t.tid; e < k.E; e += t.n) s[e] = sin[e];
+        t.sync();
 
         int slot = 0;
         if (slot < a.n_emit && a.emit_steps[slot] == 0) {
-            emit(s, k, inst, slot);
+            emit(s, k, inst, slot, t);
             ++slot;
         }
+        int next_emit = slot < a.n_emit ? a.emit_steps[slot] : -1;
         for (int step = 1; step <= a.n_steps && slot < a.n_emit; ++step) {
-            for (int o = 0; o < a.n_ops; ++o) {
-                const qsx_op& op = ops[o];
-                switch (op.type) {
-                    case QSX_OP_DIAG: pass_diag(s, k, op, P); break;
-                    case QSX_OP_HOP: pass_hop(s, k, op, P, cfgA, cfgB, rankA, rankB); break;
-                    case QSX_OP_PROT: pass_prot(s, k, op, P, cfgA, cfgB); break;
-                    case QSX_OP_AD:
-                    case QSX_OP_RESET: pass_ad_or_reset(s, k, op, P); break;
-                    default: break;
+            if (a.n_passes > 0) {
+                for (int pi = 0; pi < a.n_passes; ++pi) {
+                    const qsx_pass& ps = passes[pi];
+                    if (ps.type == QSX_PASS_CFG) pass_cfg_dispatch<W, CLS>(s, k, ps, P, tb, t);
+                    else if (ps.type == QSX_PASS_MODE) {
+                        if (ps.f[2] == 2) pass_mode<2, W>(s, k, ps, P, tb, t);
+                        else pass_mode<1, W>(s, k, ps, P, tb, t);
+                    } else sweep_op(s, k, ops[ps.f[0]], P, tb, t);
                 }
+            } else {
+                for (int o = 0; o < a.n_ops; ++o) sweep_op(s, k, ops[o], P, tb, t);
             }
-            if (a.emit_steps[slot] == step) {
-                emit(s, k, inst, slot);
+            if (next_emit == step) {
+                emit(s, k, inst, slot, t);
                 ++slot;
+                next_emit = slot < a.n_emit ? a.emit_steps[slot] : -1;
             }
         }
     }
@@ -332,16 +650,11 @@ __global__ void dfma_peak_kernel(double* out, int iters, double seed) {
 }
 
 int32_t check_block(const qsx_block& b) {
-    if (b.n_sites < 1 || b.n_sites > 16) return fail(QSX_ERR_INVALID, "n_sites out of range%s");
+    if (b.n_sites < 1 || b.n_sites > 12) return fail(QSX_ERR_INVALID, "n_sites out of range%s");
     if (b.n_bits < 0 || b.n_bits > 14) return fail(QSX_ERR_INVALID, "n_bits out of range%s");
     if (b.nA < 1 || b.nB < 1) return fail(QSX_ERR_INVALID, "empty sector%s");
     if (!b.cfgA || !b.cfgB || !b.rankA || !b.rankB) return fail(QSX_ERR_INVALID, "null sector table%s");
     return QSX_OK;
-}
-
-size_t evolve_static_smem(const qsx_evolve_args& a) {
-    return (size_t)((a.param_stride + 1) & ~1) * sizeof(double) + (size_t)a.n_ops * sizeof(qsx_op) +
-           (size_t)(a.block.nA + a.block.nB + 2 * (1 << a.block.n_sites)) * sizeof(int) + 16;
 }
 
 int32_t device_limits(int* sms, int* smem) {
@@ -349,6 +662,84 @@ int32_t device_limits(int* sms, int* smem) {
     QSX_CUDA(cudaGetDevice(&dev));
     QSX_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
     QSX_CUDA(cudaDeviceGetAttribute(smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    return QSX_OK;
+}
+
+struct Plan {
+    EvolveParams k;
+    size_t smem;
+    int grid, threads;
+    bool warp;
+};
+
+int32_t evolve_plan(const qsx_evolve_args* a, Plan* pl) {
+    if (!a) return fail(QSX_ERR_INVALID, "null args%s");
+    int32_t rc = check_block(a->block);
+    if (rc) return rc;
+    if (a->n_inst < 0 || a->n_steps < 0 || a->n_emit < 0 || a->n_ops < 0 || a->n_obs < 0 || a->n_passes < 0)
+        return fail(QSX_ERR_INVALID, "negative count%s");
+    if (a->n_ops > 0 && !a->ops) return fail(QSX_ERR_INVALID, "null ops%s");
+    if (a->n_passes > 0 && (!a->passes || a->n_tile_ints < 0 || a->n_hop_ints < 0 ||
+                            (a->n_tile_ints > 0 && !a->tiles) || (a->n_hop_ints > 0 && !a->hops)))
+        return fail(QSX_ERR_INVALID, "bad pass tables%s");
+    if (a->param_stride > 0 && !a->params) return fail(QSX_ERR_INVALID, "null params%s");
+    if (a->n_inst > 0 && !a->sigma_in) return fail(QSX_ERR_INVALID, "null sigma_in%s");
+    if (a->n_emit > 0 && !a->emit_steps) return fail(QSX_ERR_INVALID, "null emit_steps%s");
+    if (a->n_obs > 0 && (!a->obs_ptr || !a->obs_idx || !a->obs_w || !a->out_obs))
+        return fail(QSX_ERR_INVALID, "null read-out table%s");
+    int64_t DA = (int64_t)a->block.nA << a->block.n_bits, DB = (int64_t)a->block.nB << a->block.n_bits;
+    if (DA * DB > (int64_t)1 << 28) return fail(QSX_ERR_INVALID, "block too large%s");
+    EvolveParams& k = pl->k;
+    k.a = *a;
+    k.DA = (int32_t)DA;
+    k.DB = (int32_t)DB;
+    k.E = (int32_t)(DA * DB);
+    const int n_tile_ints = a->n_passes > 0 ? a->n_tile_ints : 0, n_hop_ints = a->n_passes > 0 ? a->n_hop_ints : 0;
+    k.n_tile_ints = n_tile_ints;
+    k.n_hop_ints = n_hop_ints;
+    int sms = 0, smem_max = 0;
+    rc = device_limits(&sms, &smem_max);
+    if (rc) return rc;
+
+    int t = a->threads;
+    if (t <= 0) {
+        t = 1;
+        while (t < 256 && t * 4 < k.E) t <<= 1;          // about 4 elements per thread and sweep
+    }
+    if (t & (t - 1) || t > 256) return fail(QSX_ERR_INVALID, "threads must be a power of two <= 256%s");
+    pl->warp = t <= 32;
+    k.team = t;
+    k.inst_per_cta = pl->warp ? 128 / t : 1;
+    pl->threads = pl->warp ? 128 : t;
+
+    size_t tables = (size_t)a->n_ops * sizeof(qsx_op) + (size_t)a->n_passes * sizeof(qsx_pass) +
+                    (size_t)(n_tile_ints + n_hop_ints) * sizeof(int) +
+                    (size_t)(a->block.nA + a->block.nB + 2 * (1 << a->block.n_sites)) * sizeof(int) + 16;
+    size_t p_bytes = (size_t)((a->param_stride + 1) & ~1) * sizeof(double);
+    size_t sigma_bytes = (size_t)k.E * sizeof(double2);
+    size_t with_sigma = tables + (size_t)k.inst_per_cta * (sigma_bytes + p_bytes);
+    k.use_workspace = with_sigma > (size_t)smem_max;
+    if (k.use_workspace) {
+        k.team = pl->threads = 256;
+        pl->warp = false;
+        k.inst_per_cta = 1;
+        k.inst_stride = (int32_t)p_bytes;
+        pl->smem = tables + p_bytes;
+    } else {
+        k.inst_stride = (int32_t)(sigma_bytes + p_bytes);
+        pl->smem = with_sigma;
+    }
+    if (pl->smem > (size_t)smem_max) return fail(QSX_ERR_TOO_LARGE, "program tables exceed shared memory%s");
+    // resident CTAs per SM: bounded by shared memory (228 KB per SM, 1 KB reserved per CTA), 2048 threads, 32 CTAs
+    int per_sm = (int)((size_t)(228 * 1024) / (pl->smem + 1024));
+    if (per_sm > 2048 / pl->threads) per_sm = 2048 / pl->threads;
+    if (per_sm > 32) per_sm = 32;
+    if (per_sm < 1) per_sm = 1;
+    int need = (a->n_inst + k.inst_per_cta - 1) / k.inst_per_cta;
+    int g = sms * per_sm;
+    if (g > need) g = need;
+    if (g < 1) g = 1;
+    pl->grid = g;
     return QSX_OK;
 }
 
@@ -373,71 +764,43 @@ int32_t qsx_device_info(int32_t* sm_count, int32_t* smem_optin, int32_t* cc) {
     return QSX_OK;
 }
 
-static int32_t evolve_plan(const qsx_evolve_args* a, EvolveParams* k, size_t* smem_bytes, int* grid, int* threads) {
-    if (!a) return fail(QSX_ERR_INVALID, "null args%s");
-    int32_t rc = check_block(a->block);
-    if (rc) return rc;
-    if (a->n_inst < 0 || a->n_steps < 0 || a->n_emit < 0 || a->n_ops < 0 || a->n_obs < 0)
-        return fail(QSX_ERR_INVALID, "negative count%s");
-    if (a->n_ops > 0 && !a->ops) return fail(QSX_ERR_INVALID, "null ops%s");
-    if (a->param_stride > 0 && !a->params) return fail(QSX_ERR_INVALID, "null params%s");
-    if (a->n_inst > 0 && !a->sigma_in) return fail(QSX_ERR_INVALID, "null sigma_in%s");
-    if (a->n_emit > 0 && !a->emit_steps) return fail(QSX_ERR_INVALID, "null emit_steps%s");
-    if (a->n_obs > 0 && (!a->obs_ptr || !a->obs_idx || !a->obs_w || !a->out_obs))
-        return fail(QSX_ERR_INVALID, "null read-out table%s");
-    int64_t DA = (int64_t)a->block.nA << a->block.n_bits, DB = (int64_t)a->block.nB << a->block.n_bits;
-    if (DA * DB > (int64_t)1 << 28) return fail(QSX_ERR_INVALID, "block too large%s");
-    k->a = *a;
-    k->DA = (int32_t)DA;
-    k->DB = (int32_t)DB;
-    k->E = (int32_t)(DA * DB);
-    int sms = 0, smem_max = 0;
-    rc = device_limits(&sms, &smem_max);
-    if (rc) return rc;
-    size_t fixed = evolve_static_smem(*a);
-    size_t with_sigma = fixed + (size_t)k->E * sizeof(double2);
-    k->use_workspace = with_sigma > (size_t)smem_max;
-    *smem_bytes = k->use_workspace ? fixed : with_sigma;
-    if (*smem_bytes > (size_t)smem_max) return fail(QSX_ERR_TOO_LARGE, "program tables exceed shared memory%s");
-    int t = a->threads;
-    if (t <= 0) {
-        t = 32;
-        while (t < 512 && t * 4 < k->E) t <<= 1;     // ~4+ elements per thread
-    }
-    if (t % 32 || t > 1024) return fail(QSX_ERR_INVALID, "threads must be a multiple of 32, <= 1024%s");
-    *threads = t;
-    // resident CTAs per SM bounded by shared memory (228 KB per SM, 1 KB reserved per CTA) and 2048 threads
-    int per_sm = (int)((size_t)(228 * 1024) / (*smem_bytes + 1024));
-    if (per_sm > 2048 / t) per_sm = 2048 / t;
-    if (per_sm > 32) per_sm = 32;
-    if (per_sm < 1) per_sm = 1;
-    int g = sms * per_sm;
-    if (g > a->n_inst) g = a->n_inst;
-    if (g < 1) g = 1;
-    *grid = g;
-    return QSX_OK;
-}
-
 int64_t qsx_evolve_workspace_bytes(const qsx_evolve_args* args) {
-    EvolveParams k;
-    size_t smem = 0;
-    int grid = 0, threads = 0;
-    int32_t rc = evolve_plan(args, &k, &smem, &grid, &threads);
+    Plan pl;
+    int32_t rc = evolve_plan(args, &pl);
     if (rc) return rc;
-    return k.use_workspace ? (int64_t)grid * k.E * (int64_t)sizeof(double2) : 0;
+    return pl.k.use_workspace ? (int64_t)pl.grid * pl.k.E * (int64_t)sizeof(double2) : 0;
 }
 
 int32_t qsx_evolve(const qsx_evolve_args* args, void* stream) {
-    EvolveParams k;
-    size_t smem = 0;
-    int grid = 0, threads = 0;
-    int32_t rc = evolve_plan(args, &k, &smem, &grid, &threads);
+    if (!args) return fail(QSX_ERR_INVALID, "null args%s");
+    Plan pl;
+    int32_t rc = evolve_plan(args, &pl);
     if (rc) return rc;
     if (args->n_inst == 0 || args->n_emit == 0) return QSX_OK;
-    if (k.use_workspace && !args->workspace)
+    if (pl.k.use_workspace && !args->workspace)
         return fail(QSX_ERR_TOO_LARGE, "block does not fit shared memory; pass a workspace%s");
-    QSX_CUDA(cudaFuncSetAttribute(evolve_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    evolve_generic_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(k);
+    const int big = args->block.nA > args->block.nB ? args->block.nA : args->block.nB;
+    const int cls = big <= 2 ? 0 : (big <= 4 ? 1 : 2);
+#define QSX_LAUNCH(WARP, CLS, WS)                                                                                    \
+    do {                                                                                                             \
+        QSX_CUDA(cudaFuncSetAttribute(evolve_kernel<WARP, CLS, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                      (int)pl.smem));                                                                \
+        evolve_kernel<WARP, CLS, WS><<<pl.grid, pl.threads, pl.smem, (cudaStream_t)stream>>>(pl.k);                  \
+    } while (0)
+    if (pl.k.use_workspace) {
+        if (cls == 0) QSX_LAUNCH(false, 0, true);
+        else if (cls == 1) QSX_LAUNCH(false, 1, true);
+        else QSX_LAUNCH(false, 2, true);
+    } else if (pl.warp) {
+        if (cls == 0) QSX_LAUNCH(true, 0, false);
+        else if (cls == 1) QSX_LAUNCH(true, 1, false);
+        else QSX_LAUNCH(true, 2, false);
+    } else {
+        if (cls == 0) QSX_LAUNCH(false, 0, false);
+        else if (cls == 1) QSX_LAUNCH(false, 1, false);
+        else QSX_LAUNCH(false, 2, false);
+    }
+#undef QSX_LAUNCH
     QSX_CUDA(cudaGetLastError());
     return QSX_OK;
 }

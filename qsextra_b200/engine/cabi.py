@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libqsx.so')
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = ('qsx_abi_version', 'qsx_last_error', 'qsx_device_info', 'qsx_evolve_workspace_bytes', 'qsx_evolve',
            'qsx_apply_dipole', 'qsx_fp64_peak')
@@ -23,6 +23,10 @@ class QsxError(RuntimeError):
 
 class QsxOp(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('type', 'i0', 'i1', 'i2', 'i3', 'i4', 'p', 'reserved')]
+
+
+class QsxPass(C.Structure):
+    _fields_ = [('type', C.c_int32), ('f', C.c_int32 * 11)]
 
 
 class QsxBlock(C.Structure):
@@ -39,7 +43,10 @@ class QsxEvolveArgs(C.Structure):
                 ('n_steps', C.c_int32), ('n_emit', C.c_int32), ('emit_steps', C.c_void_p),
                 ('n_obs', C.c_int32), ('obs_ptr', C.c_void_p), ('obs_idx', C.c_void_p), ('obs_w', C.c_void_p),
                 ('out_obs', C.c_void_p), ('obs_real', C.c_int32),
-                ('out_snap', C.c_void_p), ('workspace', C.c_void_p), ('threads', C.c_int32)]
+                ('out_snap', C.c_void_p), ('workspace', C.c_void_p), ('threads', C.c_int32),
+                ('n_passes', C.c_int32), ('passes', C.c_void_p),
+                ('n_tile_ints', C.c_int32), ('tiles', C.c_void_p),
+                ('n_hop_ints', C.c_int32), ('hops', C.c_void_p)]
 
 
 _lib = None

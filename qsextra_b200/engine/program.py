@@ -406,6 +406,10 @@ class BoundProgram:
     ops: np.ndarray          # [n_ops, 8] int32 (qsx_op)
     params: np.ndarray       # [B, stride] float64
     labels: list             # human-readable op names, for reports
+    passes: np.ndarray = None    # [n_passes, 12] int32 (qsx_pass) or None: run the plain operation list
+    tiles: np.ndarray = None
+    hops: np.ndarray = None
+    team: int = 0                # threads per instance the pass tables were built for (0: library default)
 
 
 class StepProgram:
@@ -429,11 +433,12 @@ class StepProgram:
     def block(self, ka: int, kb: int) -> Block:
         return Block(self.n_sites, self.n_bits, ka, kb)
 
-    def bind(self, block: Block) -> BoundProgram:
-        """Angle tables and qsx_op array for one (KA, KB) block."""
+    def bind(self, block: Block, fused: bool = True, team: int | None = None, kb: int | None = None) -> BoundProgram:
+        """Angle tables, qsx_op array and (``fused``) the equivalent pass program for one (KA, KB) block."""
         B = self.batch.batch
         nb = block.n_bits
         chunks, ops, labels = [], [], []
+        op_slots = []                                # per lowered op: (index in ops, {name: parameter slot})
         cursor = 0
 
         def push(arr):                               # arr [B, n] doubles; slots are kept even (16-byte aligned)
@@ -470,10 +475,12 @@ class StepProgram:
                         c, s = np.cos(phi), np.sin(phi)
                         t = t * np.where(differs[site][None], (c * c - s * s)[:, None, None], 1.0)
                     slot_t = push(t)
+                op_slots.append((len(ops), dict(ga=slot_a, gb=slot_b, t=slot_t)))
                 ops.append([OP_DIAG, slot_a, slot_b, slot_t, 0, 0, 0, 0])
                 labels.append('diag')
             elif isinstance(op, _Hop):
                 slot = push(np.stack([np.cos(2 * op.xx), np.sin(2 * op.xx)], axis=1))
+                op_slots.append((len(ops), dict(cs=slot)))
                 ops.append([OP_HOP, op.i, op.j, 0, 0, 0, slot, 0])
                 labels.append('hop({},{})'.format(op.i, op.j))
             elif isinstance(op, _Prot):
@@ -481,17 +488,26 @@ class StepProgram:
                 skip0 = int(op.site >= 0 and not np.any(th0 != 0))
                 slot = push(np.stack([np.cos(th0), np.sin(th0), np.cos(th1), np.sin(th1)], axis=1))
                 ny = _popcount(op.xb & op.zb) & 3
+                op_slots.append((len(ops), dict(cs=slot, skip0=skip0)))
                 ops.append([OP_PROT, op.xb, op.zb, ny, op.site, skip0, slot, 0])
                 labels.append('prot(x={:b},z={:b},site={})'.format(op.xb, op.zb, op.site))
             elif isinstance(op, Damp):
                 slot = push(np.stack([np.cos(op.phi), np.sin(op.phi) ** 2], axis=1))
+                op_slots.append((len(ops), dict(cs=slot)))
                 ops.append([OP_AD, op.bit, 0, 0, 0, 0, slot, 0])
                 labels.append('damp({})'.format(op.bit))
             elif isinstance(op, Reset):
+                op_slots.append((len(ops), {}))
                 ops.append([OP_RESET, op.bit, 0, 0, 0, 0, 0, 0])
                 labels.append('reset({})'.format(op.bit))
         params = np.concatenate(chunks, axis=1) if chunks else np.zeros((B, 2))
-        return BoundProgram(block, np.array(ops, dtype=np.int32).reshape(-1, 8), params, labels)
+        bound = BoundProgram(block, np.array(ops, dtype=np.int32).reshape(-1, 8), params, labels)
+        if fused and self.lowered:
+            from .passes import build_passes, default_team
+            bound.team = team or default_team(block)
+            bit_site = {bit: site for (site, _), bits in self.layout.mode.items() for bit in bits}
+            bound.passes, bound.tiles, bound.hops = build_passes(self.lowered, op_slots, block, bit_site, bound.team, kb)
+        return bound
 
 
 # ---------------------------------------------------------------------------------------------

@@ -65,11 +65,18 @@ class Engine:
 
     def upload_program(self, bound: BoundProgram):
         """-> dict of device tensors for a bound program (ops + parameter sets)."""
-        return dict(block=self.device_block(bound.block),
-                    ops=self.to_device(bound.ops, torch.int32),
-                    params=self.to_device(bound.params, torch.float64),
-                    n_ops=int(bound.ops.shape[0]), stride=int(bound.params.shape[1]),
-                    n_sets=int(bound.params.shape[0]))
+        dev = dict(block=self.device_block(bound.block),
+                   ops=self.to_device(bound.ops, torch.int32),
+                   params=self.to_device(bound.params, torch.float64),
+                   n_ops=int(bound.ops.shape[0]), stride=int(bound.params.shape[1]),
+                   n_sets=int(bound.params.shape[0]), n_passes=0, team=0)
+        if bound.passes is not None and len(bound.passes):
+            dev.update(n_passes=int(bound.passes.shape[0]), team=int(bound.team),
+                       passes=self.to_device(bound.passes, torch.int32),
+                       tiles=self.to_device(bound.tiles if len(bound.tiles) else np.zeros(2, np.int32), torch.int32),
+                       hops=self.to_device(bound.hops if len(bound.hops) else np.zeros(4, np.int32), torch.int32),
+                       n_tile_ints=int(len(bound.tiles)), n_hop_ints=int(len(bound.hops)))
+        return dev
 
     def upload_observables(self, ptr, idx, w):
         return dict(n=len(ptr) - 1, ptr=self.to_device(ptr, torch.int32), idx=self.to_device(idx, torch.int32),
@@ -105,7 +112,11 @@ class Engine:
             args.out_obs = out_obs.data_ptr()
         args.obs_real = int(obs_real)
         args.out_snap = None if out_snap is None else out_snap.data_ptr()
-        args.threads = threads
+        args.threads = threads or prog.get('team', 0)
+        if prog.get('n_passes', 0) > 0:
+            args.n_passes, args.passes = prog['n_passes'], prog['passes'].data_ptr()
+            args.n_tile_ints, args.tiles = prog['n_tile_ints'], prog['tiles'].data_ptr()
+            args.n_hop_ints, args.hops = prog['n_hop_ints'], prog['hops'].data_ptr()
         with torch.cuda.device(self.device):
             ws_bytes = self.lib.qsx_evolve_workspace_bytes(C.byref(args))
             cabi.check(ws_bytes)

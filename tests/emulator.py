@@ -139,3 +139,84 @@ def response_function(program, mu, side_seq, direction_seq, step_counts):
     sigma[0, 0] = 1.0
     descend(sigma, block, 0, ())
     return signal
+
+
+def apply_pass_program(sigma, bound, set_index=0):
+    """One step through ``bound.passes`` (QSX_PASS_* semantics of include/qsx.h), tile by tile."""
+    from qsextra_b200.engine.passes import PASS_CFG, PASS_MODE, PASS_OP
+    blk = bound.block
+    nb, DA, DB = blk.n_bits, blk.dim_a, blk.dim_b
+    P = bound.params[set_index]
+    s = sigma.copy().reshape(-1)
+    for ps in bound.passes:
+        typ, f = int(ps[0]), [int(v) for v in ps[1:]]
+        if typ == PASS_OP:
+            single = type(bound)(blk, bound.ops[f[0]:f[0] + 1], bound.params, [])
+            s = apply_step(s.reshape(DA, DB), single, set_index).reshape(-1)
+        elif typ == PASS_CFG:
+            off, n, TA, TB, sga, sgb, stpre, stpost, h0, h1 = f[:10]
+            sA, sB = (1 << nb) * DB, 1 << nb
+            for ti in range(n):
+                base, mm = bound.tiles[off + 2 * ti], bound.tiles[off + 2 * ti + 1]
+                ma, mb = mm & 0xffff, mm >> 16
+                idx = np.array([[base + i * sA + j * sB for j in range(TB)] for i in range(TA)])
+                v = s[idx]
+                if sga >= 0:
+                    ga = np.array([complex(P[sga + 2 * ((i << nb) | ma)], P[sga + 2 * ((i << nb) | ma) + 1]) for i in range(TA)])
+                    gb = np.array([complex(P[sgb + 2 * ((j << nb) | mb)], P[sgb + 2 * ((j << nb) | mb) + 1]) for j in range(TB)])
+                    v = v * ga[:, None] * gb.conj()[None, :]
+                    if stpre >= 0:
+                        v = v * P[stpre:stpre + TA * TB].reshape(TA, TB)
+                for h in range(h0, h1):
+                    side, p, q, slot = (int(x) for x in bound.hops[4 * h:4 * h + 4])
+                    c, sn = P[slot], P[slot + 1]
+                    if side == 0:
+                        x, y = v[p].copy(), v[q].copy()
+                        v[p], v[q] = c * x - 1j * sn * y, c * y - 1j * sn * x
+                    else:
+                        x, y = v[:, p].copy(), v[:, q].copy()
+                        v[:, p], v[:, q] = c * x + 1j * sn * y, c * y + 1j * sn * x
+                if stpost >= 0:
+                    v = v * P[stpost:stpost + TA * TB].reshape(TA, TB)
+                s[idx] = v
+        elif typ == PASS_MODE:
+            off, n, KB = f[0], f[1], f[2]
+            bits, rots, ads, skip = f[3:3 + KB], f[5:5 + KB], f[7:7 + KB], f[9]
+            TS = 1 << KB
+            offs = [sum(1 << bits[b] for b in range(KB) if (i >> b) & 1) for i in range(TS)]
+            for ti in range(n):
+                base, flags = int(bound.tiles[off + 2 * ti]), int(bound.tiles[off + 2 * ti + 1])
+                idx = np.array([[base + offs[ia] * DB + offs[ib] for ib in range(TS)] for ia in range(TS)])
+                v = s[idx]
+                for b in range(KB):
+                    if rots[b] >= 0:
+                        for side in (0, 1):
+                            occ = (flags >> (2 * b + side)) & 1
+                            if not occ and (skip >> b) & 1:
+                                continue
+                            c, sn = P[rots[b] + 2 * occ], P[rots[b] + 2 * occ + 1]
+                            for i0 in range(TS):
+                                if (i0 >> b) & 1:
+                                    continue
+                                i1 = i0 | (1 << b)
+                                if side == 0:
+                                    x, y = v[i0].copy(), v[i1].copy()
+                                    v[i0], v[i1] = c * x - 1j * sn * y, c * y - 1j * sn * x
+                                else:
+                                    x, y = v[:, i0].copy(), v[:, i1].copy()
+                                    v[:, i0], v[:, i1] = c * x + 1j * sn * y, c * y + 1j * sn * x
+                    if ads[b] >= 0:
+                        c, s2 = P[ads[b]], P[ads[b] + 1]
+                        new = v.copy()
+                        for ia in range(TS):
+                            for ib in range(TS):
+                                ha, hb = (ia >> b) & 1, (ib >> b) & 1
+                                if not ha and not hb:
+                                    new[ia, ib] = v[ia, ib] + s2 * v[ia | (1 << b), ib | (1 << b)]
+                                elif ha != hb:
+                                    new[ia, ib] = c * v[ia, ib]
+                                else:
+                                    new[ia, ib] = c * c * v[ia, ib]
+                        v = new
+                s[idx] = v
+    return s.reshape(DA, DB)

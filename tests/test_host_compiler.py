@@ -1,0 +1,126 @@
+"""Host-side logic on the CPU: the step-program compiler (masks, lowering, pass regrouping, sector tables) checked
+against the reference goldens through the NumPy emulation of the engine's operation semantics (tests/emulator.py)."""
+import numpy as np
+import pytest
+
+import emulator
+from helpers import build_spectroscopy, build_system, golden_names, load_golden, time_arg
+from qsextra_b200.engine.program import StepProgram, SystemBatch, mode_operator_terms, resolve_time_grid
+from qsextra_b200.engine.response import interaction_plan
+from qsextra_b200.engine.sectors import Block, sector_configs, sector_rank, split_state_by_sector
+from qsextra_b200.qcomo.evolution.qevolve import _program_for, initial_amplitudes
+from qsextra_b200.spectroscopy.simulation.qspectroscopy import delay_step_counts
+
+
+def _program(system, kw, time=None):
+    dt, dtt, tn, counts = resolve_time_grid(time if time is not None else kw['dt'], kw.get('dt'), kw.get('Trotter_number', 1))
+    return _program_for(system, dt, dtt, tn, kw.get('Trotter_order', 1), kw.get('coll_rates')), counts
+
+
+@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('name', golden_names('qevolve_'))
+def test_step_program_reproduces_reference_distribution(name, fused):
+    meta, arrays = load_golden(name)
+    system = build_system(meta['system'])
+    kw = dict(meta['kwargs'])
+    t = kw.pop('time')
+    prog, counts = _program(system, kw, time_arg(t))
+    n = system.system_size
+    wanted = sorted(set(int(c) for c in counts))
+    dist = np.zeros((len(wanted), 1 << n))
+    for k, amp in split_state_by_sector(n, initial_amplitudes(system)).items():
+        blk = prog.block(k, k)
+        bound = prog.bind(blk, fused=fused)
+        sig = np.zeros((blk.dim_a, blk.dim_b), complex)
+        at = np.arange(blk.n_a) << blk.n_bits
+        sig[np.ix_(at, at)] = np.outer(amp, amp.conj())
+        step = emulator.apply_pass_program if fused and bound.passes is not None else emulator.apply_step
+        for s in range(max(wanted) + 1):
+            if s:
+                sig = step(sig, bound)
+            if s in wanted:
+                dist[wanted.index(s), list(sector_configs(n, k))] += np.real(np.diag(sig)).reshape(blk.n_a, -1).sum(1)
+    assert np.abs(dist - arrays['distribution']).max() < 1e-12
+
+
+@pytest.mark.parametrize('name', golden_names('qspectroscopy_'))
+def test_response_tree_reproduces_reference_signal(name):
+    meta, arrays = load_golden(name)
+    system = build_system(meta['system'])
+    spec = build_spectroscopy(meta['label'], meta['delay_time'])
+    kw = dict(meta['kwargs'])
+    counts, (dt, dtt, tn, _) = delay_step_counts(spec.delay_time, kw.get('dt'), kw.get('Trotter_number', 1))
+    prog = _program_for(system, dt, dtt, tn, kw.get('Trotter_order', 1), kw.get('coll_rates'))
+    got = emulator.response_function(prog, system.dipole_moments, spec.side_seq, spec.direction_seq, counts)
+    assert np.abs(got - arrays['signal']).max() < 1e-12 * max(1.0, np.abs(arrays['signal']).max())
+
+
+def test_mode_operator_masks_match_reference_dictionaries():
+    """Same Pauli strings, same order, same coefficients as qevolve.py:107-195 (fixture from the reference)."""
+    meta, _ = load_golden('mode_operators')
+
+    def label(x, z, nq):
+        return ''.join('IXZY'[((x >> q) & 1) | (((z >> q) & 1) << 1)] for q in range(nq - 1, -1, -1))
+    for d, dicts in meta.items():
+        got = mode_operator_terms(int(d))
+        nq = len(dicts[0][0][0])
+        for want, have in zip(dicts, got):
+            assert [k for k, _ in want] == [label(x, z, nq) for (x, z) in have]
+            for (_, (re, im)), v in zip(want, have.values()):
+                assert abs(complex(re, im) - v) < 1e-15
+
+
+def test_pass_program_equals_operation_list_on_random_blocks():
+    rng = np.random.default_rng(5)
+    sd = dict(energies=[1.55, 1.50, 1.46, 1.52], couplings=[[0, -.01, 0, 0], [-.01, 0, -.01, 0], [0, -.01, 0, -.01], [0, 0, -.01, 0]],
+              dipole_moments=[1.] * 4, frequencies_pseudomode=0.02, levels_pseudomode=2, couplings_ep=0.054)
+    system = build_system(sd)
+    prog = _program_for(system, 0.15, 0.15, 1, 1, [0.2])
+    for ka, kb in ((0, 1), (1, 1), (2, 1), (1, 0)):
+        blk = prog.block(ka, kb)
+        for width in (1, 2):
+            bound = prog.bind(blk, kb=width)
+            assert {int(p[0]) for p in bound.passes} == {0, 1}            # fully fused: one cfg pass + mode passes
+            assert len(bound.passes) == 1 + (4 if width == 1 else 2)
+            sig = rng.normal(size=(blk.dim_a, blk.dim_b)) + 1j * rng.normal(size=(blk.dim_a, blk.dim_b))
+            assert np.abs(emulator.apply_step(sig, bound) - emulator.apply_pass_program(sig, bound)).max() < 1e-13
+
+
+def test_batched_parameters_equal_single_compiles():
+    rng = np.random.default_rng(2)
+    systems = []
+    for _ in range(3):
+        s = build_system(dict(energies=rng.uniform(1.4, 1.6, 2).tolist(), couplings=float(rng.uniform(-.05, .05)),
+                              dipole_moments=[1., 1.], frequencies_pseudomode=float(rng.uniform(.01, .2)),
+                              levels_pseudomode=2, couplings_ep=float(rng.uniform(.01, .1))))
+        systems.append(s)
+    rates = rng.uniform(0.1, 0.4, (3, 1))
+    batch_prog = StepProgram(SystemBatch.from_systems(systems), 0.15, 1, 1, rates)
+    blk = batch_prog.block(1, 1)
+    together = batch_prog.bind(blk)
+    for b, s in enumerate(systems):
+        alone = _program_for(s, 0.15, 0.15, 1, 1, rates[b].tolist()).bind(blk)
+        assert np.array_equal(alone.ops, together.ops)
+        assert np.abs(alone.params[0] - together.params[b]).max() < 1e-15
+
+
+def test_time_grid_rules():
+    dt, dtt, tn, counts = resolve_time_grid([0., 0.3, 0.1, 0.3], 0.1, 2)
+    assert (dt, dtt, tn) == (0.1, 0.05, 2) and counts.tolist() == [0, 3, 1, 3]
+    dt, dtt, tn, counts = resolve_time_grid(np.arange(0, 1.01, 0.5), None, 5)      # dt from the grid, collisions every dt/5
+    assert abs(dt - 0.1) < 1e-15 and tn == 1 and counts.tolist() == [0, 5, 10]
+    with pytest.raises(ValueError):
+        resolve_time_grid([0., 0.25], 0.1, 1)
+
+
+def test_sector_tables_and_interaction_plan():
+    assert sector_configs(4, 2) == (3, 5, 6, 9, 10, 12)
+    rank = sector_rank(4, 2)
+    assert rank[6] == 2 and rank[7] == -1
+    blk = Block(4, 4, 2, 1)
+    assert (blk.dim_a, blk.dim_b, blk.size) == (96, 64, 6144)
+    assert interaction_plan('bbkk', 'ioio') == [('b', 'X'), ('b', 'raise'), ('k', 'X'), ('k', 'X')]
+    assert interaction_plan('bkkk', 'iiio') == [('b', 'X'), ('k', 'X'), ('k', 'raise'), ('k', 'X')]
+    assert interaction_plan('kk', 'io') == [('k', 'X'), ('k', 'X')]
+    ptr, idx, w = Block(2, 0, 1, 0).emission_observable([2.0, 3.0])
+    assert idx.tolist() == [0, 1] and w.tolist() == [2.0, 3.0]
