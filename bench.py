@@ -187,14 +187,14 @@ def run_ours(args):
     program = StepProgram(batch, DT, 1, 1, params['rates'][lo:hi])
     block = program.block(1, 1)
     bound = program.bind(block)
-    dev = eng.upload_program(bound)
+    dev = eng.upload_program(bound, program)
     sigma0 = torch.zeros((1, block.size), dtype=torch.complex128, device=eng.device)
     site0 = (0 << block.n_bits) * block.dim_b + (0 << block.n_bits)    # |cfg 0 (site 0 excited), modes 0>
     sigma0[0, site0] = 1.0
     inst_set = torch.arange(N_SETS, dtype=torch.int32, device=eng.device)
     inst_src = torch.zeros(N_SETS, dtype=torch.int32, device=eng.device)
     emit = eng.to_device(np.arange(N_STEPS + 1), torch.int32)
-    obs = eng.upload_observables(*population_observables(block))
+    obs = eng.upload_observables(*population_observables(block), kind='populations')
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
 
     def hot_path():

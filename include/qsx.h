@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define QSX_ABI_VERSION 2
+#define QSX_ABI_VERSION 5
 
 enum {
     QSX_OK = 0,
@@ -129,6 +129,68 @@ typedef struct qsx_evolve_args {
     int32_t n_hop_ints;         /* length of `hops` in int32 */
     const int32_t* hops;        /* DEVICE hop entries of all QSX_PASS_CFG passes (p < q) */
 } qsx_evolve_args;
+
+/* Register-resident evolution of SMALL blocks whose dimensions are powers of two ("RR kernel").
+ * sigma, the diagonal table(s) and nothing else live in registers: every thread of a team of 2^L lanes holds 2^R
+ * elements; the physical index of an element is lane << R | reg and `logical_index` maps it to a*DB + b.  An
+ * operation combines every element with the element whose physical index differs by the xor mask (reg_xor, lane_xor):
+ *   QSX_RR_DIAG  v *= W[table aux0]                      (W per parameter set, physical order, complex128)
+ *   QSX_RR_ROT   v <- c v - i sign s partner   on the registers in `reg_mask`   (hops and conditioned X-rotations;
+ *                p -> {cos, sin}; the participation never depends on lane bits)
+ *   QSX_RR_AD    amplitude damping of the bit pair (ket, bra) whose register part is reg_xor and whose lane parts are
+ *                aux0 (ket lane mask) and aux1 (bra lane mask); p -> {cos phi, sin^2 phi}
+ * Parameter set layout: n_diag tables of E complex128 (physical order) followed by the op parameters (slots p are
+ * relative to the start of the set). */
+enum { QSX_RR_DIAG = 0, QSX_RR_ROT = 1, QSX_RR_AD = 2 };
+#define QSX_RR_MAX_OPS 24
+#define QSX_RR_MAX_OBS 8
+#define QSX_RR_MAX_ENTRIES 4
+
+typedef struct qsx_rr_op {
+    int32_t kind;
+    int32_t reg_xor, lane_xor;
+    uint32_t reg_mask;
+    int32_t p;
+    int32_t sign;            /* +1 ket side, -1 bra side */
+    int32_t aux0, aux1;
+} qsx_rr_op;
+
+typedef struct qsx_rr_args {
+    int32_t reg_bits;            /* R: 2^R elements per thread (0..4) */
+    int32_t lane_bits;           /* L: team = 2^L lanes (0..5) */
+    int32_t n_diag;              /* 0, 1 or 2 diagonal tables */
+    int32_t n_ops;
+    qsx_rr_op ops[QSX_RR_MAX_OPS];
+    const int32_t* logical_index;   /* DEVICE [E] */
+    int32_t param_stride;
+    const double* params;        /* DEVICE [n_sets][param_stride] */
+    int32_t n_inst;
+    const int32_t* inst_set;     /* DEVICE or NULL */
+    const int32_t* inst_src;     /* DEVICE or NULL */
+    const double* sigma_in;      /* DEVICE [n_src][E] complex128, LOGICAL order (same as qsx_evolve) */
+    int32_t n_steps, n_emit;
+    const int32_t* emit_steps;   /* DEVICE */
+    int32_t n_obs;               /* <= QSX_RR_MAX_OBS */
+    const double* obs_weights;   /* DEVICE [n_obs][E] complex128 weights in PHYSICAL order */
+    uint32_t obs_reg_mask[QSX_RR_MAX_OBS];  /* registers with a non-zero weight on some lane */
+    /* Optional factorised form of the read-outs (n_entries[o] > 0 for every o, else the dense weights are used):
+     * out[o] = sum_k weight[o][k] * [lane in lane_mask[o][k]] * sum_{r in reg_mask[o][k]} sigma(lane, r). */
+    int32_t n_entries[QSX_RR_MAX_OBS];
+    uint32_t entry_reg_mask[QSX_RR_MAX_OBS][QSX_RR_MAX_ENTRIES];
+    uint32_t entry_lane_mask[QSX_RR_MAX_OBS][QSX_RR_MAX_ENTRIES];
+    double entry_weight[QSX_RR_MAX_OBS][QSX_RR_MAX_ENTRIES];
+    /* What the read-outs ARE, when the host knows it (lets a compile-time program use compile-time read-out masks):
+     * 0 = unspecified (use the tables above), 1 = site populations (n_obs = N, obs_real),
+     * 2 = emission trace Tr[(sum_s mu_s X_s) sigma] (n_obs = 1) with the dipole moments in `mu`. */
+    int32_t readout_kind;
+    double mu[16];
+    double* out_obs;             /* DEVICE [n_inst][n_emit][n_obs] complex128 (or real parts if obs_real) */
+    int32_t obs_real;
+    double* out_snap;            /* DEVICE [n_inst][n_emit][E] complex128 in LOGICAL order, or NULL */
+} qsx_rr_args;
+
+/* Same contract as qsx_evolve, for programs the host could map onto the register-resident form. */
+int32_t qsx_evolve_rr(const qsx_rr_args* args, void* stream);
 
 int32_t qsx_abi_version(void);
 

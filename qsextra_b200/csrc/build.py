@@ -5,13 +5,13 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ['qsx_engine.cu']
+SOURCES = ["qsx_engine.cu"]
 OUT = os.path.join(HERE, 'libqsx.so')
 
 
 def build(force: bool = False, verbose: bool = True) -> str:
     srcs = [os.path.join(HERE, s) for s in SOURCES]
-    deps = srcs + [os.path.join(REPO, 'include', 'qsx.h')] + [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith('.cuh')]
+    deps = srcs + [os.path.join(REPO, 'include', 'qsx.h')] + [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(('.cuh', '.inc'))]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')

@@ -585,6 +585,10 @@ __global__ void __launch_bounds__(256) evolve_kernel(const EvolveParams k) {
     }
 }
 
+}  // namespace (helpers above are shared with the register-resident kernel)
+#include "qsx_rr.cuh"
+namespace {
+
 // ------------------------------------------------------------------------------------------------
 // collective dipole operator
 // ------------------------------------------------------------------------------------------------
@@ -837,6 +841,78 @@ int32_t qsx_apply_dipole(const qsx_block* in_blk, const qsx_block* out_blk, int3
     size_t blocks = (total + 255) / 256;
     if (blocks > (size_t)sms * 8) blocks = (size_t)sms * 8;
     dipole_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(k);
+    QSX_CUDA(cudaGetLastError());
+    return QSX_OK;
+}
+
+int32_t qsx_evolve_rr(const qsx_rr_args* a, void* stream) {
+    if (!a) return fail(QSX_ERR_INVALID, "null args%s");
+    if (a->reg_bits < 0 || a->reg_bits > 4 || a->lane_bits < 0 || a->lane_bits > 5)
+        return fail(QSX_ERR_INVALID, "reg_bits must be 0..4 and lane_bits 0..5%s");
+    if (a->n_diag < 0 || a->n_diag > 2) return fail(QSX_ERR_INVALID, "n_diag must be 0, 1 or 2%s");
+    if (a->n_ops < 0 || a->n_ops > QSX_RR_MAX_OPS) return fail(QSX_ERR_INVALID, "too many operations%s");
+    if (a->n_obs < 0 || a->n_obs > QSX_RR_MAX_OBS) return fail(QSX_ERR_INVALID, "too many read-outs%s");
+    if (a->n_inst < 0 || a->n_steps < 0 || a->n_emit < 0) return fail(QSX_ERR_INVALID, "negative count%s");
+    if (!a->logical_index || !a->params || (a->n_inst > 0 && !a->sigma_in) || (a->n_emit > 0 && !a->emit_steps))
+        return fail(QSX_ERR_INVALID, "null table%s");
+    if (a->n_obs > 0 && (!a->obs_weights || !a->out_obs)) return fail(QSX_ERR_INVALID, "null read-out table%s");
+    rr::Params k;
+    k.a = *a;
+    k.E = 1 << (a->reg_bits + a->lane_bits);
+    k.team = 1 << a->lane_bits;
+    k.inst_per_cta = 32 / k.team;                 // one warp per CTA: spreads few instances over all SM sub-partitions
+    k.p_ops = a->param_stride - 2 * a->n_diag * k.E;
+    if (k.p_ops < 0) return fail(QSX_ERR_INVALID, "param_stride smaller than the diagonal tables%s");
+    for (int i = 0; i < a->n_ops; ++i) {
+        const qsx_rr_op& op = a->ops[i];
+        if (op.kind == QSX_RR_DIAG) {
+            if (op.aux0 < 0 || op.aux0 >= a->n_diag) return fail(QSX_ERR_INVALID, "bad diagonal table index%s");
+        } else if (op.kind == QSX_RR_ROT || op.kind == QSX_RR_AD) {
+            if (op.p < 2 * a->n_diag * k.E || op.p + 2 > a->param_stride || (op.p & 1))
+                return fail(QSX_ERR_INVALID, "bad parameter slot%s");
+            if (op.reg_xor < 0 || op.reg_xor >= (1 << a->reg_bits) || op.lane_xor < 0 || op.lane_xor >= k.team)
+                return fail(QSX_ERR_INVALID, "xor mask out of range%s");
+        } else {
+            return fail(QSX_ERR_INVALID, "unknown RR operation%s");
+        }
+    }
+    if (a->n_inst == 0 || a->n_emit == 0) return QSX_OK;
+    int sms = 0, smem_max = 0;
+    int32_t rc = device_limits(&sms, &smem_max);
+    if (rc) return rc;
+    size_t smem = (size_t)a->n_obs * k.E * sizeof(double2) + (size_t)k.inst_per_cta * ((k.p_ops + 1) & ~1) * sizeof(double) + 16;
+    if (smem > (size_t)smem_max) return fail(QSX_ERR_TOO_LARGE, "RR tables exceed shared memory%s");
+    int need = (a->n_inst + k.inst_per_cta - 1) / k.inst_per_cta;
+    int grid = sms * 16;
+    if (grid > need) grid = need;
+    {   // a program that equals a compile-time menu entry runs with its operation list as constants
+        bool launched = false;
+        QSX_CUDA(rr::launch_static<0>(k, grid, smem, (cudaStream_t)stream, &launched));
+        if (launched) return QSX_OK;
+    }
+    // the parameter slots of the ops are made relative to the op-parameter region held in shared memory
+    for (int i = 0; i < a->n_ops; ++i)
+        if (k.a.ops[i].kind != QSX_RR_DIAG) k.a.ops[i].p -= 2 * a->n_diag * k.E;
+#define QSX_RR_LAUNCH(R, ND)                                                                                        \
+    do {                                                                                                            \
+        QSX_CUDA(cudaFuncSetAttribute(rr::evolve_rr_kernel<R, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        rr::evolve_rr_kernel<R, ND><<<grid, 32, smem, (cudaStream_t)stream>>>(k);                                   \
+    } while (0)
+#define QSX_RR_ND(R)                                  \
+    do {                                              \
+        if (a->n_diag == 0) QSX_RR_LAUNCH(R, 0);      \
+        else if (a->n_diag == 1) QSX_RR_LAUNCH(R, 1); \
+        else QSX_RR_LAUNCH(R, 2);                     \
+    } while (0)
+    switch (a->reg_bits) {
+        case 0: QSX_RR_ND(0); break;
+        case 1: QSX_RR_ND(1); break;
+        case 2: QSX_RR_ND(2); break;
+        case 3: QSX_RR_ND(3); break;
+        default: QSX_RR_ND(4); break;
+    }
+#undef QSX_RR_ND
+#undef QSX_RR_LAUNCH
     QSX_CUDA(cudaGetLastError());
     return QSX_OK;
 }

@@ -11,10 +11,11 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libqsx.so')
-ABI_VERSION = 2
+ABI_VERSION = 5
 
 EXPORTS = ('qsx_abi_version', 'qsx_last_error', 'qsx_device_info', 'qsx_evolve_workspace_bytes', 'qsx_evolve',
-           'qsx_apply_dipole', 'qsx_fp64_peak')
+           'qsx_evolve_rr', 'qsx_apply_dipole', 'qsx_fp64_peak')
+RR_MAX_OPS, RR_MAX_OBS, RR_MAX_ENTRIES = 24, 8, 4
 
 
 class QsxError(RuntimeError):
@@ -49,6 +50,27 @@ class QsxEvolveArgs(C.Structure):
                 ('n_hop_ints', C.c_int32), ('hops', C.c_void_p)]
 
 
+class QsxRROp(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('reg_xor', C.c_int32), ('lane_xor', C.c_int32), ('reg_mask', C.c_uint32),
+                ('p', C.c_int32), ('sign', C.c_int32), ('aux0', C.c_int32), ('aux1', C.c_int32)]
+
+
+class QsxRRArgs(C.Structure):
+    _fields_ = [('reg_bits', C.c_int32), ('lane_bits', C.c_int32), ('n_diag', C.c_int32), ('n_ops', C.c_int32),
+                ('ops', QsxRROp * RR_MAX_OPS),
+                ('logical_index', C.c_void_p),
+                ('param_stride', C.c_int32), ('params', C.c_void_p),
+                ('n_inst', C.c_int32), ('inst_set', C.c_void_p), ('inst_src', C.c_void_p), ('sigma_in', C.c_void_p),
+                ('n_steps', C.c_int32), ('n_emit', C.c_int32), ('emit_steps', C.c_void_p),
+                ('n_obs', C.c_int32), ('obs_weights', C.c_void_p), ('obs_reg_mask', C.c_uint32 * RR_MAX_OBS),
+                ('n_entries', C.c_int32 * RR_MAX_OBS),
+                ('entry_reg_mask', (C.c_uint32 * RR_MAX_ENTRIES) * RR_MAX_OBS),
+                ('entry_lane_mask', (C.c_uint32 * RR_MAX_ENTRIES) * RR_MAX_OBS),
+                ('entry_weight', (C.c_double * RR_MAX_ENTRIES) * RR_MAX_OBS),
+                ('readout_kind', C.c_int32), ('mu', C.c_double * 16),
+                ('out_obs', C.c_void_p), ('obs_real', C.c_int32), ('out_snap', C.c_void_p)]
+
+
 _lib = None
 
 
@@ -69,6 +91,8 @@ def load():
     lib.qsx_evolve_workspace_bytes.restype = C.c_int64
     lib.qsx_evolve.argtypes = [C.POINTER(QsxEvolveArgs), C.c_void_p]
     lib.qsx_evolve.restype = C.c_int32
+    lib.qsx_evolve_rr.argtypes = [C.POINTER(QsxRRArgs), C.c_void_p]
+    lib.qsx_evolve_rr.restype = C.c_int32
     lib.qsx_apply_dipole.argtypes = [C.POINTER(QsxBlock), C.POINTER(QsxBlock), C.c_int32, C.c_void_p, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
     lib.qsx_apply_dipole.restype = C.c_int32

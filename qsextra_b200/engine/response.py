@@ -85,14 +85,14 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
             sharded, shard_units = True, n_global
         sigma = eng.apply_dipole(block, new_block, 0 if side == 'k' else 1, mu_dev, sigma)
         block, ka, kb = new_block, nka, nkb
-        dev = eng.upload_program(program.bind(block))
+        dev = eng.upload_program(program.bind(block), program)
         n_local = sigma.shape[0]
         emit = uniq[level]
         if level < len(plan) - 2:
             _, snap = eng.evolve(dev, sigma, n_local, int(emit.max()), emit, snapshots=True)
             sigma = snap.reshape(n_local * len(emit), block.size)
         else:
-            obs = eng.upload_observables(*block.emission_observable(np.asarray(mu, dtype=float)))
+            obs = eng.upload_observables(*block.emission_observable(np.asarray(mu, dtype=float)), kind='emission', mu=mu)
             out, _ = eng.evolve(dev, sigma, n_local, int(emit.max()), emit, obs=obs)
             out = out.reshape(n_local, len(emit))
         n_global *= len(emit)

@@ -1,0 +1,217 @@
+"""Map a lowered step program onto the register-resident kernel (include/qsx.h, qsx_rr_args) when the block is
+small and all its dimensions are powers of two.
+
+Index bits of an element a*DB + b (logical order, low to high):
+    bra pseudomode bits | bra configuration bits | ket pseudomode bits | ket configuration bits
+Placement: configuration bits always go to REGISTER bits (so that the conditions "site occupied" are uniform per
+register), then pseudomode (ket, bra) pairs while they fit; the remaining pseudomode bits live on the lanes of the team.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from .program import BoundProgram, Damp, StepProgram, _Diag, _Hop, _Prot
+from .sectors import Block, sector_rank
+
+RR_DIAG, RR_ROT, RR_AD = 0, 1, 2
+MAX_OPS, MAX_OBS = 24, 8
+
+
+@dataclass
+class RRProgram:
+    block: Block
+    reg_bits: int
+    lane_bits: int
+    n_diag: int
+    ops: np.ndarray             # [n_ops, 8] int32 (qsx_rr_op; reg_mask stored as uint32 bit pattern)
+    logical_index: np.ndarray   # [E] int32: physical -> logical
+    params: np.ndarray          # [B, stride] float64: n_diag tables (physical order) then the op parameters
+    labels: list
+
+    @property
+    def team(self):
+        return 1 << self.lane_bits
+
+    def observables(self, ptr, idx, w):
+        """CSR read-outs (logical indices) -> dense weights in physical order + per-read-out register masks."""
+        E = self.block.size
+        n_obs = len(ptr) - 1
+        phys_of = np.empty(E, dtype=np.int64)
+        phys_of[self.logical_index] = np.arange(E)
+        dense = np.zeros((n_obs, E), dtype=complex)
+        masks = np.zeros(n_obs, dtype=np.uint32)
+        nr = 1 << self.reg_bits
+        for o in range(n_obs):
+            for k in range(ptr[o], ptr[o + 1]):
+                ph = phys_of[idx[k]]
+                dense[o, ph] += w[k]
+                masks[o] |= np.uint32(1 << (ph % nr))
+        return dense, masks, self._factorise(dense)
+
+    def _factorise(self, dense, max_entries: int = 4):
+        """Read-outs as sums over (register mask x lane mask) pieces with one real weight each, or None."""
+        nr, team = 1 << self.reg_bits, 1 << self.lane_bits
+        out = []
+        for row in dense:
+            if np.any(row.imag != 0):
+                return None
+            grid = row.real.reshape(team, nr)
+            entries = []
+            for wgt in np.unique(grid[grid != 0]):
+                pattern = grid == wgt
+                groups = {}
+                for lane in range(team):
+                    rm = int(sum(1 << r for r in range(nr) if pattern[lane, r]))
+                    if rm:
+                        groups[rm] = groups.get(rm, 0) | (1 << lane)
+                entries += [(rm, lm, float(wgt)) for rm, lm in groups.items()]
+            if not entries or len(entries) > max_entries:
+                return None
+            out.append(entries)
+        return out
+
+
+def _log2(v: int):
+    return v.bit_length() - 1 if v > 0 and v & (v - 1) == 0 else None
+
+
+def eligible(program: StepProgram, block: Block, max_elements: int = 512) -> bool:
+    if _log2(block.n_a) is None or _log2(block.n_b) is None or block.size > max_elements:
+        return False
+    n_diag = 0
+    for op in program.lowered:
+        if isinstance(op, _Diag):
+            n_diag += 1
+        elif isinstance(op, (_Hop, Damp)):
+            continue
+        elif isinstance(op, _Prot):
+            if bin(op.xb).count('1') != 1 or op.zb != 0:
+                return False
+            if op.site >= 0 and np.any(op.plain + op.signed != 0):
+                return False                       # a rotation that also acts on an empty site
+        else:
+            return False
+    return n_diag <= 2
+
+
+def build(program: StepProgram, bound: BoundProgram, reg_bits: int | None = None) -> RRProgram | None:
+    block = bound.block
+    if not eligible(program, block):
+        return None
+    nb, cA, cB = block.n_bits, _log2(block.n_a), _log2(block.n_b)
+    n = 2 * nb + cA + cB
+    # logical bit numbers
+    bra_mode = list(range(nb))
+    bra_cfg = list(range(nb, nb + cB))
+    ket_mode = list(range(nb + cB, 2 * nb + cB))
+    ket_cfg = list(range(2 * nb + cB, n))
+    if reg_bits is None:
+        reg_bits = min(4 if max(cA, cB) <= 1 else 3, n)
+    reg_bits = min(reg_bits, n)
+    if cA + cB > reg_bits or n - reg_bits > 5:
+        return None
+    order = ket_cfg + bra_cfg                       # physical register bits, low to high
+    rest = []
+    for j in range(nb):
+        if len(order) + 2 <= reg_bits:
+            order += [ket_mode[j], bra_mode[j]]
+        else:
+            rest += [ket_mode[j], bra_mode[j]]
+    while len(order) < reg_bits and rest:
+        order.append(rest.pop(0))
+    order += rest                                   # positions >= reg_bits are lane bits
+    place = {lb: pos for pos, lb in enumerate(order)}
+    if max(cA, cB) >= 2 and reg_bits > 3:
+        return None
+    E, NR = block.size, 1 << reg_bits
+    phys = np.arange(E)
+    logical = np.zeros(E, dtype=np.int64)
+    for pos, lb in enumerate(order):
+        logical |= ((phys >> pos) & 1) << lb
+    DB = block.dim_b
+    a_of, b_of = logical // DB, logical % DB
+
+    def split(mask_logical_bits):
+        m = sum(1 << place[lb] for lb in mask_logical_bits)
+        return m & (NR - 1), m >> reg_bits
+
+    def reg_cfg_values(side):
+        """configuration index of every register (cfg bits are register bits)."""
+        bits = ket_cfg if side == 0 else bra_cfg
+        out = np.zeros(NR, dtype=np.int64)
+        for k, lb in enumerate(bits):
+            out |= ((np.arange(NR) >> place[lb]) & 1) << k
+        return out
+
+    B = bound.params.shape[0]
+    base = 0                                        # filled below: tables come first
+    tables, ops, labels = [], [], []
+    ranks = (sector_rank(block.n_sites, block.ka), sector_rank(block.n_sites, block.kb))
+    cfgs = (block.cfg_a, block.cfg_b)
+    lowered = program.lowered
+    slot_of = {}
+    cursor = 0
+    for idx, op in enumerate(lowered):             # recover parameter slots in the same order bind() assigned them
+        row = bound.ops[cursor]
+        slot_of[idx] = row
+        cursor += 1
+    n_diag = sum(isinstance(op, _Diag) for op in lowered)
+    shift = 2 * n_diag * E
+    for idx, op in enumerate(lowered):
+        row = slot_of[idx]
+        if isinstance(op, _Diag):
+            sa, sb, st = int(row[1]), int(row[2]), int(row[3])
+            ga = bound.params[:, sa:sa + 2 * block.dim_a].reshape(B, -1, 2) @ np.array([1, 1j])
+            gb = bound.params[:, sb:sb + 2 * block.dim_b].reshape(B, -1, 2) @ np.array([1, 1j])
+            w = ga[:, a_of] * gb[:, b_of].conj()
+            if st >= 0:
+                t = bound.params[:, st:st + block.n_a * block.n_b].reshape(B, block.n_a, block.n_b)
+                w = w * t[:, a_of >> nb, b_of >> nb]
+            ops.append([RR_DIAG, 0, 0, 0, 0, 1, len(tables), 0])
+            tables.append(np.stack([w.real, w.imag], axis=-1).reshape(B, -1))
+            labels.append('diag')
+        elif isinstance(op, _Hop):
+            slot = int(row[6])
+            flip = (1 << op.i) | (1 << op.j)
+            for side in (0, 1):
+                cfg_bits = ket_cfg if side == 0 else bra_cfg
+                regcfg = reg_cfg_values(side)
+                groups = {}
+                for p, mask in enumerate(cfgs[side]):
+                    if (mask >> op.i) & 1 and not (mask >> op.j) & 1:
+                        q = int(ranks[side][mask ^ flip])
+                        x = p ^ q
+                        groups.setdefault(x, set()).update((p, q))
+                for x, members in groups.items():
+                    rx, lx = split([cfg_bits[k] for k in range(len(cfg_bits)) if (x >> k) & 1])
+                    rmask = sum(1 << r for r in range(NR) if int(regcfg[r]) in members)
+                    ops.append([RR_ROT, rx, lx, rmask, shift + slot, 1 if side == 0 else -1, 0, 0])
+                    labels.append('hop{}({},{})'.format('kb'[side], op.i, op.j))
+        elif isinstance(op, _Prot):
+            slot = int(row[6]) + (2 if op.site >= 0 else 0)
+            j = op.xb.bit_length() - 1
+            for side in (0, 1):
+                rx, lx = split([(ket_mode if side == 0 else bra_mode)[j]])
+                regcfg = reg_cfg_values(side)
+                if op.site >= 0:
+                    rmask = sum(1 << r for r in range(NR) if (cfgs[side][int(regcfg[r])] >> op.site) & 1)
+                else:
+                    rmask = (1 << NR) - 1
+                if rmask:
+                    ops.append([RR_ROT, rx, lx, rmask, shift + slot, 1 if side == 0 else -1, 0, 0])
+                    labels.append('rot{}({})'.format('kb'[side], j))
+        elif isinstance(op, Damp):
+            slot = int(row[6])
+            pa, pb = place[ket_mode[op.bit]], place[bra_mode[op.bit]]
+            rx = (1 << pa if pa < reg_bits else 0) | (1 << pb if pb < reg_bits else 0)
+            la = 1 << (pa - reg_bits) if pa >= reg_bits else 0
+            lb = 1 << (pb - reg_bits) if pb >= reg_bits else 0
+            ops.append([RR_AD, rx, la | lb, 0, shift + slot, 1, la, lb])
+            labels.append('damp({})'.format(op.bit))
+    if len(ops) > MAX_OPS:
+        return None
+    params = np.concatenate(tables + [bound.params], axis=1) if tables else bound.params
+    return RRProgram(block, reg_bits, n - reg_bits, n_diag, np.array(ops, dtype=np.int64).astype(np.uint32).view(np.int32).reshape(-1, 8),
+                     logical.astype(np.int32), np.ascontiguousarray(params), labels)

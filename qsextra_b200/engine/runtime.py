@@ -63,8 +63,16 @@ class Engine:
         self.h2d_bytes += t.numel() * t.element_size()
         return t.to(self.device, non_blocking=True)
 
-    def upload_program(self, bound: BoundProgram):
-        """-> dict of device tensors for a bound program (ops + parameter sets)."""
+    def upload_program(self, bound: BoundProgram, program=None, use_rr: bool = True, reg_bits=None):
+        """-> dict of device tensors for a bound program (ops + parameter sets).  With ``program`` (the StepProgram
+        it was bound from) small power-of-two blocks are additionally mapped onto the register-resident kernel."""
+        rr_entries = {}
+        if program is not None and use_rr:
+            from . import rr as rr_mod
+            rrp = rr_mod.build(program, bound, reg_bits=reg_bits)
+            if rrp is not None:
+                rr_entries = dict(rr=rrp, rr_params=self.to_device(rrp.params, torch.float64),
+                                  logical=self.to_device(rrp.logical_index, torch.int32))
         dev = dict(block=self.device_block(bound.block),
                    ops=self.to_device(bound.ops, torch.int32),
                    params=self.to_device(bound.params, torch.float64),
@@ -76,11 +84,66 @@ class Engine:
                        tiles=self.to_device(bound.tiles if len(bound.tiles) else np.zeros(2, np.int32), torch.int32),
                        hops=self.to_device(bound.hops if len(bound.hops) else np.zeros(4, np.int32), torch.int32),
                        n_tile_ints=int(len(bound.tiles)), n_hop_ints=int(len(bound.hops)))
+        dev.update(rr_entries)
         return dev
 
-    def upload_observables(self, ptr, idx, w):
+    def upload_observables(self, ptr, idx, w, kind: str | None = None, mu=None):
+        """CSR read-outs -> device tables.  ``kind`` ('populations' | 'emission' with ``mu``) tells the engine what the
+        read-outs are, so that compile-time programs can use compile-time read-out masks."""
         return dict(n=len(ptr) - 1, ptr=self.to_device(ptr, torch.int32), idx=self.to_device(idx, torch.int32),
-                    w=self.to_device(np.asarray(w, dtype=np.complex128)))
+                    w=self.to_device(np.asarray(w, dtype=np.complex128)), host=(np.asarray(ptr), np.asarray(idx), np.asarray(w)),
+                    kind={'populations': 1, 'emission': 2}.get(kind, 0), mu=None if mu is None else np.asarray(mu, dtype=float))
+
+    def _evolve_rr(self, prog, sigma_in, n_inst, n_steps, emit, obs, obs_real, snapshots, inst_set, inst_src):
+        rrp = prog['rr']
+        E = rrp.block.size
+        n_emit = int(emit.numel())
+        out_obs = out_snap = None
+        args = cabi.QsxRRArgs()
+        args.reg_bits, args.lane_bits, args.n_diag, args.n_ops = rrp.reg_bits, rrp.lane_bits, rrp.n_diag, len(rrp.ops)
+        for i, row in enumerate(rrp.ops):
+            o = args.ops[i]
+            o.kind, o.reg_xor, o.lane_xor = int(row[0]), int(row[1]), int(row[2])
+            o.reg_mask = int(row[3]) & 0xffffffff
+            o.p, o.sign, o.aux0, o.aux1 = int(row[4]), int(row[5]), int(row[6]), int(row[7])
+        args.logical_index = prog['logical'].data_ptr()
+        args.param_stride, args.params = int(rrp.params.shape[1]), prog['rr_params'].data_ptr()
+        args.n_inst = n_inst
+        args.inst_set = None if inst_set is None else inst_set.data_ptr()
+        args.inst_src = None if inst_src is None else inst_src.data_ptr()
+        args.sigma_in = sigma_in.data_ptr()
+        args.n_steps, args.n_emit, args.emit_steps = int(n_steps), n_emit, emit.data_ptr()
+        if obs is not None:
+            key = ('rr', id(rrp))
+            if key not in obs:
+                dense, masks, entries = rrp.observables(*obs['host'])
+                obs[key] = (self.to_device(dense), masks, entries)
+            dense_dev, masks, entries = obs[key]
+            args.n_obs, args.obs_weights = obs['n'], dense_dev.data_ptr()
+            for i, m in enumerate(masks):
+                args.obs_reg_mask[i] = int(m)
+            args.readout_kind = obs.get('kind', 0)
+            if obs.get('mu') is not None:
+                for i, m in enumerate(obs['mu'][:16]):
+                    args.mu[i] = float(m)
+            if entries is not None:
+                for o, ents in enumerate(entries):
+                    args.n_entries[o] = len(ents)
+                    for e, (rm, lm, wgt) in enumerate(ents):
+                        args.entry_reg_mask[o][e], args.entry_lane_mask[o][e], args.entry_weight[o][e] = rm, lm, wgt
+            out_obs = torch.empty((n_inst, n_emit, obs['n']), dtype=torch.float64 if obs_real else torch.complex128,
+                                  device=self.device)
+            args.out_obs = out_obs.data_ptr()
+        args.obs_real = int(obs_real)
+        if snapshots:
+            out_snap = torch.empty((n_inst, n_emit, E), dtype=torch.complex128, device=self.device)
+            args.out_snap = out_snap.data_ptr()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            cabi.check(self.lib.qsx_evolve_rr(C.byref(args), C.c_void_p(stream)))
+        if n_inst > 0 and n_emit > 0:
+            self.launches += 1
+        return out_obs, out_snap
 
     # ---- kernels ------------------------------------------------------------------------------
     def evolve(self, prog: dict, sigma_in: torch.Tensor, n_inst: int, n_steps: int, emit_steps, obs: dict | None = None,
@@ -92,6 +155,8 @@ class Engine:
         emit = emit_steps if isinstance(emit_steps, torch.Tensor) else self.to_device(np.asarray(emit_steps), torch.int32)
         n_emit = int(emit.numel())
         assert sigma_in.dtype == torch.complex128 and sigma_in.is_contiguous() and sigma_in.numel() % E == 0
+        if 'rr' in prog and (obs is None or obs['n'] <= cabi.RR_MAX_OBS):
+            return self._evolve_rr(prog, sigma_in, n_inst, n_steps, emit, obs, obs_real, snapshots, inst_set, inst_src)
         out_obs = out_snap = None
         if obs is not None:
             out_obs = torch.empty((n_inst, n_emit, obs['n']), dtype=torch.float64 if obs_real else torch.complex128,

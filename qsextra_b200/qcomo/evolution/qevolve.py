@@ -120,14 +120,14 @@ def run_populations(batch: SystemBatch, psi: np.ndarray, program: StepProgram, s
     sectors = sorted(set().union(*[split_state_by_sector(n, psi[b]).keys() for b in range(B)]))
     for k in sectors:
         block = program.block(k, k)
-        dev = eng.upload_program(program.bind(block))
+        dev = eng.upload_program(program.bind(block), program)
         cfgs = np.array(sector_configs(n, k), dtype=np.int64)
         amp = psi[:, cfgs]                                             # [B, nA]
         sigma0 = np.zeros((B, block.dim_a, block.dim_b), dtype=complex)
         at = np.arange(len(cfgs)) << block.n_bits
         sigma0[:, at[:, None], at[None, :]] = amp[:, :, None] * amp.conj()[:, None, :]
         if readout == 'populations':
-            obs = eng.upload_observables(*population_observables(block))
+            obs = eng.upload_observables(*population_observables(block), kind='populations')
         else:
             obs = eng.upload_observables(*block.config_probability_observables())
         out, _ = eng.evolve(dev, eng.to_device(sigma0.reshape(B, -1)), B, int(steps.max()), emit, obs=obs,

@@ -220,3 +220,32 @@ def apply_pass_program(sigma, bound, set_index=0):
                         v = new
                 s[idx] = v
     return s.reshape(DA, DB)
+
+
+def apply_rr_program(sigma, rr, set_index=0):
+    """One step through an RRProgram (QSX_RR_* semantics of include/qsx.h) on the physical layout."""
+    from qsextra_b200.engine.rr import RR_AD, RR_DIAG, RR_ROT
+    E = rr.block.size
+    R, NR = rr.reg_bits, 1 << rr.reg_bits
+    P = rr.params[set_index]
+    v = sigma.reshape(-1)[rr.logical_index].copy()           # physical order
+    phys = np.arange(E)
+    reg, lane = phys & (NR - 1), phys >> R
+    for op in rr.ops:
+        kind, rx, lx, rmask, p, sign, aux0, aux1 = (int(x) for x in op)
+        rmask &= 0xffffffff
+        partner = ((lane ^ lx) << R) | (reg ^ rx)
+        if kind == RR_DIAG:
+            w = P[2 * aux0 * E: 2 * (aux0 + 1) * E].reshape(E, 2) @ [1, 1j]
+            v = v * w
+        elif kind == RR_ROT:
+            c, s = P[p], P[p + 1] * sign
+            active = ((rmask >> reg) & 1) == 1
+            v = np.where(active, c * v - 1j * s * v[partner], v)
+        elif kind == RR_AD:
+            c, s2 = P[p], P[p + 1]
+            nset = _popc(reg & rx) + ((lane & aux0) != 0) + ((lane & aux1) != 0)
+            v = np.where(nset == 0, v + s2 * v[partner], np.where(nset == 1, c * v, c * c * v))
+    out = np.empty(E, dtype=complex)
+    out[rr.logical_index] = v
+    return out.reshape(sigma.shape)

@@ -15,12 +15,17 @@ block = program.block(1, 1)
 sigma0 = torch.zeros((1, block.size), dtype=torch.complex128, device=eng.device); sigma0[0, 0] = 1.0
 inst_set = torch.arange(N_SETS, dtype=torch.int32, device=eng.device)
 inst_src = torch.zeros(N_SETS, dtype=torch.int32, device=eng.device)
-obs = eng.upload_observables(*population_observables(block))
-configs = [(None, None, 'ops')] + [(t, kb, 'passes') for t in (2, 4, 8, 16, 32) for kb in (1, 2)]
+obs = eng.upload_observables(*population_observables(block), kind='populations')
+configs = [(8, 1, 'passes')] + [(rb, None, 'rr') for rb in (3, 4)]
 ref = None
 for team, kb, kind in configs:
-    bound = program.bind(block, fused=(kind == 'passes'), team=team, kb=kb)
-    dev = eng.upload_program(bound)
+    if kind == 'rr':
+        bound = program.bind(block, fused=False)
+        dev = eng.upload_program(bound, program, reg_bits=team)
+        assert 'rr' in dev
+    else:
+        bound = program.bind(block, fused=(kind == 'passes'), team=team, kb=kb)
+        dev = eng.upload_program(bound)
     for emit_every in (True, False):
         emit = eng.to_device(np.arange(N_STEPS + 1) if emit_every else np.array([N_STEPS]), torch.int32)
         run = lambda: eng.evolve(dev, sigma0, N_SETS, N_STEPS, emit, obs=obs, obs_real=True, inst_set=inst_set, inst_src=inst_src)[0]
