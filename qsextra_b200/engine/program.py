@@ -524,7 +524,8 @@ def resolve_time_grid(time, dt, Trotter_number):
         dt, Trotter_number = dt_trotter, 1
     else:
         dt_trotter = dt / Trotter_number
-    times = [time] if np.isscalar(time) else list(time)
-    if not all(abs(t - np.round(t / dt) * dt) < 1e-10 for t in times):
+    times = np.atleast_1d(np.asarray(time, dtype=float))
+    counts = np.round(times / dt)
+    if not np.all(np.abs(times - counts * dt) < 1e-10):
         raise ValueError('Entries in time are not multiples of dt_collisions.')
-    return dt, dt_trotter, Trotter_number, np.round(np.array(times) / dt).astype(int)
+    return dt, dt_trotter, Trotter_number, counts.astype(int)

@@ -163,14 +163,14 @@ def build(program: StepProgram, bound: BoundProgram, reg_bits: int | None = None
         row = slot_of[idx]
         if isinstance(op, _Diag):
             sa, sb, st = int(row[1]), int(row[2]), int(row[3])
-            ga = bound.params[:, sa:sa + 2 * block.dim_a].reshape(B, -1, 2) @ np.array([1, 1j])
-            gb = bound.params[:, sb:sb + 2 * block.dim_b].reshape(B, -1, 2) @ np.array([1, 1j])
-            w = ga[:, a_of] * gb[:, b_of].conj()
+            ga = np.ascontiguousarray(bound.params[:, sa:sa + 2 * block.dim_a]).view(np.complex128)
+            gb = np.ascontiguousarray(bound.params[:, sb:sb + 2 * block.dim_b]).view(np.complex128)
+            w = ga[:, a_of] * gb.conj()[:, b_of]
             if st >= 0:
                 t = bound.params[:, st:st + block.n_a * block.n_b].reshape(B, block.n_a, block.n_b)
                 w = w * t[:, a_of >> nb, b_of >> nb]
             ops.append([RR_DIAG, 0, 0, 0, 0, 1, len(tables), 0])
-            tables.append(np.stack([w.real, w.imag], axis=-1).reshape(B, -1))
+            tables.append(np.ascontiguousarray(w).view(np.float64))
             labels.append('diag')
         elif isinstance(op, _Hop):
             slot = int(row[6])
@@ -212,6 +212,9 @@ def build(program: StepProgram, bound: BoundProgram, reg_bits: int | None = None
             labels.append('damp({})'.format(op.bit))
     if len(ops) > MAX_OPS:
         return None
-    params = np.concatenate(tables + [bound.params], axis=1) if tables else bound.params
+    params = np.empty((B, shift + bound.params.shape[1]))
+    for d, tab in enumerate(tables):
+        params[:, 2 * d * E: 2 * (d + 1) * E] = tab
+    params[:, shift:] = bound.params
     return RRProgram(block, reg_bits, n - reg_bits, n_diag, np.array(ops, dtype=np.int64).astype(np.uint32).view(np.int32).reshape(-1, 8),
                      logical.astype(np.int32), np.ascontiguousarray(params), labels)

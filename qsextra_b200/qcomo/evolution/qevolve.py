@@ -114,27 +114,31 @@ def run_populations(batch: SystemBatch, psi: np.ndarray, program: StepProgram, s
     n, B = batch.n_sites, batch.batch
     steps = np.asarray(step_counts, dtype=np.int32)
     width = n if readout == 'populations' else 2 ** n
-    total = torch.zeros((B, len(steps), width), dtype=torch.float64, device=eng.device)
+    total = None
     emit = eng.to_device(steps, torch.int32)
     inst_set = torch.arange(B, dtype=torch.int32, device=eng.device) if B > 1 else None
-    sectors = sorted(set().union(*[split_state_by_sector(n, psi[b]).keys() for b in range(B)]))
+    sectors = [k for k in range(n + 1) if np.any(psi[:, np.array(sector_configs(n, k), dtype=np.int64)] != 0)]
+    same_state = B > 1 and not np.any(psi != psi[0])                   # one initial block shared by every instance
+    inst_src = torch.zeros(B, dtype=torch.int32, device=eng.device) if same_state else None
     for k in sectors:
         block = program.block(k, k)
         dev = eng.upload_program(program.bind(block), program)
         cfgs = np.array(sector_configs(n, k), dtype=np.int64)
-        amp = psi[:, cfgs]                                             # [B, nA]
-        sigma0 = np.zeros((B, block.dim_a, block.dim_b), dtype=complex)
+        amp = psi[:1, cfgs] if same_state else psi[:, cfgs]            # [B or 1, nA]
+        sigma0 = np.zeros((amp.shape[0], block.dim_a, block.dim_b), dtype=complex)
         at = np.arange(len(cfgs)) << block.n_bits
         sigma0[:, at[:, None], at[None, :]] = amp[:, :, None] * amp.conj()[:, None, :]
         if readout == 'populations':
             obs = eng.upload_observables(*population_observables(block), kind='populations')
         else:
             obs = eng.upload_observables(*block.config_probability_observables())
-        out, _ = eng.evolve(dev, eng.to_device(sigma0.reshape(B, -1)), B, int(steps.max()), emit, obs=obs,
-                            obs_real=True, inst_set=inst_set)
+        out, _ = eng.evolve(dev, eng.to_device(sigma0.reshape(sigma0.shape[0], -1)), B, int(steps.max()), emit, obs=obs,
+                            obs_real=True, inst_set=inst_set, inst_src=inst_src)
         if readout == 'populations':
-            total += out
+            total = out if total is None else total + out
         else:
+            if total is None:
+                total = torch.zeros((B, len(steps), width), dtype=torch.float64, device=eng.device)
             total[:, :, torch.as_tensor(cfgs, device=eng.device)] += out
     return total if device_output else total.cpu().numpy()
 
