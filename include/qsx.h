@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define QSX_ABI_VERSION 5
+#define QSX_ABI_VERSION 6
 
 enum {
     QSX_OK = 0,
@@ -184,6 +184,10 @@ typedef struct qsx_rr_args {
      * 2 = emission trace Tr[(sum_s mu_s X_s) sigma] (n_obs = 1) with the dipole moments in `mu`. */
     int32_t readout_kind;
     double mu[16];
+    /* site-resolved pieces of that read-out (site s: registers site_reg_mask[s][e] on lanes site_lane_mask[s][e]);
+     * a compile-time program only uses its compile-time read-out masks when they equal these */
+    uint32_t site_reg_mask[16][QSX_RR_MAX_ENTRIES];
+    uint32_t site_lane_mask[16][QSX_RR_MAX_ENTRIES];
     double* out_obs;             /* DEVICE [n_inst][n_emit][n_obs] complex128 (or real parts if obs_real) */
     int32_t obs_real;
     double* out_snap;            /* DEVICE [n_inst][n_emit][E] complex128 in LOGICAL order, or NULL */

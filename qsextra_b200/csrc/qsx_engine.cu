@@ -15,6 +15,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "qsx.h"
 
@@ -887,7 +888,7 @@ int32_t qsx_evolve_rr(const qsx_rr_args* a, void* stream) {
     if (grid > need) grid = need;
     {   // a program that equals a compile-time menu entry runs with its operation list as constants
         bool launched = false;
-        QSX_CUDA(rr::launch_static<0>(k, grid, smem, (cudaStream_t)stream, &launched));
+        if (!getenv("QSX_RR_NO_STATIC")) QSX_CUDA(rr::launch_static<0>(k, grid, smem, (cudaStream_t)stream, &launched));
         if (launched) return QSX_OK;
     }
     // the parameter slots of the ops are made relative to the op-parameter region held in shared memory

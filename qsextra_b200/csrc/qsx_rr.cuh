@@ -444,6 +444,24 @@ bool matches_static(const qsx_rr_args& a) {
     return true;
 }
 
+// host: do the site-resolved read-out pieces sent by the caller equal the compile-time tables of PID?
+template <int PID, int RO>
+bool matches_static_readout(const qsx_rr_args& a) {
+    using SP = StaticProg<PID>;
+    constexpr int NS = RO == 1 ? SP::NPOP : SP::NEM, NE = RO == 1 ? SP::POPE : SP::EME;
+    for (int s = 0; s < 16; ++s)
+        for (int e = 0; e < QSX_RR_MAX_ENTRIES; ++e) {
+            unsigned rm = 0, lm = 0;
+            if (s < NS && e < NE) {
+                rm = RO == 1 ? SP::pop_reg[s < NS ? s : 0][e < NE ? e : 0] : SP::em_reg[s < NS ? s : 0][e < NE ? e : 0];
+                lm = RO == 1 ? SP::pop_lane[s < NS ? s : 0][e < NE ? e : 0] : SP::em_lane[s < NS ? s : 0][e < NE ? e : 0];
+            }
+            if (rm == 0) lm = 0;
+            if (a.site_reg_mask[s][e] != rm || a.site_lane_mask[s][e] != lm) return false;
+        }
+    return true;
+}
+
 template <int PID>
 cudaError_t launch_static(const Params& k, int grid, size_t smem, cudaStream_t stream, bool* launched) {
     if constexpr (PID >= kNumStaticProgs) {
@@ -462,10 +480,12 @@ cudaError_t launch_static(const Params& k, int grid, size_t smem, cudaStream_t s
         return cudaGetLastError();                                                                                    \
     } while (0)
             if constexpr (SP::NPOP > 0) {
-                if (k.a.readout_kind == 1 && k.a.n_obs == SP::NPOP && k.a.obs_real) QSX_RR_STATIC_LAUNCH(1);
+                if (k.a.readout_kind == 1 && k.a.n_obs == SP::NPOP && k.a.obs_real && matches_static_readout<PID, 1>(k.a))
+                    QSX_RR_STATIC_LAUNCH(1);
             }
             if constexpr (SP::NEM > 0) {
-                if (k.a.readout_kind == 2 && k.a.n_obs == 1 && !k.a.obs_real) QSX_RR_STATIC_LAUNCH(2);
+                if (k.a.readout_kind == 2 && k.a.n_obs == 1 && !k.a.obs_real && matches_static_readout<PID, 2>(k.a))
+                    QSX_RR_STATIC_LAUNCH(2);
             }
             QSX_RR_STATIC_LAUNCH(0);
 #undef QSX_RR_STATIC_LAUNCH

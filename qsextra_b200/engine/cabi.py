@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libqsx.so')
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 EXPORTS = ('qsx_abi_version', 'qsx_last_error', 'qsx_device_info', 'qsx_evolve_workspace_bytes', 'qsx_evolve',
            'qsx_evolve_rr', 'qsx_apply_dipole', 'qsx_fp64_peak')
@@ -68,6 +68,7 @@ class QsxRRArgs(C.Structure):
                 ('entry_lane_mask', (C.c_uint32 * RR_MAX_ENTRIES) * RR_MAX_OBS),
                 ('entry_weight', (C.c_double * RR_MAX_ENTRIES) * RR_MAX_OBS),
                 ('readout_kind', C.c_int32), ('mu', C.c_double * 16),
+                ('site_reg_mask', (C.c_uint32 * RR_MAX_ENTRIES) * 16), ('site_lane_mask', (C.c_uint32 * RR_MAX_ENTRIES) * 16),
                 ('out_obs', C.c_void_p), ('obs_real', C.c_int32), ('out_snap', C.c_void_p)]
 
 

@@ -50,6 +50,20 @@ class RRProgram:
                 masks[o] |= np.uint32(1 << (ph % nr))
         return dense, masks, self._factorise(dense)
 
+    def site_pieces(self, kind: int, n_sites: int):
+        """(register mask, lane mask) pieces per site of the two known read-outs (1: populations, 2: emission
+        trace), in the order the compile-time tables use (tools/gen_rr_programs.py), or None."""
+        from .sectors import population_observables
+        blk = self.block
+        if kind == 1 and blk.ka == blk.kb:
+            _, _, ent = self.observables(*population_observables(blk))
+            return None if ent is None else [sorted((rm, lm) for rm, lm, _ in e) for e in ent]
+        if kind == 2 and abs(blk.ka - blk.kb) == 1:
+            marks = np.arange(1, n_sites + 1, dtype=float)          # distinct weights identify the sites
+            _, _, ent = self.observables(*blk.emission_observable(marks))
+            return None if ent is None else [sorted((rm, lm) for rm, lm, w in ent[0] if w == marks[s]) for s in range(n_sites)]
+        return None
+
     def _factorise(self, dense, max_entries: int = 4):
         """Read-outs as sums over (register mask x lane mask) pieces with one real weight each, or None."""
         nr, team = 1 << self.reg_bits, 1 << self.lane_bits

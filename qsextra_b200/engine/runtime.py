@@ -6,6 +6,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -67,7 +68,7 @@ class Engine:
         """-> dict of device tensors for a bound program (ops + parameter sets).  With ``program`` (the StepProgram
         it was bound from) small power-of-two blocks are additionally mapped onto the register-resident kernel."""
         rr_entries = {}
-        if program is not None and use_rr:
+        if program is not None and use_rr and not os.environ.get('QSX_DISABLE_RR'):
             from . import rr as rr_mod
             rrp = rr_mod.build(program, bound, reg_bits=reg_bits)
             if rrp is not None:
@@ -123,6 +124,16 @@ class Engine:
             for i, m in enumerate(masks):
                 args.obs_reg_mask[i] = int(m)
             args.readout_kind = obs.get('kind', 0)
+            if args.readout_kind:
+                pkey = ('rr_sites', id(rrp))
+                if pkey not in obs:
+                    obs[pkey] = rrp.site_pieces(args.readout_kind, rrp.block.n_sites)
+                if obs[pkey] is None or any(len(p) > cabi.RR_MAX_ENTRIES for p in obs[pkey]):
+                    args.readout_kind = 0
+                else:
+                    for s_, pieces in enumerate(obs[pkey]):
+                        for e_, (rm, lm) in enumerate(pieces):
+                            args.site_reg_mask[s_][e_], args.site_lane_mask[s_][e_] = rm, lm
             if obs.get('mu') is not None:
                 for i, m in enumerate(obs['mu'][:16]):
                     args.mu[i] = float(m)

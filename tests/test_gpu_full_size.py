@@ -1,0 +1,115 @@
+"""GPU checks at BASELINE.json's FULL sizes through size-independent properties (the oracle only samples them):
+normalisation, linearity in the dipoles, sub-grid consistency (prefix sharing), gsb == se at t2 = 0, plus an
+oracle comparison on a corner of each grid."""
+import numpy as np
+import pytest
+
+from oracle import fast, reference_path as R
+from qsextra_b200 import ChromophoreSystem, ExcitonicSystem
+from qsextra_b200.engine.program import SystemBatch
+from qsextra_b200.qcomo import qevolve, qevolve_batch
+from qsextra_b200.spectroscopy import FeynmanDiagram, qspectroscopy
+
+pytestmark = pytest.mark.gpu
+HBAR = 0.658212
+DT = 0.1 / HBAR
+GAMMA = 59.08e-3
+
+
+def c2_batch(n_sets, seed=0):
+    rng = np.random.default_rng(seed)
+    eps = rng.uniform(1.4, 1.6, (n_sets, 2))
+    J = rng.uniform(-0.05, 0.05, n_sets)
+    omega = rng.uniform(0.01, 0.2, n_sets)
+    Gamma = rng.uniform(0.02, 0.1, n_sets)
+    Omega = rng.uniform(0.05, 0.2, n_sets)
+    coup = np.zeros((n_sets, 2, 2))
+    coup[:, 0, 1] = coup[:, 1, 0] = J
+    batch = SystemBatch(eps, coup, np.ones((n_sets, 2)), omega[:, None], np.sqrt(Gamma * Omega / 2)[:, None], (2,))
+    return batch, (2 * Omega)[:, None]
+
+
+def test_c1_markovian_dimer_200_steps(engine):
+    """BASELINE configs[0] in full against the oracle."""
+    s = ExcitonicSystem(energies=[1.55, 1.46], couplings=-0.01, dipole_moments=[1., 1.])
+    s.set_state('localized excitation', 0)
+    t = np.arange(201) * DT
+    res = qevolve(s, t, shots=0, dt=DT, coll_rates=GAMMA / 4, verbose=False)
+    ref = R.qevolve_exact(s, t, dt=DT, coll_rates=GAMMA / 4)
+    assert res.populations.shape == (201, 2)
+    assert np.abs(res.populations - ref['populations']).max() < 1e-10
+    assert np.abs(res.populations.sum(1) - 1).max() < 1e-12
+
+
+def test_c2_full_batch_properties_and_sampled_parity(engine):
+    """BASELINE configs[1] in full: 4096 parameter sets x 1000 steps."""
+    batch, rates = c2_batch(4096)
+    t = np.arange(1001) * DT
+    pops = qevolve_batch(batch, t, dt=DT, coll_rates=rates)
+    assert pops.shape == (4096, 1001, 2)
+    assert np.abs(pops.sum(-1) - 1).max() < 1e-11           # one exciton is conserved (pseudomode damping only)
+    assert pops.min() > -1e-13 and pops.max() < 1 + 1e-13
+    assert np.abs(pops[:, 0] - [1., 0.]).max() == 0
+    # parity on a sample of parameter sets against the C oracle (full-space literal gates)
+    pick = [0, 1, 2047, 4095]
+    systems, r = [], []
+    for b in pick:
+        s = ChromophoreSystem(energies=batch.energies[b].tolist(), couplings=float(batch.couplings[b, 0, 1]), dipole_moments=[1., 1.],
+                              frequencies_pseudomode=float(batch.omega[b, 0]), levels_pseudomode=2, couplings_ep=float(batch.coupl_ep[b, 0]))
+        s.set_state('localized excitation', 0)
+        systems.append(s)
+        r.append([float(rates[b, 0])])
+    ref, _ = fast.populations_batch(systems, t, dt=DT, coll_rates=np.array(r))
+    assert np.abs(pops[pick] - ref).max() < 1e-10
+    # idempotence: a second identical call returns identical bits; a sub-batch equals the slice of the batch
+    again = qevolve_batch(batch, t, dt=DT, coll_rates=rates)
+    assert np.array_equal(pops, again)
+    sub = SystemBatch(batch.energies[100:132], batch.couplings[100:132], batch.dipole_moments[100:132], batch.omega[100:132],
+                      batch.coupl_ep[100:132], (2,))
+    assert np.array_equal(qevolve_batch(sub, t, dt=DT, coll_rates=rates[100:132]), pops[100:132])
+
+
+def test_c3_dimer_2des_full_grid(engine):
+    """BASELINE configs[2]: 64 x 64 t1/t3 grid at t2 = 0, rephasing pathways."""
+    s = ExcitonicSystem(energies=[1.55, 1.46], couplings=-0.01, dipole_moments=[1., 0.8])
+    grid = (30 * DT * np.arange(64)).tolist()
+    kw = dict(dt=DT, coll_rates=GAMMA / 4)
+    sig = {lab: qspectroscopy(s, FeynmanDiagram(lab, [grid, [0.], grid]), verbose=False, **kw) for lab in ('gsb', 'se', 'esa')}
+    mu2 = 1. + 0.8 ** 2
+    assert abs(sig['gsb'][0, 0, 0] - mu2 ** 2) < 1e-12 and sig['gsb'].shape == (64, 1, 64)
+    assert np.abs(sig['gsb'] - sig['se']).max() < 1e-11           # identical at t2 = 0 for this model
+    # linearity: doubling every dipole multiplies a third-order response by 16
+    s2 = ExcitonicSystem(energies=[1.55, 1.46], couplings=-0.01, dipole_moments=[2., 1.6])
+    twice = qspectroscopy(s2, FeynmanDiagram('esa', [grid, [0.], grid]), verbose=False, **kw)
+    assert np.abs(twice - 16 * sig['esa']).max() < 1e-10 * np.abs(twice).max()
+    # sub-grid consistency (prefix sharing) and unsorted / repeated delays
+    pick1, pick3 = [5, 0, 63, 5], [7, 62, 1]
+    sub = qspectroscopy(s, FeynmanDiagram('esa', [[grid[i] for i in pick1], [0.], [grid[i] for i in pick3]]), verbose=False, **kw)
+    assert np.abs(sub - sig['esa'][np.ix_(pick1, [0], pick3)]).max() < 1e-12
+    # oracle on a corner
+    corner = [grid[i] for i in (0, 1, 2)]
+    for lab in ('gsb', 'esa'):
+        ref = R.qspectroscopy_operator(s, FeynmanDiagram(lab, [corner, [0.], corner]), **kw)
+        assert np.abs(sig[lab][:3, :, :3] - ref).max() < 1e-10 * np.abs(ref).max()
+
+
+def test_c4_chain_with_pseudomodes_reduced_grid(engine):
+    """BASELINE configs[3] geometry (4 sites, one pseudomode each) on a reduced grid: all block shapes of the full run
+    (16x64, 64x64, 16x16, 64x16, 96x64) through the shared-memory pass kernel, against the oracle on a corner."""
+    J = np.zeros((4, 4))
+    for i in range(3):
+        J[i, i + 1] = J[i + 1, i] = -0.01
+    s = ChromophoreSystem(energies=[1.55, 1.50, 1.46, 1.52], couplings=J, dipole_moments=[1., 0.9, 1.1, 1.],
+                          frequencies_pseudomode=0.02, levels_pseudomode=2, couplings_ep=float(np.sqrt(GAMMA * 0.1 / 2)))
+    kw = dict(dt=DT, coll_rates=[0.2])
+    t1 = (15 * DT * np.arange(6)).tolist()
+    t2 = (100 * DT * np.arange(2)).tolist()
+    sig = {lab: qspectroscopy(s, FeynmanDiagram(lab, [t1, t2, t1]), verbose=False, **kw) for lab in ('gsb', 'se', 'esa')}
+    mu2 = float(np.sum(np.array([1., 0.9, 1.1, 1.]) ** 2))
+    assert abs(sig['gsb'][0, 0, 0] - mu2 ** 2) < 1e-11
+    assert np.abs(sig['gsb'][:, 0, :] - sig['se'][:, 0, :]).max() < 1e-10
+    small = [0., 2 * DT]
+    for lab in ('gsb', 'se', 'esa'):
+        got = qspectroscopy(s, FeynmanDiagram(lab, [small, [0., 3 * DT], small]), verbose=False, **kw)
+        ref = R.qspectroscopy_operator(s, FeynmanDiagram(lab, [small, [0., 3 * DT], small]), **kw)
+        assert np.abs(got - ref).max() < 1e-10 * np.abs(ref).max()
