@@ -135,7 +135,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.QUERY,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except OSError:
             pass
@@ -165,6 +165,49 @@ class ClockSampler:
                     samples=len(sm), reasons=sorted(reasons))
 
 
+def spectroscopy_extras(world, rank, barrier):
+    """BASELINE metric part 1, '2DES grid points/sec': full C3 (dimer, 64 x 64, t2 = 0) and full C4 (4-site chain with
+    pseudomodes, 128 x 128 x 16) grids, three rephasing diagrams each, through the public qspectroscopy API (delay-grid
+    chains sharded over the ranks, one all-gather).  Wall-clock with synchronisation on both sides, max over ranks by the
+    barrier.  Reported next to the headline line; not part of the timed K steps."""
+    import warnings
+    import torch
+    from qsextra_b200 import ChromophoreSystem, ExcitonicSystem
+    from qsextra_b200.spectroscopy import FeynmanDiagram, qspectroscopy
+    gamma = 59.08e-3
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        dimer = ExcitonicSystem(energies=[1.55, 1.46], couplings=-0.01, dipole_moments=[1., 1.])
+        J = np.zeros((4, 4))
+        for i in range(3):
+            J[i, i + 1] = J[i + 1, i] = -0.01
+        chain = ChromophoreSystem(energies=[1.55, 1.50, 1.46, 1.52], couplings=J, dipole_moments=[1., 1., 1., 1.],
+                                  frequencies_pseudomode=0.02, levels_pseudomode=2, couplings_ep=float(np.sqrt(gamma * 0.1 / 2)))
+        configs = {'C3_dimer_64x1x64': (dimer, dict(dt=DT, coll_rates=gamma / 4),
+                                        [(30 * DT * np.arange(64)).tolist(), [0.], (30 * DT * np.arange(64)).tolist()]),
+                   'C4_chain4_pseudomodes_128x16x128': (chain, dict(dt=DT, coll_rates=[0.2]),
+                                                        [(15 * DT * np.arange(128)).tolist(), (100 * DT * np.arange(16)).tolist(),
+                                                         (15 * DT * np.arange(128)).tolist()])}
+        for name, (system, kw, delays) in configs.items():
+            try:
+                specs = [FeynmanDiagram(lab, delays) for lab in ('gsb', 'se', 'esa')]
+                if name.startswith('C3'):
+                    for sp in specs:
+                        qspectroscopy(system, sp, verbose=False, **kw)          # warm-up
+                barrier()
+                t0 = time.perf_counter()
+                sigs = [qspectroscopy(system, sp, verbose=False, **kw) for sp in specs]
+                barrier()
+                sec = time.perf_counter() - t0
+                points = 3 * int(np.prod([len(d) for d in delays]))
+                out[name] = dict(grid_points=points, seconds=sec, grid_points_per_s=points / sec,
+                                 checksum=float(sum(np.abs(s_).sum() for s_ in sigs)))
+            except Exception as exc:                                              # keep the headline line alive
+                out[name] = dict(error=repr(exc))
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -173,6 +216,7 @@ def run_ours(args):
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     from qsextra_b200.engine.program import StepProgram, SystemBatch
     from qsextra_b200.engine.runtime import get_engine
@@ -272,6 +316,8 @@ def run_ours(args):
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = e2e_iters * N_SETS * N_STEPS * world_was / float(t_e2e.item())
 
+    spectro = spectroscopy_extras(world, rank, barrier) if not args.no_spectroscopy else None
+
     if rank == 0:
         fp64_peak = eng.fp64_peak(5)
         peaks = {}
@@ -286,14 +332,19 @@ def run_ours(args):
         out_bytes = N_SETS * (N_STEPS + 1) * 2 * 8
         in_bytes = bound.params.nbytes + block.size * 16
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
-        cpu_value, cpu_threads, cpu_sec = cpu_sample(params, 128)
+        cpu_baseline = None
+        if world == 1:                                  # reported on rank 0 at N = 1 only
+            cpu_value, cpu_threads, cpu_sec = cpu_sample(params, 128)
+            cpu_baseline = dict(value=cpu_value, unit=UNIT, cores=cpu_threads, kind='port',
+                                sample='128 of 4096 parameter sets x 1000 steps, C oracle port '
+                                       '(full-space literal gates, OpenMP), %.1f s' % cpu_sec)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=total_ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                     dtype='f64', data='synthetic', config=workload_config(world),
                     clocks=clocks, gpu_launches=launches,
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(pinned.numel() * 8),
                              api='qsextra_b200.qcomo.qevolve_batch(SystemBatch of host arrays) -> pinned host tensor'),
-                    roofline=dict(bound='fp64', kernel='evolve_generic_kernel', achieved=achieved, peak=fp64_peak,
+                    roofline=dict(bound='fp64', kernel='rr::evolve_rr_static_kernel<0, 1> (register-resident, compile-time program)', achieved=achieved, peak=fp64_peak,
                                   unit='TFLOP/s', frac=achieved / fp64_peak if fp64_peak else None, traffic=None,
                                   peak_source='qsx_fp64_peak DFMA micro-benchmark measured in this run '
                                               '(MEASURED_PEAKS.json has no FP64 figure)',
@@ -302,10 +353,8 @@ def run_ours(args):
                                   hbm=dict(achieved=(in_bytes + out_bytes) / (per_launch_ms * 1e-3) / 1e9, peak=hbm_peak,
                                            unit='GB/s', algorithmic_bytes_per_launch=in_bytes + out_bytes,
                                            peak_source='MEASURED_PEAKS.json' if peaks else 'fallback')),
-                    cpu_baseline=dict(value=cpu_value, unit=UNIT, cores=cpu_threads, kind='port',
-                                      sample='128 of 4096 parameter sets x 1000 steps, C oracle port '
-                                             '(full-space literal gates, OpenMP), %.1f s' % cpu_sec),
-                    parity_max_abs_err_vs_oracle=parity, wall_s_timed_region=wall)
+                    cpu_baseline=cpu_baseline,
+                    parity_max_abs_err_vs_oracle=parity, wall_s_timed_region=wall, spectroscopy=spectro)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -314,9 +363,10 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-spectroscopy', action='store_true', help='skip the 2DES extras (C3 / C4 grid points per second)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
