@@ -83,7 +83,7 @@ def cpu_sample(params, n_sample, n_steps=N_STEPS):
     time_grid = np.arange(n_steps + 1) * DT
     fast.populations_batch(systems[:2], time_grid[:3], dt=DT, coll_rates=rates[:2])      # load + warm
     t0 = time.perf_counter()
-    _, threads = fast.populations_batch(systems, time_grid, dt=DT, coll_rates=rates)
+    _, threads = fast.populations_batch(systems, time_grid, dt=DT, coll_rates=rates, n_threads=os.cpu_count() or 1)
     sec = time.perf_counter() - t0
     return n_sample * n_steps / sec, threads, sec
 

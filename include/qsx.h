@@ -137,11 +137,13 @@ typedef struct qsx_evolve_args {
  *   QSX_RR_DIAG  v *= W[table aux0]                      (W per parameter set, physical order, complex128)
  *   QSX_RR_ROT   v <- c v - i sign s partner   on the registers in `reg_mask`   (hops and conditioned X-rotations;
  *                p -> {cos, sin}; the participation never depends on lane bits)
+ *   QSX_RR_ROTT  v <- v - i sign t partner, t = tan: the same rotation without its cos factor, which the host has
+ *                folded into the diagonal table of the step (scalars commute with every operation); p -> {cos, tan}
  *   QSX_RR_AD    amplitude damping of the bit pair (ket, bra) whose register part is reg_xor and whose lane parts are
  *                aux0 (ket lane mask) and aux1 (bra lane mask); p -> {cos phi, sin^2 phi}
  * Parameter set layout: n_diag tables of E complex128 (physical order) followed by the op parameters (slots p are
  * relative to the start of the set). */
-enum { QSX_RR_DIAG = 0, QSX_RR_ROT = 1, QSX_RR_AD = 2 };
+enum { QSX_RR_DIAG = 0, QSX_RR_ROT = 1, QSX_RR_AD = 2, QSX_RR_ROTT = 3 };
 #define QSX_RR_MAX_OPS 24
 #define QSX_RR_MAX_OBS 8
 #define QSX_RR_MAX_ENTRIES 4

@@ -868,7 +868,7 @@ int32_t qsx_evolve_rr(const qsx_rr_args* a, void* stream) {
         const qsx_rr_op& op = a->ops[i];
         if (op.kind == QSX_RR_DIAG) {
             if (op.aux0 < 0 || op.aux0 >= a->n_diag) return fail(QSX_ERR_INVALID, "bad diagonal table index%s");
-        } else if (op.kind == QSX_RR_ROT || op.kind == QSX_RR_AD) {
+        } else if (op.kind == QSX_RR_ROT || op.kind == QSX_RR_AD || op.kind == QSX_RR_ROTT) {
             if (op.p < 2 * a->n_diag * k.E || op.p + 2 > a->param_stride || (op.p & 1))
                 return fail(QSX_ERR_INVALID, "bad parameter slot%s");
             if (op.reg_xor < 0 || op.reg_xor >= (1 << a->reg_bits) || op.lane_xor < 0 || op.lane_xor >= k.team)

@@ -19,16 +19,22 @@ struct Params {
     int32_t E, team, inst_per_cta, p_ops;     // p_ops: doubles of op parameters per set (after the diagonal tables)
 };
 
-// v <- c v - i s p  (s already carries the ket/bra sign)
+// v <- c v - i s p  (s already carries the ket/bra sign).  TAN: v <- v - i t p (cos folded into the diagonal table).
+template <bool TAN>
 __device__ __forceinline__ void rot_one(double2& v, const double2 p, double c, double s) {
-    const double nx = fma(c, v.x, s * p.y), ny = fma(c, v.y, -s * p.x);
-    v.x = nx;
-    v.y = ny;
+    if (TAN) {
+        v.x = fma(s, p.y, v.x);
+        v.y = fma(-s, p.x, v.y);
+    } else {
+        const double nx = fma(c, v.x, s * p.y), ny = fma(c, v.y, -s * p.x);
+        v.x = nx;
+        v.y = ny;
+    }
 }
 
 // Hops and conditioned X-rotations.  The partner differs in the register bits op.reg_xor or in the lane bits
 // op.lane_xor; op.reg_mask lists the registers that take part (set for both members of an in-thread pair).
-template <int R>
+template <int R, bool TAN>
 __device__ __forceinline__ void op_rot(double2 (&v)[1 << R], const qsx_rr_op& op, double c, double s, unsigned wmask) {
     constexpr int NR = 1 << R;
     const unsigned am = op.reg_mask;
@@ -40,7 +46,7 @@ __device__ __forceinline__ void op_rot(double2 (&v)[1 << R], const qsx_rr_op& op
                 double2 p;
                 p.x = __shfl_xor_sync(wmask, v[r].x, op.lane_xor);
                 p.y = __shfl_xor_sync(wmask, v[r].y, op.lane_xor);
-                rot_one(v[r], p, c, s);
+                rot_one<TAN>(v[r], p, c, s);
             }
     } else if ((mr & (mr - 1)) == 0) {                  // single register bit: in-thread pairs, static indices
 #pragma unroll
@@ -50,8 +56,8 @@ __device__ __forceinline__ void op_rot(double2 (&v)[1 << R], const qsx_rr_op& op
                 for (int r = 0; r < NR; ++r)
                     if (!((r >> B) & 1) && ((am >> r) & 1)) {
                         const double2 x = v[r], y = v[r | (1 << B)];
-                        rot_one(v[r], y, c, s);
-                        rot_one(v[r | (1 << B)], x, c, s);
+                        rot_one<TAN>(v[r], y, c, s);
+                        rot_one<TAN>(v[r | (1 << B)], x, c, s);
                     }
             }
     } else if (R <= 3) {                                // several register bits (configuration index of N = 4)
@@ -64,7 +70,7 @@ __device__ __forceinline__ void op_rot(double2 (&v)[1 << R], const qsx_rr_op& op
             }
 #pragma unroll
         for (int r = 0; r < NR; ++r)
-            if ((am >> r) & 1) rot_one(v[r], p[r], c, s);
+            if ((am >> r) & 1) rot_one<TAN>(v[r], p[r], c, s);
     }
 }
 
@@ -235,7 +241,8 @@ __global__ void __launch_bounds__(32) evolve_rr_kernel(const Params k) {
                             }
                     } else {
                         const double2 cs = *reinterpret_cast<const double2*>(P + op.p);
-                        if (op.kind == QSX_RR_ROT) op_rot<R>(v, op, cs.x, op.sign > 0 ? cs.y : -cs.y, wmask);
+                        if (op.kind == QSX_RR_ROT) op_rot<R, false>(v, op, cs.x, op.sign > 0 ? cs.y : -cs.y, wmask);
+                        else if (op.kind == QSX_RR_ROTT) op_rot<R, true>(v, op, cs.x, op.sign > 0 ? cs.y : -cs.y, wmask);
                         else op_ad<R>(v, op, cs.x, cs.y, lt, wmask);
                     }
                 }
@@ -270,7 +277,9 @@ __device__ __forceinline__ void static_op(double2 (&v)[1 << StaticProg<PID>::R],
 #pragma unroll
         for (int r = 0; r < NR; ++r) v[r] = cmul(v[r], w[op.aux0][r]);
     } else if constexpr (op.kind == QSX_RR_ROT) {
-        op_rot<R>(v, op, cs[O].x, op.sign > 0 ? cs[O].y : -cs[O].y, wmask);
+        op_rot<R, false>(v, op, cs[O].x, op.sign > 0 ? cs[O].y : -cs[O].y, wmask);
+    } else if constexpr (op.kind == QSX_RR_ROTT) {
+        op_rot<R, true>(v, op, cs[O].x, op.sign > 0 ? cs[O].y : -cs[O].y, wmask);
     } else {
         op_ad<R>(v, op, cs[O].x, cs[O].y, lt, wmask);
     }

@@ -15,7 +15,7 @@ import numpy as np
 from .program import BoundProgram, Damp, StepProgram, _Diag, _Hop, _Prot
 from .sectors import Block, sector_rank
 
-RR_DIAG, RR_ROT, RR_AD = 0, 1, 2
+RR_DIAG, RR_ROT, RR_AD, RR_ROTT = 0, 1, 2, 3
 MAX_OPS, MAX_OBS = 24, 8
 
 
@@ -85,6 +85,29 @@ class RRProgram:
                 return None
             out.append(entries)
         return out
+
+
+def _fold_cosines(ops, params, E, NR, tables):
+    """Tangent form: G = cos(th) (1 - i tan(th) P).  The cos factors of all rotations of the step are multiplied into
+    the first diagonal table (element by element, following each rotation's participation mask -- scalars commute with
+    every operation of the step), and the rotations become QSX_RR_ROTT, two fused multiply-adds per element and side
+    instead of two multiplies and two.  Skipped when the step has no diagonal table or some |cos| < 0.5."""
+    rot = [op for op in ops if op[0] == RR_ROT]
+    if not tables or not rot:
+        return
+    slots = sorted({op[4] for op in rot})
+    if np.any(np.abs(params[:, slots]) < 0.5):
+        return
+    reg = np.arange(E) & (NR - 1)
+    scale = np.ones((params.shape[0], E))
+    for op in rot:
+        takes_part = ((op[3] >> reg) & 1).astype(bool)
+        scale[:, takes_part] *= params[:, op[4]][:, None]
+        op[0] = RR_ROTT
+    table = params[:, :2 * E].reshape(-1, E, 2)
+    table *= scale[:, :, None]
+    for slot in slots:
+        params[:, slot + 1] = params[:, slot + 1] / params[:, slot]
 
 
 def _log2(v: int):
@@ -230,5 +253,6 @@ def build(program: StepProgram, bound: BoundProgram, reg_bits: int | None = None
     for d, tab in enumerate(tables):
         params[:, 2 * d * E: 2 * (d + 1) * E] = tab
     params[:, shift:] = bound.params
+    _fold_cosines(ops, params, E, NR, tables)
     return RRProgram(block, reg_bits, n - reg_bits, n_diag, np.array(ops, dtype=np.int64).astype(np.uint32).view(np.int32).reshape(-1, 8),
                      logical.astype(np.int32), np.ascontiguousarray(params), labels)

@@ -224,7 +224,7 @@ def apply_pass_program(sigma, bound, set_index=0):
 
 def apply_rr_program(sigma, rr, set_index=0):
     """One step through an RRProgram (QSX_RR_* semantics of include/qsx.h) on the physical layout."""
-    from qsextra_b200.engine.rr import RR_AD, RR_DIAG, RR_ROT
+    from qsextra_b200.engine.rr import RR_AD, RR_DIAG, RR_ROT, RR_ROTT
     E = rr.block.size
     R, NR = rr.reg_bits, 1 << rr.reg_bits
     P = rr.params[set_index]
@@ -242,6 +242,10 @@ def apply_rr_program(sigma, rr, set_index=0):
             c, s = P[p], P[p + 1] * sign
             active = ((rmask >> reg) & 1) == 1
             v = np.where(active, c * v - 1j * s * v[partner], v)
+        elif kind == RR_ROTT:
+            t = P[p + 1] * sign
+            active = ((rmask >> reg) & 1) == 1
+            v = np.where(active, v - 1j * t * v[partner], v)
         elif kind == RR_AD:
             c, s2 = P[p], P[p + 1]
             nset = _popc(reg & rx) + ((lane & aux0) != 0) + ((lane & aux1) != 0)
