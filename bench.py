@@ -326,6 +326,18 @@ def run_ours(args):
         except OSError:
             pass
         f_step = algorithmic_flops_per_step(2, 1, block.size)
+        executed = None
+        if 'rr' in dev:
+            ex_flops, ex_instr = dev['rr'].executed_flops_per_step()
+            ex_tf = ex_flops * N_SETS * N_STEPS / (float(np.mean(kernel_ms)) * 1e-3) / 1e12
+            # FP64 pipe: 64 lanes per clock and SM; every DFMA / DMUL / DADD occupies one lane-slot
+            sm_clock = (clocks.get('sm_mhz') or 1965.0) * 1e6
+            pipe = ex_instr * N_SETS * N_STEPS / (float(np.mean(kernel_ms)) * 1e-3) / (64 * eng.sm_count * sm_clock)
+            executed = dict(flops_per_collision_step=ex_flops, fp64_instructions_per_collision_step=ex_instr,
+                            achieved=ex_tf, unit='TFLOP/s', frac_of_dfma_peak=ex_tf / fp64_peak if fp64_peak else None,
+                            fp64_pipe_utilisation_estimate=pipe,
+                            note='flops the register-resident kernel executes, counted from its operation list '
+                                 '(read-outs excluded); the SURVEY formula above counts the un-fused gate list')
         per_launch_flops = f_step * N_SETS * N_STEPS
         per_launch_ms = float(np.mean(kernel_ms))
         achieved = per_launch_flops / (per_launch_ms * 1e-3) / 1e12
@@ -349,7 +361,7 @@ def run_ours(args):
                                   peak_source='qsx_fp64_peak DFMA micro-benchmark measured in this run '
                                               '(MEASURED_PEAKS.json has no FP64 figure)',
                                   flops_per_collision_step=f_step, flops_per_launch=per_launch_flops,
-                                  kernel_ms_per_launch=per_launch_ms,
+                                  kernel_ms_per_launch=per_launch_ms, executed=executed,
                                   hbm=dict(achieved=(in_bytes + out_bytes) / (per_launch_ms * 1e-3) / 1e9, peak=hbm_peak,
                                            unit='GB/s', algorithmic_bytes_per_launch=in_bytes + out_bytes,
                                            peak_source='MEASURED_PEAKS.json' if peaks else 'fallback')),

@@ -50,6 +50,30 @@ class RRProgram:
                 masks[o] |= np.uint32(1 << (ph % nr))
         return dense, masks, self._factorise(dense)
 
+    def executed_flops_per_step(self):
+        """(FP64 flops, FP64 instructions) one instance executes per step in the register-resident kernels, counted
+        from the operation list: DIAG = complex multiply (2 DMUL + 2 DFMA); rotation on a participating element =
+        2 DFMA (tangent form) or 2 DMUL + 2 DFMA; damping = 2 DFMA + 6 DMUL per in-register quad, DMUL + DFMA per
+        component when the partner comes from another lane."""
+        E, nr = self.block.size, 1 << self.reg_bits
+        team = E // nr
+        flops = instr = 0
+        for op in self.ops:
+            kind, rx, lx, rmask = int(op[0]), int(op[1]), int(op[2]), int(op[3]) & 0xffffffff
+            if kind == RR_DIAG:
+                flops, instr = flops + 6 * E, instr + 4 * E
+            elif kind in (RR_ROT, RR_ROTT):
+                n = bin(rmask).count('1') * team
+                flops, instr = flops + (4 if kind == RR_ROTT else 6) * n, instr + (2 if kind == RR_ROTT else 4) * n
+            elif kind == RR_AD:
+                if lx == 0:
+                    flops, instr = flops + 10 * (E // 4), instr + 8 * (E // 4)
+                elif rx == 0:
+                    flops, instr = flops + 6 * E, instr + 4 * E
+                else:
+                    flops, instr = flops + 8 * (E // 2), instr + 6 * (E // 2)
+        return flops, instr
+
     def site_pieces(self, kind: int, n_sites: int):
         """(register mask, lane mask) pieces per site of the two known read-outs (1: populations, 2: emission
         trace), in the order the compile-time tables use (tools/gen_rr_programs.py), or None."""
@@ -88,25 +112,43 @@ class RRProgram:
 
 
 def _fold_cosines(ops, params, E, NR, tables):
-    """Tangent form: G = cos(th) (1 - i tan(th) P).  The cos factors of all rotations of the step are multiplied into
-    the first diagonal table (element by element, following each rotation's participation mask -- scalars commute with
-    every operation of the step), and the rotations become QSX_RR_ROTT, two fused multiply-adds per element and side
-    instead of two multiplies and two.  Skipped when the step has no diagonal table or some |cos| < 0.5."""
-    rot = [op for op in ops if op[0] == RR_ROT]
-    if not tables or not rot:
+    """Tangent form where it is exact (engine/fold.py): the cos factors of the foldable rotations are multiplied into
+    the first diagonal table, element by element following each rotation's participation mask, and those rotations
+    become QSX_RR_ROTT: two fused multiply-adds per element and side instead of two multiplies and two.
+    Skipped when the step has no diagonal table; rotations with some |cos| < 0.5 are never folded."""
+    from .fold import foldable, value_classes
+    if not tables or not any(op[0] == RR_ROT for op in ops):
         return
-    slots = sorted({op[4] for op in rot})
-    if np.any(np.abs(params[:, slots]) < 0.5):
+    phys = np.arange(E)
+    reg, lane = phys & (NR - 1), phys // NR
+    rot_idx = [k for k, op in enumerate(ops) if op[0] == RR_ROT]
+    cls_of = dict(zip(rot_idx, value_classes([params[:, ops[k][4]] for k in rot_idx])))
+    info = []
+    for k, op in enumerate(ops):
+        partner = ((lane ^ op[2]) * NR) | (reg ^ op[1])
+        if op[0] == RR_ROT:
+            ok = not np.any(np.abs(params[:, op[4]]) < 0.5)
+            info.append(dict(mixes=True, takes_part=((op[3] >> reg) & 1).astype(bool), partner=partner,
+                             cls=cls_of[k] if ok else None))
+        elif op[0] == RR_AD:
+            clear = ((reg & op[1]) == 0) & ((lane & op[6]) == 0) & ((lane & op[7]) == 0)
+            info.append(dict(mixes=True, takes_part=clear, partner=partner, cls=None))
+        else:
+            info.append(dict(mixes=False, takes_part=np.zeros(E, bool), partner=phys, cls=None))
+    fold = foldable(E, info)
+    if not fold:
         return
-    reg = np.arange(E) & (NR - 1)
+    folded_slots = {ops[k][4] for k in fold}
+    if folded_slots & {ops[k][4] for k in rot_idx if k not in fold}:
+        fold = {k for k in fold if ops[k][4] not in {ops[j][4] for j in rot_idx if j not in fold}}
+        folded_slots = {ops[k][4] for k in fold}
     scale = np.ones((params.shape[0], E))
-    for op in rot:
-        takes_part = ((op[3] >> reg) & 1).astype(bool)
-        scale[:, takes_part] *= params[:, op[4]][:, None]
-        op[0] = RR_ROTT
+    for k in fold:
+        scale[:, info[k]['takes_part']] *= params[:, ops[k][4]][:, None]
+        ops[k][0] = RR_ROTT
     table = params[:, :2 * E].reshape(-1, E, 2)
     table *= scale[:, :, None]
-    for slot in slots:
+    for slot in folded_slots:
         params[:, slot + 1] = params[:, slot + 1] / params[:, slot]
 
 

@@ -253,3 +253,41 @@ def apply_rr_program(sigma, rr, set_index=0):
     out = np.empty(E, dtype=complex)
     out[rr.logical_index] = v
     return out.reshape(sigma.shape)
+
+
+def apply_rrc_program(sigma, prog, set_index=0):
+    """One step through an RRCProgram (engine/rrc.py; kernel csrc/qsx_rrc.cuh) on the logical layout."""
+    from qsextra_b200.engine import rrc as K
+    blk = prog.block
+    nb, nA, nB = blk.n_bits, blk.n_a, blk.n_b
+    M = 1 << nb
+    P = prog.params[set_index]
+    v = sigma.reshape(nA, M, nB, M).transpose(0, 2, 1, 3).copy()            # [i][j][m_a][m_b]
+    n_w = 2 * nA * nB
+    w_cfg = P[:n_w].reshape(nA, nB, 2) @ [1, 1j]
+    gm_a = P[n_w:n_w + 2 * M].reshape(M, 2) @ [1, 1j]
+    gm_b = P[n_w + 2 * M:n_w + 4 * M].reshape(M, 2) @ [1, 1j]
+    m = np.arange(M)
+    for kind, a, b, mask, slot in prog.ops:
+        if kind == K.OP_DIAG:
+            v = v * w_cfg[:, :, None, None] * gm_a[None, None, :, None] * gm_b.conj()[None, None, None, :]
+            continue
+        c, t = P[slot], P[slot + 1]
+        if kind == K.OP_HOPK:                        # (cos, sin) form
+            x, y = v[a].copy(), v[b].copy()
+            v[a], v[b] = c * x - 1j * t * y, c * y - 1j * t * x
+        elif kind == K.OP_HOPB:
+            x, y = v[:, a].copy(), v[:, b].copy()
+            v[:, a], v[:, b] = c * x + 1j * t * y, c * y + 1j * t * x
+        elif kind == K.OP_ROTK:
+            rows = [i for i in range(nA) if (mask >> i) & 1]
+            v[rows] = v[rows] - 1j * t * v[rows][:, :, m ^ (1 << a), :]
+        elif kind == K.OP_ROTB:
+            cols = [j for j in range(nB) if (mask >> j) & 1]
+            v[:, cols] = v[:, cols] + 1j * t * v[:, cols][:, :, :, m ^ (1 << a)]
+        elif kind == K.OP_AD:
+            s2 = t
+            ha, hb = ((m >> a) & 1)[:, None], ((m >> a) & 1)[None, :]
+            partner = v[:, :, m ^ (1 << a), :][:, :, :, m ^ (1 << a)]
+            v = np.where((ha == 0) & (hb == 0), v + s2 * partner, np.where(ha != hb, c * v, c * c * v))
+    return v.transpose(0, 2, 1, 3).reshape(sigma.shape)
