@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define QSX_ABI_VERSION 6
+#define QSX_ABI_VERSION 7
 
 enum {
     QSX_OK = 0,
@@ -197,6 +197,32 @@ typedef struct qsx_rr_args {
 
 /* Same contract as qsx_evolve, for programs the host could map onto the register-resident form. */
 int32_t qsx_evolve_rr(const qsx_rr_args* args, void* stream);
+
+/* CTA-wide register-resident evolution of LARGE blocks of systems with one 2-level pseudomode per site (DESIGN.md,
+ * "RRC kernel").  Thread t of a CTA of 4^n_bits threads owns the configuration tile sigma[(i, m_a), (j, m_b)], i < nA,
+ * j < nB, of ONE pair of pseudomode states for the whole evolution; pseudomode rotations and damping exchange with the
+ * thread whose pair differs in one bit (pair), by warp shuffle or through a shared-memory buffer.  Only programs whose
+ * `signature` (engine/rrc.py: RRCProgram.signature) equals a compile-time entry of csrc/qsx_rrc_programs.inc can run;
+ * the call returns QSX_ERR_INVALID with "no compile-time program" otherwise and the caller uses qsx_evolve.
+ * Parameter set: Wcfg (nA*nB complex) | gmA (2^n_bits complex) | gmB (2^n_bits complex) | op parameters. */
+typedef struct qsx_rrc_args {
+    int32_t n_signature;
+    const int32_t* signature;    /* HOST */
+    int32_t param_stride;
+    const double* params;        /* DEVICE [n_sets][param_stride] */
+    int32_t n_inst;
+    const int32_t* inst_set;     /* DEVICE or NULL */
+    const int32_t* inst_src;     /* DEVICE or NULL */
+    const double* sigma_in;      /* DEVICE [n_src][DA*DB] complex128, logical order */
+    int32_t n_steps, n_emit;
+    const int32_t* emit_steps;   /* DEVICE */
+    int32_t emit_trace;          /* 1: out_obs[inst][emit] = Tr[(sum_s mu_s X_s) sigma] (complex128) */
+    double mu[16];
+    double* out_obs;             /* DEVICE [n_inst][n_emit] complex128 or NULL */
+    double* out_snap;            /* DEVICE [n_inst][n_emit][DA*DB] complex128, logical order, or NULL */
+} qsx_rrc_args;
+
+int32_t qsx_evolve_rrc(const qsx_rrc_args* args, void* stream);
 
 int32_t qsx_abi_version(void);
 

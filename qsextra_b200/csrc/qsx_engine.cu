@@ -588,6 +588,7 @@ __global__ void __launch_bounds__(256) evolve_kernel(const EvolveParams k) {
 
 }  // namespace (helpers above are shared with the register-resident kernel)
 #include "qsx_rr.cuh"
+#include "qsx_rrc.cuh"
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -915,6 +916,23 @@ int32_t qsx_evolve_rr(const qsx_rr_args* a, void* stream) {
 #undef QSX_RR_ND
 #undef QSX_RR_LAUNCH
     QSX_CUDA(cudaGetLastError());
+    return QSX_OK;
+}
+
+int32_t qsx_evolve_rrc(const qsx_rrc_args* a, void* stream) {
+    if (!a) return fail(QSX_ERR_INVALID, "null args%s");
+    if (a->n_signature <= 0 || !a->signature) return fail(QSX_ERR_INVALID, "missing program signature%s");
+    if (a->n_inst < 0 || a->n_steps < 0 || a->n_emit < 0) return fail(QSX_ERR_INVALID, "negative count%s");
+    if (!a->params || (a->n_inst > 0 && !a->sigma_in) || (a->n_emit > 0 && !a->emit_steps))
+        return fail(QSX_ERR_INVALID, "null table%s");
+    if (a->emit_trace && !a->out_obs) return fail(QSX_ERR_INVALID, "null read-out buffer%s");
+    if (a->n_inst == 0 || a->n_emit == 0) return QSX_OK;
+    int sms = 0, smem_max = 0;
+    int32_t rc = device_limits(&sms, &smem_max);
+    if (rc) return rc;
+    int r = rrc::launch<0>(*a, sms, smem_max, (cudaStream_t)stream);
+    if (r == 1) return fail(QSX_ERR_INVALID, "no compile-time program matches this block%s");
+    if (r < 0) return fail(QSX_ERR_CUDA, "CUDA error: %s", cudaGetErrorString((cudaError_t)(-r)));
     return QSX_OK;
 }
 

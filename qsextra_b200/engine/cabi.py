@@ -11,10 +11,10 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libqsx.so')
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 EXPORTS = ('qsx_abi_version', 'qsx_last_error', 'qsx_device_info', 'qsx_evolve_workspace_bytes', 'qsx_evolve',
-           'qsx_evolve_rr', 'qsx_apply_dipole', 'qsx_fp64_peak')
+           'qsx_evolve_rr', 'qsx_evolve_rrc', 'qsx_apply_dipole', 'qsx_fp64_peak')
 RR_MAX_OPS, RR_MAX_OBS, RR_MAX_ENTRIES = 24, 8, 4
 
 
@@ -72,6 +72,15 @@ class QsxRRArgs(C.Structure):
                 ('out_obs', C.c_void_p), ('obs_real', C.c_int32), ('out_snap', C.c_void_p)]
 
 
+class QsxRRCArgs(C.Structure):
+    _fields_ = [('n_signature', C.c_int32), ('signature', C.c_void_p),
+                ('param_stride', C.c_int32), ('params', C.c_void_p),
+                ('n_inst', C.c_int32), ('inst_set', C.c_void_p), ('inst_src', C.c_void_p), ('sigma_in', C.c_void_p),
+                ('n_steps', C.c_int32), ('n_emit', C.c_int32), ('emit_steps', C.c_void_p),
+                ('emit_trace', C.c_int32), ('mu', C.c_double * 16),
+                ('out_obs', C.c_void_p), ('out_snap', C.c_void_p)]
+
+
 _lib = None
 
 
@@ -94,6 +103,8 @@ def load():
     lib.qsx_evolve.restype = C.c_int32
     lib.qsx_evolve_rr.argtypes = [C.POINTER(QsxRRArgs), C.c_void_p]
     lib.qsx_evolve_rr.restype = C.c_int32
+    lib.qsx_evolve_rrc.argtypes = [C.POINTER(QsxRRCArgs), C.c_void_p]
+    lib.qsx_evolve_rrc.restype = C.c_int32
     lib.qsx_apply_dipole.argtypes = [C.POINTER(QsxBlock), C.POINTER(QsxBlock), C.c_int32, C.c_void_p, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
     lib.qsx_apply_dipole.restype = C.c_int32

@@ -86,6 +86,12 @@ class Engine:
                        hops=self.to_device(bound.hops if len(bound.hops) else np.zeros(4, np.int32), torch.int32),
                        n_tile_ints=int(len(bound.tiles)), n_hop_ints=int(len(bound.hops)))
         dev.update(rr_entries)
+        if program is not None and use_rr and not rr_entries and not os.environ.get('QSX_DISABLE_RRC'):
+            from . import rrc as rrc_mod
+            big = rrc_mod.build(program, bound)
+            if big is not None:
+                dev.update(rrc=big, rrc_params=self.to_device(big.params, torch.float64),
+                           rrc_signature=np.ascontiguousarray(big.signature()))
         return dev
 
     def upload_observables(self, ptr, idx, w, kind: str | None = None, mu=None):
@@ -94,6 +100,41 @@ class Engine:
         return dict(n=len(ptr) - 1, ptr=self.to_device(ptr, torch.int32), idx=self.to_device(idx, torch.int32),
                     w=self.to_device(np.asarray(w, dtype=np.complex128)), host=(np.asarray(ptr), np.asarray(idx), np.asarray(w)),
                     kind={'populations': 1, 'emission': 2}.get(kind, 0), mu=None if mu is None else np.asarray(mu, dtype=float))
+
+    def _evolve_rrc(self, prog, sigma_in, n_inst, n_steps, emit, obs, snapshots, inst_set, inst_src):
+        """CTA-wide register-resident kernel (compile-time programs only).  Returns None when no compile-time program
+        matches, so that the caller falls back to the shared-memory pass kernel."""
+        big = prog['rrc']
+        E = big.block.size
+        n_emit = int(emit.numel())
+        args = cabi.QsxRRCArgs()
+        sig = prog['rrc_signature']
+        args.n_signature, args.signature = int(sig.size), sig.ctypes.data
+        args.param_stride, args.params = int(big.params.shape[1]), prog['rrc_params'].data_ptr()
+        args.n_inst = n_inst
+        args.inst_set = None if inst_set is None else inst_set.data_ptr()
+        args.inst_src = None if inst_src is None else inst_src.data_ptr()
+        args.sigma_in = sigma_in.data_ptr()
+        args.n_steps, args.n_emit, args.emit_steps = int(n_steps), n_emit, emit.data_ptr()
+        out_obs = out_snap = None
+        if obs is not None:
+            args.emit_trace = 1
+            for i, m in enumerate(obs['mu'][:16]):
+                args.mu[i] = float(m)
+            out_obs = torch.empty((n_inst, n_emit, 1), dtype=torch.complex128, device=self.device)
+            args.out_obs = out_obs.data_ptr()
+        if snapshots:
+            out_snap = torch.empty((n_inst, n_emit, E), dtype=torch.complex128, device=self.device)
+            args.out_snap = out_snap.data_ptr()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.qsx_evolve_rrc(C.byref(args), C.c_void_p(stream))
+        if rc < 0 and b'no compile-time program' in self.lib.qsx_last_error():
+            return None
+        cabi.check(rc)
+        if n_inst > 0 and n_emit > 0:
+            self.launches += 1
+        return out_obs, out_snap
 
     def _evolve_rr(self, prog, sigma_in, n_inst, n_steps, emit, obs, obs_real, snapshots, inst_set, inst_src):
         rrp = prog['rr']
@@ -168,6 +209,11 @@ class Engine:
         assert sigma_in.dtype == torch.complex128 and sigma_in.is_contiguous() and sigma_in.numel() % E == 0
         if 'rr' in prog and (obs is None or obs['n'] <= cabi.RR_MAX_OBS):
             return self._evolve_rr(prog, sigma_in, n_inst, n_steps, emit, obs, obs_real, snapshots, inst_set, inst_src)
+        if prog.get('rrc') is not None and not obs_real and (obs is None or (obs.get('kind') == 2 and obs['n'] == 1)):
+            done = self._evolve_rrc(prog, sigma_in, n_inst, n_steps, emit, obs, snapshots, inst_set, inst_src)
+            if done is not None:
+                return done
+            prog['rrc'] = None                        # no compile-time program: remember and use the pass kernel
         out_obs = out_snap = None
         if obs is not None:
             out_obs = torch.empty((n_inst, n_emit, obs['n']), dtype=torch.float64 if obs_real else torch.complex128,
