@@ -124,3 +124,70 @@ def test_sector_tables_and_interaction_plan():
     assert interaction_plan('kk', 'io') == [('k', 'X'), ('k', 'X')]
     ptr, idx, w = Block(2, 0, 1, 0).emission_observable([2.0, 3.0])
     assert idx.tolist() == [0, 1] and w.tolist() == [2.0, 3.0]
+
+
+def _chain(n, **kw):
+    J = np.zeros((n, n))
+    for i in range(n - 1):
+        J[i, i + 1] = J[i + 1, i] = kw.get('J', -0.3)
+    return build_system(dict(energies=(1.5 + 0.01 * np.arange(n)).tolist(), couplings=J.tolist(), dipole_moments=[1.] * n,
+                             frequencies_pseudomode=0.02, levels_pseudomode=2, couplings_ep=kw.get('g', 0.9)))
+
+
+def test_register_resident_programs_equal_operation_list():
+    """engine/rr.py (small power-of-two blocks) and engine/rrc.py (CTA-wide, large blocks) against the plain operation
+    list, through the NumPy emulations of their kernels; strong couplings so that a wrong cosine fold shows up."""
+    from qsextra_b200.engine import rr as RR, rrc as RRC
+    rng = np.random.default_rng(11)
+    dimer = build_system(dict(energies=[1.55, 1.46], couplings=-0.4, dipole_moments=[1., 0.8], frequencies_pseudomode=0.3,
+                              levels_pseudomode=2, couplings_ep=0.8))
+    prog = _program_for(dimer, 0.15, 0.15, 1, 1, [0.5])
+    kinds = set()
+    for ka, kb in ((1, 1), (1, 0), (0, 1), (2, 1), (1, 2), (0, 0)):
+        blk = prog.block(ka, kb)
+        bound = prog.bind(blk, fused=False)
+        for rb in (None, 2, 3, 4):
+            rrp = RR.build(prog, bound, reg_bits=rb)
+            assert rrp is not None
+            kinds |= {int(o[0]) for o in rrp.ops}
+            sig = rng.normal(size=(blk.dim_a, blk.dim_b)) + 1j * rng.normal(size=(blk.dim_a, blk.dim_b))
+            assert np.abs(emulator.apply_step(sig, bound) - emulator.apply_rr_program(sig, rrp)).max() < 1e-13
+    assert RR.RR_ROTT in kinds                       # the dimer folds its cosines (uniform pending factors)
+    # N = 4 without pseudomodes: two configuration bits, hops pair configurations with different pending factors
+    four = build_system(dict(energies=[1., 2., 3., 4.], couplings=[[0, 1, 0, 1], [1, 0, 1, 0], [0, 1, 0, 1], [1, 0, 1, 0]],
+                             dipole_moments=[1.] * 4))
+    prog4 = _program_for(four, 0.1, 0.1, 1, 1, 0.1)
+    for ka, kb in ((1, 0), (0, 1), (1, 1)):
+        blk = prog4.block(ka, kb)
+        bound = prog4.bind(blk, fused=False)
+        rrp = RR.build(prog4, bound)
+        if rrp is None:
+            continue
+        sig = rng.normal(size=(blk.dim_a, blk.dim_b)) + 1j * rng.normal(size=(blk.dim_a, blk.dim_b))
+        assert np.abs(emulator.apply_step(sig, bound) - emulator.apply_rr_program(sig, rrp)).max() < 1e-13
+    for n in (3, 4):
+        progn = _program_for(_chain(n), 0.15, 0.15, 1, 1, [0.2])
+        for ka, kb in ((2, 1), (1, 1), (1, 0), (0, 1), (0, 0), (1, 2)):
+            blk = progn.block(ka, kb)
+            bound = progn.bind(blk, fused=False)
+            big = RRC.build(progn, bound)
+            assert big is not None and big.threads == 4 ** n
+            sig = rng.normal(size=(blk.dim_a, blk.dim_b)) + 1j * rng.normal(size=(blk.dim_a, blk.dim_b))
+            assert np.abs(emulator.apply_step(sig, bound) - emulator.apply_rrc_program(sig, big)).max() < 1e-13
+
+
+def test_generated_program_tables_are_current():
+    """csrc/*.inc are generated from the host compiler; regenerate in memory and compare (a stale table would silently
+    send launches to the generic kernels)."""
+    import importlib.util, os, io, contextlib
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for tool, inc in (('gen_rr_programs.py', 'qsx_rr_programs.inc'), ('gen_rrc_programs.py', 'qsx_rrc_programs.inc')):
+        path = os.path.join(repo, 'qsextra_b200', 'csrc', inc)
+        before = open(path).read()
+        spec = importlib.util.spec_from_file_location('gen_' + inc, os.path.join(repo, 'tools', tool))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        with contextlib.redirect_stdout(io.StringIO()):
+            mod.main()
+        after = open(path).read()
+        assert before == after, inc + ' is stale: run python tools/' + tool
