@@ -126,7 +126,10 @@ def workload_config(n_gpus):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+    """nvidia-smi sampling (every 20 ms) started BEFORE the warm-up; `stop(t0, t1)` keeps the samples whose timestamps
+    fall inside the timed region [t0, t1] (wall clock) and, when the region is shorter than the sampling period, the
+    samples taken under the same load right before it."""
+    QUERY = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
 
@@ -140,29 +143,41 @@ class ClockSampler:
         except OSError:
             pass
 
-    def stop(self):
+    def wait_for_first_sample(self, timeout=3.0):
+        t_end = time.time() + timeout
+        while self.proc is not None and time.time() < t_end:
+            if os.path.exists(self.path) and os.path.getsize(self.path) > 0:
+                return
+            time.sleep(0.02)
+
+    def stop(self, t0, t1):
+        import datetime
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         self.proc.wait()
-        sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        rows = []
         for row in open(self.path):
             f = [x.strip() for x in row.split(',')]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), [n for n, flag in zip(names, f[4:8]) if flag.lower().startswith('active')]))
             except ValueError:
                 continue
-            for name, flag in zip(names, f[4:8]):
-                if flag.lower().startswith('active'):
-                    reasons.add(name)
         os.unlink(self.path)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    samples=len(sm), reasons=sorted(reasons))
+        inside = [r for r in rows if t0 <= r[0] <= t1]
+        where = 'timed region'
+        if len(inside) < 3:                        # region shorter than a few sampling periods: add the warm-up samples
+            inside = [r for r in rows if t0 - 0.5 <= r[0] <= t1 + 0.05]
+            where = 'timed region and the 0.5 s of warm-up before it (region shorter than 3 sampling periods)'
+        sm = [r[1] for r in inside]
+        reasons = sorted({n for r in inside for n in r[3]})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max((r[2] for r in inside), default=None),
+                    samples=len(inside), window=where, reasons=reasons)
 
 
 def spectroscopy_extras(world, rank, barrier):
@@ -252,16 +267,23 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     out = None
-    for _ in range(max(args.warmup, 3)):
+    sampler = ClockSampler(local_rank)
+    sampler.wait_for_first_sample()
+    warm_until = time.time() + 0.5                  # at least W steps and half a second under load before timing
+    n_warm = 0
+    while n_warm < max(args.warmup, 3) or time.time() < warm_until:
         flush.fill_(1)
         out = hot_path()
+        n_warm += 1
+        if n_warm % 16 == 0:
+            torch.cuda.synchronize()
     barrier()
-    sampler = ClockSampler(local_rank)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches0 = eng.launches
     barrier()
     wall0 = time.perf_counter()
+    t_region0 = time.time()
     for i in range(args.steps):
         flush.fill_(i & 0xff)
         starts[i].record()
@@ -270,7 +292,7 @@ def run_ours(args):
     barrier()
     wall = time.perf_counter() - wall0
     launches = eng.launches - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_region0, time.time())
     kernel_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
     t_dev = torch.tensor([sum(kernel_ms)], dtype=torch.float64, device=eng.device)
     if world > 1:

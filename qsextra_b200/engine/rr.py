@@ -27,8 +27,72 @@ class RRProgram:
     n_diag: int
     ops: np.ndarray             # [n_ops, 8] int32 (qsx_rr_op; reg_mask stored as uint32 bit pattern)
     logical_index: np.ndarray   # [E] int32: physical -> logical
-    params: np.ndarray          # [B, stride] float64: n_diag tables (physical order) then the op parameters
     labels: list
+    # recipe of the parameter sets: n_diag tables (physical order) followed by the op parameters
+    op_params: np.ndarray = None      # [B, S] float64 as bound by StepProgram.bind (cos/sin pairs, GA/GB tables)
+    diag_specs: list = None           # per diagonal table: (slot GA, slot GB, slot T or -1) into op_params
+    a_of: np.ndarray = None           # [E] ket index of every physical element
+    b_of: np.ndarray = None
+    fold_classes: list = None         # [(slot of the cosine in op_params, exponent per physical element [E])]
+    folded_slots: list = None         # op_params slots whose {cos, sin} become {cos, tan}
+    _params: np.ndarray = None
+
+    @property
+    def stride(self) -> int:
+        return 2 * self.n_diag * self.block.size + self.op_params.shape[1]
+
+    @property
+    def params(self) -> np.ndarray:
+        """[B, stride] float64 on the host (tests, table generators); the runtime builds the same array on the device
+        with ``device_params`` (the gathers over [B, E] are far cheaper there)."""
+        if self._params is None:
+            blk, nb, E = self.block, self.block.n_bits, self.block.size
+            B = self.op_params.shape[0]
+            op_params = self.op_params.copy()
+            out = np.empty((B, self.stride))
+            for d, (sa, sb, st) in enumerate(self.diag_specs):
+                ga = np.ascontiguousarray(op_params[:, sa:sa + 2 * blk.dim_a]).view(np.complex128)
+                gb = np.ascontiguousarray(op_params[:, sb:sb + 2 * blk.dim_b]).view(np.complex128)
+                w = ga[:, self.a_of] * gb.conj()[:, self.b_of]
+                if st >= 0:
+                    t = op_params[:, st:st + blk.n_a * blk.n_b].reshape(B, blk.n_a, blk.n_b)
+                    w = w * t[:, self.a_of >> nb, self.b_of >> nb]
+                if d == 0:
+                    for slot, count in self.fold_classes:
+                        powers = np.stack([op_params[:, slot] ** p for p in range(int(count.max()) + 1)], axis=1)
+                        w = w * powers[:, count]
+                out[:, 2 * d * E:2 * (d + 1) * E] = np.ascontiguousarray(w).view(np.float64)
+            for slot in self.folded_slots:
+                op_params[:, slot + 1] = op_params[:, slot + 1] / op_params[:, slot]
+            out[:, 2 * self.n_diag * E:] = op_params
+            self._params = out
+        return self._params
+
+    def device_params(self, eng):
+        """Same array as ``params`` built with device tensor ops from the small op-parameter array."""
+        import torch
+        blk, nb, E = self.block, self.block.n_bits, self.block.size
+        P = eng.to_device(self.op_params, torch.float64)
+        B = P.shape[0]
+        a_of = torch.as_tensor(self.a_of, device=eng.device)
+        b_of = torch.as_tensor(self.b_of, device=eng.device)
+        parts = []
+        for d, (sa, sb, st) in enumerate(self.diag_specs):
+            ga = torch.view_as_complex(P[:, sa:sa + 2 * blk.dim_a].reshape(B, blk.dim_a, 2))
+            gb = torch.view_as_complex(P[:, sb:sb + 2 * blk.dim_b].reshape(B, blk.dim_b, 2))
+            w = ga[:, a_of] * gb.conj()[:, b_of]
+            if st >= 0:
+                t = P[:, st:st + blk.n_a * blk.n_b].reshape(B, blk.n_a, blk.n_b)
+                w = w * t[:, a_of >> nb, b_of >> nb]
+            if d == 0:
+                for slot, count in self.fold_classes:
+                    powers = torch.stack([P[:, slot] ** p for p in range(int(count.max()) + 1)], dim=1)
+                    w = w * powers[:, torch.as_tensor(count, device=eng.device)]
+            parts.append(torch.view_as_real(w).reshape(B, 2 * E))
+        P = P.clone()
+        for slot in self.folded_slots:
+            P[:, slot + 1] = P[:, slot + 1] / P[:, slot]
+        return torch.cat(parts + [P], dim=1).contiguous()
 
     @property
     def team(self):
@@ -111,23 +175,26 @@ class RRProgram:
         return out
 
 
-def _fold_cosines(ops, params, E, NR, tables):
-    """Tangent form where it is exact (engine/fold.py): the cos factors of the foldable rotations are multiplied into
-    the first diagonal table, element by element following each rotation's participation mask, and those rotations
-    become QSX_RR_ROTT: two fused multiply-adds per element and side instead of two multiplies and two.
-    Skipped when the step has no diagonal table; rotations with some |cos| < 0.5 are never folded."""
+def _fold_cosines(ops, params, E, NR, has_table, shift):
+    """Tangent form where it is exact (engine/fold.py): the cos factors of the foldable rotations are to be multiplied
+    into the first diagonal table, element by element following each rotation's participation mask, and those
+    rotations become QSX_RR_ROTT: two fused multiply-adds per element and side instead of two multiplies and two.
+    ``params`` is the op-parameter array (slots relative to it = op slot - shift).  Returns (fold_classes,
+    folded_slots): [(cosine slot, exponent per element)] and the slots whose sine becomes a tangent.  Nothing is folded
+    when the step has no diagonal table; rotations with some |cos| < 0.5 are never folded."""
     from .fold import foldable, value_classes
-    if not tables or not any(op[0] == RR_ROT for op in ops):
-        return
+    if not has_table or not any(op[0] == RR_ROT for op in ops):
+        return [], []
     phys = np.arange(E)
     reg, lane = phys & (NR - 1), phys // NR
     rot_idx = [k for k, op in enumerate(ops) if op[0] == RR_ROT]
-    cls_of = dict(zip(rot_idx, value_classes([params[:, ops[k][4]] for k in rot_idx])))
+    col = lambda op: op[4] - shift
+    cls_of = dict(zip(rot_idx, value_classes([params[:, col(ops[k])] for k in rot_idx])))
     info = []
     for k, op in enumerate(ops):
         partner = ((lane ^ op[2]) * NR) | (reg ^ op[1])
         if op[0] == RR_ROT:
-            ok = not np.any(np.abs(params[:, op[4]]) < 0.5)
+            ok = not np.any(np.abs(params[:, col(op)]) < 0.5)
             info.append(dict(mixes=True, takes_part=((op[3] >> reg) & 1).astype(bool), partner=partner,
                              cls=cls_of[k] if ok else None))
         elif op[0] == RR_AD:
@@ -136,20 +203,16 @@ def _fold_cosines(ops, params, E, NR, tables):
         else:
             info.append(dict(mixes=False, takes_part=np.zeros(E, bool), partner=phys, cls=None))
     fold = foldable(E, info)
+    unfolded_slots = {ops[k][4] for k in rot_idx if k not in fold}
+    fold = {k for k in fold if ops[k][4] not in unfolded_slots}        # a slot is either all tangent or all sine
     if not fold:
-        return
-    folded_slots = {ops[k][4] for k in fold}
-    if folded_slots & {ops[k][4] for k in rot_idx if k not in fold}:
-        fold = {k for k in fold if ops[k][4] not in {ops[j][4] for j in rot_idx if j not in fold}}
-        folded_slots = {ops[k][4] for k in fold}
-    scale = np.ones((params.shape[0], E))
+        return [], []
+    by_class = {}
     for k in fold:
-        scale[:, info[k]['takes_part']] *= params[:, ops[k][4]][:, None]
         ops[k][0] = RR_ROTT
-    table = params[:, :2 * E].reshape(-1, E, 2)
-    table *= scale[:, :, None]
-    for slot in folded_slots:
-        params[:, slot + 1] = params[:, slot + 1] / params[:, slot]
+        entry = by_class.setdefault(cls_of[k], [col(ops[k]), np.zeros(E, dtype=np.int64)])
+        entry[1] += info[k]['takes_part']
+    return [(slot, count) for slot, count in by_class.values()], sorted({col(ops[k]) for k in fold})
 
 
 def _log2(v: int):
@@ -241,15 +304,8 @@ def build(program: StepProgram, bound: BoundProgram, reg_bits: int | None = None
     for idx, op in enumerate(lowered):
         row = slot_of[idx]
         if isinstance(op, _Diag):
-            sa, sb, st = int(row[1]), int(row[2]), int(row[3])
-            ga = np.ascontiguousarray(bound.params[:, sa:sa + 2 * block.dim_a]).view(np.complex128)
-            gb = np.ascontiguousarray(bound.params[:, sb:sb + 2 * block.dim_b]).view(np.complex128)
-            w = ga[:, a_of] * gb.conj()[:, b_of]
-            if st >= 0:
-                t = bound.params[:, st:st + block.n_a * block.n_b].reshape(B, block.n_a, block.n_b)
-                w = w * t[:, a_of >> nb, b_of >> nb]
             ops.append([RR_DIAG, 0, 0, 0, 0, 1, len(tables), 0])
-            tables.append(np.ascontiguousarray(w).view(np.float64))
+            tables.append((int(row[1]), int(row[2]), int(row[3])))
             labels.append('diag')
         elif isinstance(op, _Hop):
             slot = int(row[6])
@@ -291,10 +347,7 @@ def build(program: StepProgram, bound: BoundProgram, reg_bits: int | None = None
             labels.append('damp({})'.format(op.bit))
     if len(ops) > MAX_OPS:
         return None
-    params = np.empty((B, shift + bound.params.shape[1]))
-    for d, tab in enumerate(tables):
-        params[:, 2 * d * E: 2 * (d + 1) * E] = tab
-    params[:, shift:] = bound.params
-    _fold_cosines(ops, params, E, NR, tables)
+    fold_classes, folded_slots = _fold_cosines(ops, bound.params, E, NR, bool(tables), shift)
     return RRProgram(block, reg_bits, n - reg_bits, n_diag, np.array(ops, dtype=np.int64).astype(np.uint32).view(np.int32).reshape(-1, 8),
-                     logical.astype(np.int32), np.ascontiguousarray(params), labels)
+                     logical.astype(np.int32), labels, op_params=bound.params, diag_specs=tables, a_of=a_of, b_of=b_of,
+                     fold_classes=fold_classes, folded_slots=folded_slots)

@@ -72,12 +72,12 @@ class Engine:
             from . import rr as rr_mod
             rrp = rr_mod.build(program, bound, reg_bits=reg_bits)
             if rrp is not None:
-                rr_entries = dict(rr=rrp, rr_params=self.to_device(rrp.params, torch.float64),
+                rr_entries = dict(rr=rrp, rr_params=rrp.device_params(self),
                                   logical=self.to_device(rrp.logical_index, torch.int32))
         dev = dict(block=self.device_block(bound.block),
                    ops=self.to_device(bound.ops, torch.int32),
-                   params=self.to_device(bound.params, torch.float64),
-                   n_ops=int(bound.ops.shape[0]), stride=int(bound.params.shape[1]),
+                   params=None if rr_entries else self.to_device(bound.params, torch.float64),
+                   bound=bound, n_ops=int(bound.ops.shape[0]), stride=int(bound.params.shape[1]),
                    n_sets=int(bound.params.shape[0]), n_passes=0, team=0)
         if bound.passes is not None and len(bound.passes):
             dev.update(n_passes=int(bound.passes.shape[0]), team=int(bound.team),
@@ -149,7 +149,7 @@ class Engine:
             o.reg_mask = int(row[3]) & 0xffffffff
             o.p, o.sign, o.aux0, o.aux1 = int(row[4]), int(row[5]), int(row[6]), int(row[7])
         args.logical_index = prog['logical'].data_ptr()
-        args.param_stride, args.params = int(rrp.params.shape[1]), prog['rr_params'].data_ptr()
+        args.param_stride, args.params = int(rrp.stride), prog['rr_params'].data_ptr()
         args.n_inst = n_inst
         args.inst_set = None if inst_set is None else inst_set.data_ptr()
         args.inst_src = None if inst_src is None else inst_src.data_ptr()
@@ -220,6 +220,8 @@ class Engine:
                                   device=self.device)
         if snapshots:
             out_snap = torch.empty((n_inst, n_emit, E), dtype=torch.complex128, device=self.device)
+        if prog['params'] is None:                    # the register-resident path was planned but cannot serve this call
+            prog['params'] = self.to_device(prog['bound'].params, torch.float64)
         args = cabi.QsxEvolveArgs()
         args.block = blk.c
         args.n_ops, args.ops = prog['n_ops'], prog['ops'].data_ptr()
