@@ -139,11 +139,20 @@ def spectroscopy_cases():
         'se_trimer_markov': (trimer, 'se', [[0., 2.], [1.], [0., 3.]], dict(dt=0.5, coll_rates=0.02)),
         'esa_trimer_trotter': (trimer, 'esa', [[1.], [0., 2.], [2.]], dict(dt=1.0, Trotter_number=2, coll_rates=0.02)),
         # non-rephasing pathways via hand-set sequences on the base class
+        # unequal dipoles: the emission / dipole weights of the two sites are distinguishable
+        'esa_dimer_unequal_mu': (dict(DIMER, dipole_moments=[1., 0.8]), 'esa', [t2s, [0., 30 / HBAR], t2s], mk),
+        'gsb_dimer_modes_unequal_mu': (dict(dimer_modes, dipole_moments=[0.7, 1.2]), 'gsb', [t2s, [5 / HBAR], t2s],
+                                       dict(dt=DT_FS, coll_rates=[0.2])),
+        'esa_dimer_modes_unequal_mu': (dict(dimer_modes, dipole_moments=[0.7, 1.2]), 'esa', [t2s, [5 / HBAR], t2s],
+                                       dict(dt=DT_FS, coll_rates=[0.2])),
         'custom_kkkk_dimer': (DIMER, ('kkkk', 'ioio'), [t2s, [0.], t2s], mk),
         'custom_kbbk_dimer': (DIMER, ('kbbk', 'iioo'), [t2s, [0.], t2s], mk),
         'custom_kbkk_dimer': (DIMER, ('kbkk', 'iiio'), [t2s, [0.], t2s], mk),
     }
+    only = [a for a in sys.argv[1:] if a.startswith('only=')]
     for name, (sysdef, label, delays, kw) in cases.items():
+        if only and name not in only[0][5:].split(','):
+            continue
         t0 = time.time()
         system = build(sysdef)
         if isinstance(label, tuple):
@@ -206,7 +215,7 @@ def structure_cases():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['structure', 'qevolve', 'classical', 'spectroscopy']
+    which = [a for a in sys.argv[1:] if not a.startswith('only=')] or ['structure', 'qevolve', 'classical', 'spectroscopy']
     if 'structure' in which:
         structure_cases()
     if 'qevolve' in which:
