@@ -4,17 +4,25 @@
 Same signature and checks.  The reference estimates <X> + i<Y> of the ketbra ancilla of every pathway circuit
 with ``shots`` samples; this implementation returns the exact expectation value those estimates converge to
 (``engine/response.py``), so ``shots`` only matters when it is falsy/positive in the reference sense: it is accepted
-and otherwise ignored.  ``checkpoint`` / ``restart_from_checkpoint`` are accepted; a whole grid is one batched
-computation here, so nothing is written between grid points.
+and otherwise ignored.
+
+Checkpoints keep the reference's file format (qspectroscopy.py:103-111, :185-190; tools.py:120-137): a folder
+``<uuid4 hex>/`` holding ``last_time_indices_number.npy`` and ``signal.npy``.  ``restart_from_checkpoint=<folder>`` of an
+interrupted REFERENCE run is honoured: the grid points it had finished (C-order positions <= the saved number) are kept
+from ``signal.npy``, the others are computed here; the folder is removed on success like the reference does.  A whole
+grid is one batched computation here, so ``checkpoint=True`` has nothing to save in between and only mimics the
+create/destroy of the folder.
 """
 from __future__ import annotations
 
+import os
 import warnings
 
 import numpy as np
 
 from ...system import ChromophoreSystem, ExcitonicSystem
 from ...tools.oracle import ending_sentence
+from ...tools.tools import create_checkpoint_folder, destroy_checkpoint_folder
 from ...engine.program import resolve_time_grid
 from ...engine.response import response_function
 from ...qcomo.evolution.qevolve import _program_for, _validate_rates, _validate_system
@@ -70,7 +78,20 @@ def qspectroscopy(system: ChromophoreSystem | ExcitonicSystem,
                          'delay and fails at zero delay).')
     counts, (dt, dt_trotter, trotter_number, _) = delay_step_counts(spectroscopy.delay_time, dt_in, trotter_in)
     program = _program_for(system, dt, dt_trotter, trotter_number, qevolve_kwds.get('Trotter_order', 1), coll_rates)
+    folder, kept, last = None, None, -1
+    if restart_from_checkpoint is not None and os.path.exists(restart_from_checkpoint):
+        folder = restart_from_checkpoint
+        last = int(np.load(os.path.join(folder, 'last_time_indices_number.npy')))
+        kept = np.load(os.path.join(folder, 'signal.npy'))
+    elif checkpoint:
+        folder = create_checkpoint_folder()
+        print(f'Checkpoint folder created ({folder})')
     signal = response_function(program, np.asarray(system.dipole_moments, dtype=float), spectroscopy.side_seq,
                                spectroscopy.direction_seq, counts)
+    if kept is not None and kept.shape == signal.shape and last >= 0:
+        flat, old = signal.reshape(-1), kept.reshape(-1)
+        flat[:last + 1] = old[:last + 1]             # grid points the interrupted run had already finished
+    if folder is not None:
+        destroy_checkpoint_folder(folder)
     ending_sentence(verbose)
     return signal

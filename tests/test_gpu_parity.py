@@ -92,3 +92,29 @@ def test_trimer_two_excitons_vs_oracle(engine):
     spec = FeynmanDiagram('esa', [[0., 2., 1.], [1., 0.], [0., 3., 3.]])
     kw = dict(dt=dt, coll_rates=[0.2])
     close(qspectroscopy(s, spec, verbose=False, **kw), R.qspectroscopy_operator(s, spec, **kw))
+
+
+def test_restart_from_reference_checkpoint(engine, tmp_path, monkeypatch):
+    """Wire-compat with an interrupted reference run (qspectroscopy.py:103-111, :185-190): finished grid points are
+    kept from signal.npy, the rest is computed, the folder is removed."""
+    import os
+    from qsextra_b200 import ExcitonicSystem
+    from qsextra_b200.spectroscopy import FeynmanDiagram
+    monkeypatch.chdir(tmp_path)
+    s = ExcitonicSystem(energies=[1.55, 1.46], couplings=-0.01, dipole_moments=[1., 1.])
+    dt = 0.1 / 0.658212
+    spec = FeynmanDiagram('gsb', [[0., 10 * dt], [0.], [0., 5 * dt, 10 * dt]])
+    kw = dict(dt=dt, coll_rates=59.08e-3 / 4)
+    full = qspectroscopy(s, spec, verbose=False, **kw)
+    os.mkdir('ckpt')
+    partial = np.zeros_like(full)
+    partial.reshape(-1)[:4] = 77.0 + 1j                      # what the "interrupted run" had stored for points 0..3
+    np.save('ckpt/signal.npy', partial)
+    np.save('ckpt/last_time_indices_number.npy', 3)
+    resumed = qspectroscopy(s, spec, verbose=False, restart_from_checkpoint='ckpt', **kw)
+    assert np.all(resumed.reshape(-1)[:4] == 77.0 + 1j)
+    close(resumed.reshape(-1)[4:], full.reshape(-1)[4:])
+    assert not os.path.exists('ckpt')
+    again = qspectroscopy(s, spec, verbose=False, checkpoint=True, **kw)
+    close(again, full)
+    assert [d for d in os.listdir('.') if os.path.isdir(d)] == []
