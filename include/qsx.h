@@ -232,7 +232,10 @@ const char* qsx_last_error(void);
 /* sm_count, max opt-in dynamic shared memory per block (bytes), compute capability major*10+minor. */
 int32_t qsx_device_info(int32_t* sm_count, int32_t* smem_optin, int32_t* cc);
 
-/* Scratch needed by qsx_evolve when a block does not fit shared memory (0 if it fits). */
+/* Scratch needed by qsx_evolve when a block does not fit shared memory (0 if it fits).  Such a block is evolved by the
+ * streaming path: sigma of one instance at a time lives in the scratch (L2 / HBM), every operation is one grid-wide
+ * sweep, and the emission schedule is followed on the device.  That path synchronises `stream` once (it reads the
+ * operation types back to decide how many sweeps to enqueue); everything else is enqueued. */
 int64_t qsx_evolve_workspace_bytes(const qsx_evolve_args* args);
 
 /* Batched collision-model evolution (replaces AerSimulator.run / Estimator.run, see file header). */

