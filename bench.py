@@ -379,7 +379,10 @@ def run_ours(args):
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(pinned.numel() * 8),
                              api='qsextra_b200.qcomo.qevolve_batch(SystemBatch of host arrays) -> pinned host tensor'),
                     roofline=dict(bound='fp64', kernel='rr::evolve_rr_static_kernel<0, 1> (register-resident, compile-time program)', achieved=achieved, peak=fp64_peak,
-                                  unit='TFLOP/s', frac=achieved / fp64_peak if fp64_peak else None, traffic=None,
+                                  unit='TFLOP/s', frac=achieved / fp64_peak if fp64_peak else None,
+                                  traffic=18869000, traffic_source='dram__bytes_read.sum + dram__bytes_write.sum of one launch '
+                                  'in profiles/r1_c2_static_rr_kernel.md (ncu --set full); most of the 65.6 MB of read-outs is '
+                                  'still in L2 when the kernel ends',
                                   peak_source='qsx_fp64_peak DFMA micro-benchmark measured in this run '
                                               '(MEASURED_PEAKS.json has no FP64 figure)',
                                   flops_per_collision_step=f_step, flops_per_launch=per_launch_flops,

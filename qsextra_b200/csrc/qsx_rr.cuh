@@ -350,34 +350,46 @@ __device__ __forceinline__ void em_all(const double2 (&v)[1 << StaticProg<PID>::
     (em_site<PID, Ss>(v, lt, a.mu[Ss], re, im, std::make_integer_sequence<int, StaticProg<PID>::EME>{}), ...);
 }
 
+// Static read-outs are split in two so that the team reduction of emission t overlaps the arithmetic of step t+1:
+// `partial` leaves one per-lane partial sum per read-out in `pend`; `flush` (branch-free: it runs at the start of every
+// step, the compiler interleaves its shuffles with the step's independent FP64 work) reduces over the team and stores.
 template <int PID, int RO>
-__device__ __forceinline__ void emit_static(const double2 (&v)[1 << StaticProg<PID>::R], const qsx_rr_args& a, int lt,
-                                            bool valid, int inst, int slot) {
+struct Pending {
+    static constexpr int N = RO == 1 ? StaticProg<PID>::NPOP : 2;
+    double val[N > 0 ? N : 1];
+    long long at;            // index of the first output value, or -1
+};
+
+template <int PID, int RO>
+__device__ __forceinline__ void emit_partial(const double2 (&v)[1 << StaticProg<PID>::R], const qsx_rr_args& a, int lt,
+                                             Pending<PID, RO>& pend) {
     using SP = StaticProg<PID>;
-    constexpr int TEAM = 1 << SP::L;
     if constexpr (RO == 1) {
-        double p[SP::NPOP];
-        pop_all<PID>(v, lt, p, std::make_integer_sequence<int, SP::NPOP>{});
-#pragma unroll
-        for (int off = TEAM >> 1; off; off >>= 1)
-#pragma unroll
-            for (int o = 0; o < SP::NPOP; ++o) p[o] += __shfl_xor_sync(0xffffffffu, p[o], off);
-        if (lt == 0 && valid) {
-            double* dst = a.out_obs + ((size_t)inst * a.n_emit + slot) * SP::NPOP;
-#pragma unroll
-            for (int o = 0; o < SP::NPOP; ++o) dst[o] = p[o];
-        }
+        pop_all<PID>(v, lt, pend.val, std::make_integer_sequence<int, SP::NPOP>{});
     } else {
-        double re = 0.0, im = 0.0;
-        em_all<PID>(v, lt, a, re, im, std::make_integer_sequence<int, SP::NEM>{});
-#pragma unroll
-        for (int off = TEAM >> 1; off; off >>= 1) {
-            re += __shfl_xor_sync(0xffffffffu, re, off);
-            im += __shfl_xor_sync(0xffffffffu, im, off);
-        }
-        if (lt == 0 && valid)
-            reinterpret_cast<double2*>(a.out_obs)[(size_t)inst * a.n_emit + slot] = make_double2(re, im);
+        pend.val[0] = 0.0;
+        pend.val[1] = 0.0;
+        em_all<PID>(v, lt, a, pend.val[0], pend.val[1], std::make_integer_sequence<int, SP::NEM>{});
     }
+}
+
+template <int PID, int RO>
+__device__ __forceinline__ void emit_flush(const qsx_rr_args& a, int lt, Pending<PID, RO>& pend) {
+    constexpr int TEAM = 1 << StaticProg<PID>::L, N = Pending<PID, RO>::N;
+#pragma unroll
+    for (int off = TEAM >> 1; off; off >>= 1)
+#pragma unroll
+        for (int o = 0; o < N; ++o) pend.val[o] += __shfl_xor_sync(0xffffffffu, pend.val[o], off);
+    if (lt == 0 && pend.at >= 0) {
+        double* dst = a.out_obs + pend.at;
+        if constexpr (N == 2) {
+            *reinterpret_cast<double2*>(dst) = make_double2(pend.val[0], pend.val[1]);    // 16-byte aligned: at is even
+        } else {
+#pragma unroll
+            for (int o = 0; o < N; ++o) dst[o] = pend.val[o];
+        }
+    }
+    pend.at = -1;
 }
 
 template <int PID, int RO>
@@ -421,11 +433,22 @@ __global__ void __launch_bounds__(32) evolve_rr_static_kernel(const Params k) {
         int slot = 0;
         int next_emit = a.n_emit > 0 ? a.emit_steps[0] : -1;
         int after_next = a.n_emit > 1 ? a.emit_steps[1] : -1;      // schedule is read one emission ahead
+        Pending<PID, RO> pend;
+        pend.at = -1;
+#pragma unroll
+        for (int o = 0; o < Pending<PID, RO>::N; ++o) pend.val[o] = 0.0;
         for (int step = 0; step <= a.n_steps && slot < a.n_emit; ++step) {
-            if (step) static_step<PID>(v, w, cs, lt, wmask, std::make_integer_sequence<int, SP::NOPS>{});
+            if (step) {
+                if constexpr (RO != 0) emit_flush<PID, RO>(a, lt, pend);          // read-out of the previous emission
+                static_step<PID>(v, w, cs, lt, wmask, std::make_integer_sequence<int, SP::NOPS>{});
+            }
             if (step == next_emit) {
-                if constexpr (RO == 0) emit_generic<R>(v, a, obs_w, E, phys0, lt, TEAM, valid, inst, slot);
-                else emit_static<PID, RO>(v, a, lt, valid, inst, slot);
+                if constexpr (RO == 0) {
+                    emit_generic<R>(v, a, obs_w, E, phys0, lt, TEAM, valid, inst, slot);
+                } else {
+                    emit_partial<PID, RO>(v, a, lt, pend);
+                    pend.at = valid ? ((long long)inst * a.n_emit + slot) * Pending<PID, RO>::N : -1;
+                }
                 if (a.out_snap && valid) {
                     double2* dst = reinterpret_cast<double2*>(a.out_snap) + ((size_t)inst * a.n_emit + slot) * E;
 #pragma unroll
@@ -436,6 +459,7 @@ __global__ void __launch_bounds__(32) evolve_rr_static_kernel(const Params k) {
                 after_next = slot + 1 < a.n_emit ? a.emit_steps[slot + 1] : -1;
             }
         }
+        if constexpr (RO != 0) emit_flush<PID, RO>(a, lt, pend);
     }
 }
 

@@ -16,7 +16,7 @@ sigma0 = torch.zeros((1, block.size), dtype=torch.complex128, device=eng.device)
 inst_set = torch.arange(N_SETS, dtype=torch.int32, device=eng.device)
 inst_src = torch.zeros(N_SETS, dtype=torch.int32, device=eng.device)
 obs = eng.upload_observables(*population_observables(block), kind='populations')
-configs = [(8, 1, 'passes')] + [(rb, None, 'rr') for rb in (3, 4)]
+configs = [(rb, None, 'rr') for rb in (2, 3, 4)]
 ref = None
 for team, kb, kind in configs:
     if kind == 'rr':
