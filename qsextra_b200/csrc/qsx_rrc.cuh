@@ -37,8 +37,15 @@ struct Geo {
         return need;
     }
     static constexpr int BUF = buffer_elems();
+    // Exchanges only involve the two warps whose index differs in one warp bit (or one warp, for lane bits), so they
+    // synchronise pairwise with named barriers.  Each warp bit (plus one slot for exchanges inside a warp) owns two
+    // buffers used alternately: a warp can then never overwrite data its partner of an earlier exchange still reads.
+    static constexpr int NWB = 2 * NBITS > 5 ? 2 * NBITS - 5 : 0;       // warp bits
+    static constexpr int NGROUP = NWB + 1;
+    static constexpr int PAIRS = NWB > 0 ? 1 << (NWB - 1) : 1;
     static constexpr size_t smem_bytes(int p_doubles) {
-        return (size_t)2 * BUF * sizeof(double2) + (size_t)((p_doubles + 1) & ~1) * sizeof(double) + 64 * sizeof(double2);
+        return (size_t)2 * NGROUP * BUF * sizeof(double2) + (size_t)((p_doubles + 1) & ~1) * sizeof(double) +
+               64 * sizeof(double2);
     }
 };
 
@@ -57,10 +64,22 @@ __device__ __forceinline__ void tan_one(double2& v, const double2 p, double t) {
 
 __device__ __forceinline__ int remove_bit(int v, int pos) { return ((v >> (pos + 1)) << pos) | (v & ((1 << pos) - 1)); }
 
+// synchronise the threads that exchange through thread bit POS: one warp (lane bit) or a pair of warps (warp bit)
+template <int PID, int POS>
+__device__ __forceinline__ void pair_sync(int tid) {
+    if constexpr (POS < 5) {
+        __syncwarp();
+    } else {
+        constexpr int kk = POS - 5;
+        const int id = 1 + kk * Geo<PID>::PAIRS + remove_bit(tid >> 5, kk);
+        asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+    }
+}
+
 template <int PID, int O>
 __device__ __forceinline__ void big_op(double2 (&v)[BigProg<PID>::NA][BigProg<PID>::NB],
                                        const double2 (&w)[BigProg<PID>::NA][BigProg<PID>::NB], const double* P,
-                                       double2* xbuf, int& which, int tid) {
+                                       double2* xbuf, int (&which)[Geo<PID>::NGROUP], int tid) {
     using BP = BigProg<PID>;
     using G = Geo<PID>;
     constexpr int NA = G::NA, NB = G::NB, NT = G::NT;
@@ -94,21 +113,22 @@ __device__ __forceinline__ void big_op(double2 (&v)[BigProg<PID>::NA][BigProg<PI
                         tan_one(v[i][j], p, t);
                     }
         } else {
-            double2* buf = xbuf + which * G::BUF;
+            constexpr int grp = pos - 5;
+            double2* buf = xbuf + (2 * grp + which[grp]) * G::BUF;
             int e = 0;
 #pragma unroll
             for (int i = 0; i < NA; ++i)
 #pragma unroll
                 for (int j = 0; j < NB; ++j)
                     if ((mask >> (ket ? i : j)) & 1) buf[(e++) * NT + tid] = v[i][j];
-            __syncthreads();
+            pair_sync<PID, pos>(tid);
             e = 0;
 #pragma unroll
             for (int i = 0; i < NA; ++i)
 #pragma unroll
                 for (int j = 0; j < NB; ++j)
                     if ((mask >> (ket ? i : j)) & 1) tan_one(v[i][j], buf[(e++) * NT + (tid ^ (1 << pos))], t);
-            which ^= 1;
+            which[grp] ^= 1;
         }
     } else {   // amplitude damping of pseudomode `a`: ket thread bit pa, bra thread bit pb
         constexpr int pa = BP::ket_pos[a], pb = BP::bra_pos[a];
@@ -116,14 +136,15 @@ __device__ __forceinline__ void big_op(double2 (&v)[BigProg<PID>::NA][BigProg<PI
         const double2 cs = *reinterpret_cast<const double2*>(P + slot);       // {cos phi, sin^2 phi}
         const int la = (tid >> pa) & 1, lb = (tid >> pb) & 1;
         const int cid = remove_bit(remove_bit(tid, hi), lo);
-        double2* buf = xbuf + which * G::BUF;
+        constexpr int grp = hi >= 5 ? hi - 5 : G::NWB;              // exchanges inside a warp use the last buffer pair
+        double2* buf = xbuf + (2 * grp + which[grp]) * G::BUF;
         if (la & lb) {
 #pragma unroll
             for (int i = 0; i < NA; ++i)
 #pragma unroll
                 for (int j = 0; j < NB; ++j) buf[(i * NB + j) * (NT / 4) + cid] = v[i][j];
         }
-        __syncthreads();
+        pair_sync<PID, hi>(tid);
         if (!(la | lb)) {
 #pragma unroll
             for (int i = 0; i < NA; ++i)
@@ -143,14 +164,15 @@ __device__ __forceinline__ void big_op(double2 (&v)[BigProg<PID>::NA][BigProg<PI
                     v[i][j].y *= f;
                 }
         }
-        which ^= 1;
+        which[grp] ^= 1;
     }
 }
 
 template <int PID, int... Os>
 __device__ __forceinline__ void big_step(double2 (&v)[BigProg<PID>::NA][BigProg<PID>::NB],
                                          const double2 (&w)[BigProg<PID>::NA][BigProg<PID>::NB], const double* P,
-                                         double2* xbuf, int& which, int tid, std::integer_sequence<int, Os...>) {
+                                         double2* xbuf, int (&which)[Geo<PID>::NGROUP], int tid,
+                                         std::integer_sequence<int, Os...>) {
     (big_op<PID, Os>(v, w, P, xbuf, which, tid), ...);
 }
 
@@ -192,7 +214,7 @@ __global__ void __launch_bounds__(1 << (2 * BigProg<PID>::NBITS)) evolve_rrc_ker
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const qsx_rrc_args& a = k.a;
     double2* xbuf = reinterpret_cast<double2*>(smem_raw);
-    double2* red = xbuf + 2 * G::BUF;
+    double2* red = xbuf + 2 * G::NGROUP * G::BUF;
     double* P = reinterpret_cast<double*>(red + 64);
     const int tid = threadIdx.x;
     int ma, mb;
@@ -222,7 +244,10 @@ __global__ void __launch_bounds__(1 << (2 * BigProg<PID>::NBITS)) evolve_rrc_ker
                     v[i][j] = sin[(size_t)((i << NBITS) | ma) * DB + ((j << NBITS) | mb)];
                 }
         }
-        int which = 0, slot = 0;
+        int which[G::NGROUP];
+#pragma unroll
+        for (int g = 0; g < G::NGROUP; ++g) which[g] = 0;
+        int slot = 0;
         int next_emit = a.n_emit > 0 ? a.emit_steps[0] : -1;
         int after_next = a.n_emit > 1 ? a.emit_steps[1] : -1;
         for (int step = 0; step <= a.n_steps && slot < a.n_emit; ++step) {
