@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define QSX_ABI_VERSION 7
+#define QSX_ABI_VERSION 8
 
 enum {
     QSX_OK = 0,
@@ -248,6 +248,30 @@ int32_t qsx_evolve(const qsx_evolve_args* args, void* stream);
  * `mu` is DEVICE [N] doubles; blocks are [n_inst][D*D'] complex128. */
 int32_t qsx_apply_dipole(const qsx_block* in_blk, const qsx_block* out_blk, int32_t side, const double* mu,
                          int32_t n_inst, const double* sigma_in, double* sigma_out, void* stream);
+
+/* Post-processing of the response function (qsextra/spectroscopy/postprocessing.py:9-37 rotating_frame, and the
+ * zero padding of fourier_transform :57 / :77), one pass:
+ *   linear (one delay axis):  out[i]    = R[i] e^{+i rf t1[i]} e^{-damping t1[i]}                     i < n1, else 0
+ *   third order:              out[i][j] = R[i][t2_index][j] e^{-i rf (t1[i]-t3[j])} e^{-damping (t1[i]+t3[j])}, else 0
+ * `out` is [n1*pad] or [n1*pad][n3*pad] complex128; all pointers DEVICE. */
+typedef struct {
+    int32_t n1, n2, n3;          /* signal [n1][n2][n3] complex128 (linear: n2 = n3 = 1) */
+    int32_t t2_index;
+    int32_t pad;                 /* pad_extension >= 1 */
+    int32_t linear;
+    double rf_freq, damping;
+    const double* t1;
+    const double* t3;            /* NULL when linear */
+    const double* signal;
+    double* out;
+} qsx_frame_args;
+
+int32_t qsx_rotating_frame(const qsx_frame_args* args, void* stream);
+
+/* out[i][j] = scale * in[(i+s1) % m1][(j+s3) % m3] on [m1][m3] complex128 DEVICE arrays (in != out): the
+ * fftshift (s = m - m/2) / ifftshift (s = m/2) and the prefactor of postprocessing.py:61 and :84-85. */
+int32_t qsx_spectrum_shift(const double* in, double* out, int32_t m1, int32_t m3, int32_t s1, int32_t s3, double scale,
+                           void* stream);
 
 /* Unrolled DFMA micro-benchmark: achieved FP64 TFLOP/s of the CUDA cores on the current device
  * (the roofline denominator of the on-chip-resident kernels; host pointer). Synchronises. */

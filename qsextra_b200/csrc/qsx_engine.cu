@@ -589,6 +589,7 @@ __global__ void __launch_bounds__(256) evolve_kernel(const EvolveParams k) {
 }  // namespace (helpers above are shared with the register-resident kernel)
 #include "qsx_rr.cuh"
 #include "qsx_rrc.cuh"
+#include "qsx_post.cuh"
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -1041,6 +1042,48 @@ int32_t qsx_evolve_rrc(const qsx_rrc_args* a, void* stream) {
     int r = rrc::launch<0>(*a, sms, smem_max, (cudaStream_t)stream);
     if (r == 1) return fail(QSX_ERR_INVALID, "no compile-time program matches this block%s");
     if (r < 0) return fail(QSX_ERR_CUDA, "CUDA error: %s", cudaGetErrorString((cudaError_t)(-r)));
+    return QSX_OK;
+}
+
+int32_t qsx_rotating_frame(const qsx_frame_args* a, void* stream) {
+    if (!a) return fail(QSX_ERR_INVALID, "null args%s");
+    if (a->n1 < 0 || a->n2 < 1 || a->n3 < 1 || a->pad < 1) return fail(QSX_ERR_INVALID, "bad signal shape or pad_extension%s");
+    if (!a->linear && (a->t2_index < 0 || a->t2_index >= a->n2)) return fail(QSX_ERR_INVALID, "T2_index exceed length of T2%s");
+    if (a->linear && (a->n2 != 1 || a->n3 != 1)) return fail(QSX_ERR_INVALID, "a linear signal has one delay axis%s");
+    if (a->n1 == 0) return QSX_OK;
+    if (!a->t1 || !a->signal || !a->out || (!a->linear && !a->t3)) return fail(QSX_ERR_INVALID, "null argument%s");
+    post::FrameParams p;
+    p.n1 = a->n1; p.n2 = a->n2; p.n3 = a->n3; p.t2_index = a->t2_index; p.pad = a->pad; p.linear = a->linear;
+    p.rf = a->rf_freq; p.damping = a->damping;
+    p.t1 = a->t1; p.t3 = a->t3;
+    p.signal = reinterpret_cast<const double2*>(a->signal);
+    p.out = reinterpret_cast<double2*>(a->out);
+    int sms = 0, smem_max = 0;
+    int32_t rc = device_limits(&sms, &smem_max);
+    if (rc) return rc;
+    long long total = (long long)a->n1 * a->pad * (a->linear ? 1 : (long long)a->n3 * a->pad);
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    post::frame_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    QSX_CUDA(cudaGetLastError());
+    return QSX_OK;
+}
+
+int32_t qsx_spectrum_shift(const double* in, double* out, int32_t m1, int32_t m3, int32_t s1, int32_t s3, double scale,
+                           void* stream) {
+    if (m1 < 0 || m3 < 0 || s1 < 0 || s3 < 0 || (m1 > 0 && s1 >= m1) || (m3 > 0 && s3 >= m3))
+        return fail(QSX_ERR_INVALID, "bad shape or shift%s");
+    if (m1 == 0 || m3 == 0) return QSX_OK;
+    if (!in || !out || in == out) return fail(QSX_ERR_INVALID, "null or aliased argument%s");
+    int sms = 0, smem_max = 0;
+    int32_t rc = device_limits(&sms, &smem_max);
+    if (rc) return rc;
+    long long total = (long long)m1 * m3;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    post::shift_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double2*>(in),
+                                                                        reinterpret_cast<double2*>(out), m1, m3, s1, s3, scale);
+    QSX_CUDA(cudaGetLastError());
     return QSX_OK;
 }
 

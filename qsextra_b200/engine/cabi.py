@@ -11,10 +11,11 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libqsx.so')
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 EXPORTS = ('qsx_abi_version', 'qsx_last_error', 'qsx_device_info', 'qsx_evolve_workspace_bytes', 'qsx_evolve',
-           'qsx_evolve_rr', 'qsx_evolve_rrc', 'qsx_apply_dipole', 'qsx_fp64_peak')
+           'qsx_evolve_rr', 'qsx_evolve_rrc', 'qsx_apply_dipole', 'qsx_rotating_frame', 'qsx_spectrum_shift',
+           'qsx_fp64_peak')
 RR_MAX_OPS, RR_MAX_OBS, RR_MAX_ENTRIES = 24, 8, 4
 
 
@@ -84,6 +85,12 @@ class QsxRRCArgs(C.Structure):
 _lib = None
 
 
+class QsxFrameArgs(C.Structure):
+    _fields_ = [('n1', C.c_int32), ('n2', C.c_int32), ('n3', C.c_int32), ('t2_index', C.c_int32), ('pad', C.c_int32),
+                ('linear', C.c_int32), ('rf_freq', C.c_double), ('damping', C.c_double), ('t1', C.c_void_p),
+                ('t3', C.c_void_p), ('signal', C.c_void_p), ('out', C.c_void_p)]
+
+
 def load():
     """Load libqsx.so once; raise (never fall back) when it is absent or has the wrong ABI."""
     global _lib
@@ -108,6 +115,11 @@ def load():
     lib.qsx_apply_dipole.argtypes = [C.POINTER(QsxBlock), C.POINTER(QsxBlock), C.c_int32, C.c_void_p, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
     lib.qsx_apply_dipole.restype = C.c_int32
+    lib.qsx_rotating_frame.argtypes = [C.POINTER(QsxFrameArgs), C.c_void_p]
+    lib.qsx_rotating_frame.restype = C.c_int32
+    lib.qsx_spectrum_shift.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                                       C.c_void_p]
+    lib.qsx_spectrum_shift.restype = C.c_int32
     lib.qsx_fp64_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     lib.qsx_fp64_peak.restype = C.c_int32
     if lib.qsx_abi_version() != ABI_VERSION:

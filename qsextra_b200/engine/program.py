@@ -323,6 +323,15 @@ def _popcount(v: int) -> int:
     return bin(v).count('1')
 
 
+def _popcount_array(values: np.ndarray) -> np.ndarray:
+    out = np.zeros(values.shape, dtype=np.int64)
+    v = values.astype(np.int64)
+    while np.any(v):
+        out += v & 1
+        v = v >> 1
+    return out
+
+
 def _z_commutes(op, zs: int, zb: int) -> bool:
     """Does exp(-i th Z^zs Z^zb) commute with ``op`` (as maps on sigma)?"""
     if isinstance(op, _Hop):
@@ -451,21 +460,30 @@ class StepProgram:
             cursor += arr.shape[1]
             return slot
 
-        def side_table(cfgs, zterms):
+        bits_of = np.arange(1 << nb, dtype=np.int64)
+        table_cache = {}
+
+        def side_table(cfgs, zterms, key):
+            """exp(-i phase) of the merged Z rotations for every (configuration, mode bits) of one side, [B, 2*dim]."""
+            if (key, tuple(cfgs)) in table_cache:                # ket and bra sides share the table when KA == KB
+                return table_cache[key, tuple(cfgs)]
             masks = np.array(cfgs, dtype=np.int64)
-            idx = np.arange(len(cfgs) << nb, dtype=np.int64)
-            cfg_of, bits_of = masks[idx >> nb], idx & ((1 << nb) - 1)
-            phase = np.zeros((B, idx.size))
+            phase = np.zeros((B, len(cfgs), 1 << nb))
             for zs, zb, ang in zterms:
-                par = np.array([_popcount(int(c) & zs) for c in cfg_of]) + np.array([_popcount(int(m) & zb) for m in bits_of])
-                phase += ang[:, None] * (1 - 2 * (par & 1))[None, :]
-            g = np.exp(-1j * phase)
-            return np.stack([g.real, g.imag], axis=-1).reshape(B, -1)
+                par = (_popcount_array(masks & zs)[:, None] + _popcount_array(bits_of & zb)[None, :]) & 1
+                phase += ang[:, None, None] * (1 - 2 * par)[None]
+            out = np.empty((B, len(cfgs) << nb, 2))
+            flat = phase.reshape(B, -1)
+            np.cos(flat, out=out[:, :, 0])
+            np.sin(flat, out=out[:, :, 1])
+            np.negative(out[:, :, 1], out=out[:, :, 1])
+            table_cache[key, tuple(cfgs)] = out = out.reshape(B, -1)
+            return out
 
         for op in self.lowered:
             if isinstance(op, _Diag):
-                slot_a = push(side_table(block.cfg_a, op.zterms))
-                slot_b = push(side_table(block.cfg_b, op.zterms))
+                slot_a = push(side_table(block.cfg_a, op.zterms, id(op)))
+                slot_b = push(side_table(block.cfg_b, op.zterms, id(op)))
                 slot_t = -1
                 if op.deph:
                     t = np.ones((B, block.n_a, block.n_b))

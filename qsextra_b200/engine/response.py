@@ -44,9 +44,11 @@ def interaction_plan(side_seq: str, direction_seq: str):
     return plan
 
 
-def response_function(program: StepProgram, mu, side_seq: str, direction_seq: str, step_counts, engine=None):
+def response_function(program: StepProgram, mu, side_seq: str, direction_seq: str, step_counts, engine=None,
+                      device_output: bool = False):
     """Signal over the delay grid.  ``step_counts``: one integer list per delay (any order, duplicates allowed).
-    Returns a complex ndarray of shape [len(c) for c in step_counts], identical on every rank."""
+    Returns a complex ndarray of shape [len(c) for c in step_counts], identical on every rank (``device_output``: a
+    complex128 CUDA tensor instead, e.g. for the device post-processing)."""
     from .runtime import get_engine
     eng = engine or get_engine()
     n_sites = program.n_sites
@@ -100,8 +102,14 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
             rows_per_unit *= len(emit)
 
     if zero:
-        return np.zeros(shape, dtype=complex)
+        return torch.zeros(shape, dtype=torch.complex128, device=eng.device) if device_output else np.zeros(shape, dtype=complex)
     if sharded:
         out = qdist.all_gather_rows(out, shard_units, rows_per_unit)
+    if device_output:
+        table = out.reshape([len(u) for u in uniq])
+        for axis, inv in enumerate(inverse):            # back to the caller's order/duplicates, axis by axis
+            if len(inv) != table.shape[axis] or np.any(inv != np.arange(len(inv))):
+                table = table.index_select(axis, torch.as_tensor(inv, device=eng.device))
+        return table.reshape(shape).contiguous()
     table = out.cpu().numpy().reshape([len(u) for u in uniq])
     return table[np.ix_(*inverse)].reshape(shape)

@@ -49,6 +49,7 @@ def qspectroscopy(system: ChromophoreSystem | ExcitonicSystem,
                   verbose: bool = True,
                   checkpoint: bool = False,
                   restart_from_checkpoint: str | None = None,
+                  device_output: bool = False,
                   **qevolve_kwds,
                   ) -> np.ndarray:
     """Simulate ``spectroscopy`` (a ``FeynmanDiagram`` or a ``Spectroscopy`` with hand-set sequences) on ``system``.
@@ -56,13 +57,14 @@ def qspectroscopy(system: ChromophoreSystem | ExcitonicSystem,
     ``qevolve_kwds`` are forwarded to the evolution (``dt``, ``coll_rates``, ``Trotter_number``, ``Trotter_order``,
     ``GPU``); the reserved keys system/time/shots/initialize_circuit/verbose are dropped like the reference does.
     Returns a complex array with one axis per delay list.  Under ``torch.distributed`` the delay-grid chains are
-    sharded over the ranks and every rank returns the full array.
+    sharded over the ranks and every rank returns the full array.  ``device_output`` (an addition to the reference
+    signature) returns the signal as a complex128 CUDA tensor, which ``postprocessing`` accepts as it is.
     """
     _validate_system(system)
     if type(system) is ChromophoreSystem and system.mode_dict is None:
         warnings.warn("Pseudomodes not specified. Executing the dynamics with system as an ExcitonicSystem.")
         return qspectroscopy(system.extract_ExcitonicSystem(), spectroscopy, shots, verbose, checkpoint,
-                             restart_from_checkpoint, **qevolve_kwds)
+                             restart_from_checkpoint, device_output, **qevolve_kwds)
     for key in _RESERVED:
         qevolve_kwds.pop(key, None)
     if spectroscopy.side_seq == '' or spectroscopy.direction_seq == '':
@@ -87,9 +89,12 @@ def qspectroscopy(system: ChromophoreSystem | ExcitonicSystem,
         folder = create_checkpoint_folder()
         print(f'Checkpoint folder created ({folder})')
     signal = response_function(program, np.asarray(system.dipole_moments, dtype=float), spectroscopy.side_seq,
-                               spectroscopy.direction_seq, counts)
+                               spectroscopy.direction_seq, counts, device_output=device_output)
     if kept is not None and kept.shape == signal.shape and last >= 0:
         flat, old = signal.reshape(-1), kept.reshape(-1)
+        if device_output:
+            import torch
+            old = torch.as_tensor(old, device=signal.device)
         flat[:last + 1] = old[:last + 1]             # grid points the interrupted run had already finished
     if folder is not None:
         destroy_checkpoint_folder(folder)
