@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define QSX_ABI_VERSION 8
+#define QSX_ABI_VERSION 9
 
 enum {
     QSX_OK = 0,
@@ -248,6 +248,36 @@ int32_t qsx_evolve(const qsx_evolve_args* args, void* stream);
  * `mu` is DEVICE [N] doubles; blocks are [n_inst][D*D'] complex128. */
 int32_t qsx_apply_dipole(const qsx_block* in_blk, const qsx_block* out_blk, int32_t side, const double* mu,
                          int32_t n_inst, const double* sigma_in, double* sigma_out, void* stream);
+
+/* Lindblad limit of the collision model -- replaces the QuTiP solver calls of the comparison path
+ * (qsextra/qcomo/evolution/clevolve.py:27-46 and :88-107: sesolve / mesolve(H, state, time, c_ops, e_ops)).
+ * sigma' = L sigma with the sparse generator of one sector block in ELL storage; segment k propagates by seg_dt[k]
+ * (scaled Taylor series of exp(hL), `terms` terms, sub-steps h <= theta / norm1) and is followed by emission k. */
+typedef struct {
+    int32_t E;                   /* elements of the block (DA*DB) */
+    int32_t width;               /* ELL width (max entries per row) */
+    const int32_t* ell_idx;      /* DEVICE [width][E] column of entry k of row r at [k*E + r] */
+    const double* ell_val;       /* DEVICE [width][E] complex128, 0 for padding */
+    double norm1;                /* upper bound of ||L||_1 */
+    int32_t terms;               /* Taylor terms per sub-step (>= 2; 0: 20) */
+    double theta;                /* largest ||hL||_1 of a sub-step (0: 1.0) */
+    int32_t n_inst;
+    const int32_t* inst_src;     /* DEVICE [n_inst] source block per instance, or NULL (= instance index) */
+    const double* sigma_in;      /* DEVICE [n_src][E] complex128 */
+    int32_t n_seg;               /* number of segments = number of emissions */
+    const double* seg_dt;        /* HOST [n_seg] durations (>= 0; 0 emits the current state again) */
+    int32_t n_obs;               /* CSR read-outs, as qsx_evolve_args */
+    const int32_t* obs_ptr;
+    const int32_t* obs_idx;
+    const double* obs_w;
+    int32_t obs_real;
+    double* out_obs;             /* DEVICE [n_inst][n_seg][n_obs] float64 (obs_real) or complex128, or NULL */
+    double* out_snap;            /* DEVICE [n_inst][n_seg][E] complex128, or NULL */
+    double* workspace;           /* DEVICE qsx_lindblad_workspace_bytes(args) bytes */
+} qsx_lindblad_args;
+
+int64_t qsx_lindblad_workspace_bytes(const qsx_lindblad_args* args);
+int32_t qsx_lindblad_evolve(const qsx_lindblad_args* args, void* stream);
 
 /* Post-processing of the response function (qsextra/spectroscopy/postprocessing.py:9-37 rotating_frame, and the
  * zero padding of fourier_transform :57 / :77), one pass:

@@ -590,6 +590,7 @@ __global__ void __launch_bounds__(256) evolve_kernel(const EvolveParams k) {
 #include "qsx_rr.cuh"
 #include "qsx_rrc.cuh"
 #include "qsx_post.cuh"
+#include "qsx_lindblad.cuh"
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -1042,6 +1043,85 @@ int32_t qsx_evolve_rrc(const qsx_rrc_args* a, void* stream) {
     int r = rrc::launch<0>(*a, sms, smem_max, (cudaStream_t)stream);
     if (r == 1) return fail(QSX_ERR_INVALID, "no compile-time program matches this block%s");
     if (r < 0) return fail(QSX_ERR_CUDA, "CUDA error: %s", cudaGetErrorString((cudaError_t)(-r)));
+    return QSX_OK;
+}
+
+static int32_t check_lindblad(const qsx_lindblad_args* a) {
+    if (!a) return fail(QSX_ERR_INVALID, "null args%s");
+    if (a->E < 1 || a->width < 1 || a->n_inst < 0 || a->n_seg < 0 || a->n_obs < 0)
+        return fail(QSX_ERR_INVALID, "bad sizes%s");
+    if (a->terms != 0 && a->terms < 2) return fail(QSX_ERR_INVALID, "at least two Taylor terms%s");
+    if (!(a->norm1 >= 0.0) || !(a->theta >= 0.0)) return fail(QSX_ERR_INVALID, "norm1 and theta must be >= 0%s");
+    return QSX_OK;
+}
+
+int64_t qsx_lindblad_workspace_bytes(const qsx_lindblad_args* a) {
+    int32_t rc = check_lindblad(a);
+    if (rc) return rc;
+    return (int64_t)3 * a->n_inst * a->E * (int64_t)sizeof(double2);
+}
+
+int32_t qsx_lindblad_evolve(const qsx_lindblad_args* a, void* stream) {
+    int32_t rc = check_lindblad(a);
+    if (rc) return rc;
+    if (a->n_inst == 0 || a->n_seg == 0) return QSX_OK;
+    if (!a->ell_idx || !a->ell_val || !a->sigma_in || !a->seg_dt || !a->workspace)
+        return fail(QSX_ERR_INVALID, "null argument%s");
+    if (a->n_obs > 0 && (!a->obs_ptr || !a->out_obs))           // obs_idx / obs_w may be NULL when every read-out is empty
+        return fail(QSX_ERR_INVALID, "read-outs requested without tables or output%s");
+    if (!a->out_obs && !a->out_snap) return fail(QSX_ERR_INVALID, "nothing to emit%s");
+    for (int k = 0; k < a->n_seg; ++k)
+        if (!(a->seg_dt[k] >= 0.0)) return fail(QSX_ERR_INVALID, "segment durations must be >= 0%s");
+    int sms = 0, smem_max = 0;
+    rc = device_limits(&sms, &smem_max);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int terms = a->terms ? a->terms : 20;
+    const double theta = a->theta > 0.0 ? a->theta : 1.0;
+    const size_t vec = (size_t)a->n_inst * a->E;
+    double2* acc = reinterpret_cast<double2*>(a->workspace);
+    double2* y[2] = {acc + vec, acc + 2 * vec};
+    const int wide = sms * 8;
+    {
+        size_t blocks = (vec + 255) / 256;
+        if (blocks > (size_t)wide) blocks = wide;
+        lind::load_kernel<<<(int)blocks, 256, 0, st>>>(a->E, a->n_inst, a->inst_src,
+                                                        reinterpret_cast<const double2*>(a->sigma_in), acc);
+    }
+    lind::TermParams t;
+    t.E = a->E; t.width = a->width; t.n_inst = a->n_inst;
+    t.idx = a->ell_idx; t.val = reinterpret_cast<const double2*>(a->ell_val); t.acc = acc;
+    dim3 grid((a->E + 127) / 128, (a->n_inst + lind::IPT - 1) / lind::IPT);
+    if (grid.y > 65535u) grid.y = 65535u;
+    lind::EmitParams e;
+    e.E = a->E; e.n_inst = a->n_inst; e.n_emit = a->n_seg; e.n_obs = a->n_obs; e.obs_real = a->obs_real;
+    e.obs_ptr = a->obs_ptr; e.obs_idx = a->obs_idx; e.obs_w = reinterpret_cast<const double2*>(a->obs_w);
+    e.acc = acc; e.out_obs = a->n_obs > 0 ? a->out_obs : nullptr; e.out_snap = reinterpret_cast<double2*>(a->out_snap);
+    size_t emit_threads = a->out_snap ? vec : (size_t)a->n_inst * a->n_obs * 32;
+    size_t emit_blocks = (emit_threads + 255) / 256;
+    if (emit_blocks > (size_t)wide) emit_blocks = wide;
+    if (emit_blocks < 1) emit_blocks = 1;
+    for (int k = 0; k < a->n_seg; ++k) {
+        const double dt = a->seg_dt[k];
+        if (dt > 0.0 && a->norm1 > 0.0) {
+            double subs = ceil(a->norm1 * dt / theta);
+            if (subs < 1.0) subs = 1.0;
+            if (subs > 1e7) return fail(QSX_ERR_INVALID, "segment needs more than 1e7 sub-steps%s");
+            const long long n_sub = (long long)subs;
+            const double h = dt / (double)n_sub;
+            for (long long s = 0; s < n_sub; ++s)
+                for (int m = 1; m <= terms; ++m) {
+                    t.first = m == 1; t.last = m == terms;
+                    t.scale = h / (double)m;
+                    t.x = t.first ? acc : y[(m + 1) & 1];
+                    t.y = y[m & 1];
+                    lind::term_kernel<<<grid, 128, 0, st>>>(t);
+                }
+        }
+        e.k = k;
+        lind::emit_kernel<<<(int)emit_blocks, 256, 0, st>>>(e);
+    }
+    QSX_CUDA(cudaGetLastError());
     return QSX_OK;
 }
 

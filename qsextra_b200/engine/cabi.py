@@ -11,10 +11,11 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libqsx.so')
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 EXPORTS = ('qsx_abi_version', 'qsx_last_error', 'qsx_device_info', 'qsx_evolve_workspace_bytes', 'qsx_evolve',
            'qsx_evolve_rr', 'qsx_evolve_rrc', 'qsx_apply_dipole', 'qsx_rotating_frame', 'qsx_spectrum_shift',
+           'qsx_lindblad_workspace_bytes', 'qsx_lindblad_evolve',
            'qsx_fp64_peak')
 RR_MAX_OPS, RR_MAX_OBS, RR_MAX_ENTRIES = 24, 8, 4
 
@@ -85,6 +86,15 @@ class QsxRRCArgs(C.Structure):
 _lib = None
 
 
+class QsxLindbladArgs(C.Structure):
+    _fields_ = [('E', C.c_int32), ('width', C.c_int32), ('ell_idx', C.c_void_p), ('ell_val', C.c_void_p),
+                ('norm1', C.c_double), ('terms', C.c_int32), ('theta', C.c_double), ('n_inst', C.c_int32),
+                ('inst_src', C.c_void_p), ('sigma_in', C.c_void_p), ('n_seg', C.c_int32),
+                ('seg_dt', C.POINTER(C.c_double)), ('n_obs', C.c_int32), ('obs_ptr', C.c_void_p),
+                ('obs_idx', C.c_void_p), ('obs_w', C.c_void_p), ('obs_real', C.c_int32), ('out_obs', C.c_void_p),
+                ('out_snap', C.c_void_p), ('workspace', C.c_void_p)]
+
+
 class QsxFrameArgs(C.Structure):
     _fields_ = [('n1', C.c_int32), ('n2', C.c_int32), ('n3', C.c_int32), ('t2_index', C.c_int32), ('pad', C.c_int32),
                 ('linear', C.c_int32), ('rf_freq', C.c_double), ('damping', C.c_double), ('t1', C.c_void_p),
@@ -115,6 +125,10 @@ def load():
     lib.qsx_apply_dipole.argtypes = [C.POINTER(QsxBlock), C.POINTER(QsxBlock), C.c_int32, C.c_void_p, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
     lib.qsx_apply_dipole.restype = C.c_int32
+    lib.qsx_lindblad_workspace_bytes.argtypes = [C.POINTER(QsxLindbladArgs)]
+    lib.qsx_lindblad_workspace_bytes.restype = C.c_int64
+    lib.qsx_lindblad_evolve.argtypes = [C.POINTER(QsxLindbladArgs), C.c_void_p]
+    lib.qsx_lindblad_evolve.restype = C.c_int32
     lib.qsx_rotating_frame.argtypes = [C.POINTER(QsxFrameArgs), C.c_void_p]
     lib.qsx_rotating_frame.restype = C.c_int32
     lib.qsx_spectrum_shift.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double,

@@ -46,7 +46,9 @@ def interaction_plan(side_seq: str, direction_seq: str):
 
 def response_function(program: StepProgram, mu, side_seq: str, direction_seq: str, step_counts, engine=None,
                       device_output: bool = False):
-    """Signal over the delay grid.  ``step_counts``: one integer list per delay (any order, duplicates allowed).
+    """Signal over the delay grid.  ``step_counts``: one integer list per delay (any order, duplicates allowed); for
+    a continuous-time program (``engine.lindblad.LindbladProgram``, the comparison path clspectroscopy.py:18-132) the
+    lists hold the delay times themselves.
     Returns a complex ndarray of shape [len(c) for c in step_counts], identical on every rank (``device_output``: a
     complex128 CUDA tensor instead, e.g. for the device post-processing)."""
     from .runtime import get_engine
@@ -57,10 +59,22 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
         raise ValueError('side_seq must have one more entry than delay_time')
     shape = [len(c) for c in step_counts]
     uniq, inverse = [], []
+    continuous = bool(getattr(program, 'continuous', False))
     for c in step_counts:
-        u, inv = np.unique(np.asarray(c, dtype=np.int64), return_inverse=True)
-        uniq.append(u.astype(np.int32))
+        u, inv = np.unique(np.asarray(c, dtype=np.float64 if continuous else np.int64), return_inverse=True)
+        uniq.append(u if continuous else u.astype(np.int32))
         inverse.append(inv)
+
+    def upload(block):
+        if continuous:
+            return eng.upload_lindblad(program.bind(block))
+        return eng.upload_program(program.bind(block), program)
+
+    def propagate(dev, sigma, n_local, emit, **kw):
+        if continuous:
+            from .lindblad import segments_from_times
+            return eng.evolve_lindblad(dev, sigma, n_local, segments_from_times(emit), **kw)
+        return eng.evolve(dev, sigma, n_local, int(emit.max()), emit, **kw)
     mu_dev = eng.to_device(np.asarray(mu, dtype=np.float64), torch.float64)
     rank, size = qdist.world()
 
@@ -87,15 +101,15 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
             sharded, shard_units = True, n_global
         sigma = eng.apply_dipole(block, new_block, 0 if side == 'k' else 1, mu_dev, sigma)
         block, ka, kb = new_block, nka, nkb
-        dev = eng.upload_program(program.bind(block), program)
+        dev = upload(block)
         n_local = sigma.shape[0]
         emit = uniq[level]
         if level < len(plan) - 2:
-            _, snap = eng.evolve(dev, sigma, n_local, int(emit.max()), emit, snapshots=True)
+            _, snap = propagate(dev, sigma, n_local, emit, snapshots=True)
             sigma = snap.reshape(n_local * len(emit), block.size)
         else:
             obs = eng.upload_observables(*block.emission_observable(np.asarray(mu, dtype=float)), kind='emission', mu=mu)
-            out, _ = eng.evolve(dev, sigma, n_local, int(emit.max()), emit, obs=obs)
+            out, _ = propagate(dev, sigma, n_local, emit, obs=obs)
             out = out.reshape(n_local, len(emit))
         n_global *= len(emit)
         if sharded and level < len(plan) - 2:

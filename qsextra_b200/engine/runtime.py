@@ -268,6 +268,49 @@ class Engine:
             self.launches += 1
         return out
 
+    # ---- Lindblad limit ----------------------------------------------------------------------------
+    def upload_lindblad(self, bound):
+        """Device tables of a ``lindblad.BoundLindblad`` (ELL generator of one block)."""
+        return dict(lindblad=bound, E=int(bound.ell_idx.shape[1]), width=int(bound.width),
+                    idx=self.to_device(bound.ell_idx, torch.int32), val=self.to_device(bound.ell_val),
+                    norm1=float(bound.norm1))
+
+    def evolve_lindblad(self, prog: dict, sigma_in: torch.Tensor, n_inst: int, seg_dt, obs: dict | None = None,
+                        obs_real: bool = False, snapshots: bool = False, inst_src=None, terms: int = 0, theta: float = 0.0):
+        """Propagate ``n_inst`` blocks under the master equation; emission k follows segment k of duration
+        ``seg_dt[k]``.  Returns (out_obs | None, out_snap | None) shaped like ``evolve``'s."""
+        E = prog['E']
+        seg = np.ascontiguousarray(seg_dt, dtype=np.float64)
+        n_seg = int(seg.size)
+        assert sigma_in.dtype == torch.complex128 and sigma_in.is_contiguous() and sigma_in.numel() % E == 0
+        args = cabi.QsxLindbladArgs()
+        args.E, args.width = E, prog['width']
+        args.ell_idx, args.ell_val, args.norm1 = prog['idx'].data_ptr(), prog['val'].data_ptr(), prog['norm1']
+        args.terms, args.theta = int(terms), float(theta)
+        args.n_inst = int(n_inst)
+        args.inst_src = None if inst_src is None else inst_src.data_ptr()
+        args.sigma_in = sigma_in.data_ptr()
+        args.n_seg, args.seg_dt = n_seg, seg.ctypes.data_as(C.POINTER(C.c_double))
+        out_obs = out_snap = None
+        if obs is not None:
+            args.n_obs, args.obs_ptr, args.obs_idx, args.obs_w = obs['n'], obs['ptr'].data_ptr(), obs['idx'].data_ptr(), obs['w'].data_ptr()
+            out_obs = torch.empty((n_inst, n_seg, obs['n']), dtype=torch.float64 if obs_real else torch.complex128,
+                                  device=self.device)
+            args.out_obs, args.obs_real = out_obs.data_ptr(), int(obs_real)
+        if snapshots:
+            out_snap = torch.empty((n_inst, n_seg, E), dtype=torch.complex128, device=self.device)
+            args.out_snap = out_snap.data_ptr()
+        with torch.cuda.device(self.device):
+            ws_bytes = self.lib.qsx_lindblad_workspace_bytes(C.byref(args))
+            cabi.check(ws_bytes)
+            workspace = torch.empty(max(ws_bytes // 8, 1), dtype=torch.float64, device=self.device)
+            args.workspace = workspace.data_ptr()
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            cabi.check(self.lib.qsx_lindblad_evolve(C.byref(args), C.c_void_p(stream)))
+        if n_inst > 0 and n_seg > 0:
+            self.launches += 1
+        return out_obs, out_snap
+
     def rotating_frame(self, signal: torch.Tensor, t1: torch.Tensor, t3, t2_index: int, pad: int, rf_freq: float,
                        damping: float):
         """Rotating frame x damping x zero padding (postprocessing.py:9-37, :57, :77).  ``signal`` complex128 [n1]

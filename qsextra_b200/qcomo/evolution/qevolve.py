@@ -15,6 +15,7 @@ Return value (the reference returns Qiskit objects, which cannot exist here):
 """
 from __future__ import annotations
 
+import os
 import warnings
 from dataclasses import dataclass
 
@@ -24,7 +25,9 @@ from ...system import ChromophoreSystem, ExcitonicSystem
 from ...tools.tools import if_scalar_to_list
 from ...tools.oracle import ending_sentence
 from ...engine import dist as qdist
+from ...engine.cabi import RR_MAX_OBS
 from ...engine.program import StepProgram, SystemBatch, resolve_time_grid
+from ...engine.rr import eligible as rr_eligible
 from ...engine.sectors import population_observables, sector_configs, split_state_by_sector
 
 
@@ -122,7 +125,11 @@ def run_populations(batch: SystemBatch, psi: np.ndarray, program: StepProgram, s
     inst_src = torch.zeros(B, dtype=torch.int32, device=eng.device) if same_state else None
     for k in sectors:
         block = program.block(k, k)
-        dev = eng.upload_program(program.bind(block), program)
+        # the pass tables are only needed when the register-resident kernel cannot serve the block or the read-outs
+        try_rr = rr_eligible(program, block) and width <= RR_MAX_OBS and not os.environ.get('QSX_DISABLE_RR')
+        dev = eng.upload_program(program.bind(block, fused=not try_rr), program)
+        if try_rr and 'rr' not in dev:
+            dev = eng.upload_program(program.bind(block), program)
         cfgs = np.array(sector_configs(n, k), dtype=np.int64)
         amp = psi[:1, cfgs] if same_state else psi[:, cfgs]            # [B or 1, nA]
         sigma0 = np.zeros((amp.shape[0], block.dim_a, block.dim_b), dtype=complex)
@@ -242,7 +249,7 @@ def qevolve_batch(systems, time, Trotter_number: int = 1, Trotter_order: int = 1
         if not batch.chromophore:
             rates = rates.reshape(B)
     dt, dt_trotter, Trotter_number, counts = resolve_time_grid(time, dt, Trotter_number)
-    steps = sorted(set(int(c) for c in counts))
+    steps = np.unique(counts).tolist()
 
     rank, size = qdist.world() if shard else (0, 1)
     lo, hi = qdist.shard_bounds(B, rank, size)

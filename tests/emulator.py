@@ -291,3 +291,23 @@ def apply_rrc_program(sigma, prog, set_index=0):
             partner = v[:, :, m ^ (1 << a), :][:, :, :, m ^ (1 << a)]
             v = np.where((ha == 0) & (hb == 0), v + s2 * partner, np.where(ha != hb, c * v, c * c * v))
     return v.transpose(0, 2, 1, 3).reshape(sigma.shape)
+
+
+def apply_lindblad(bound, sigma, seg_dt, terms=20, theta=1.0):
+    """NumPy emulation of qsx_lindblad_evolve on one block: scaled Taylor series of exp(hL) with the ELL generator.
+    -> states after every segment [n_seg, E]."""
+    acc = np.asarray(sigma, dtype=complex).reshape(-1).copy()
+    out = []
+    for dt in seg_dt:
+        if dt > 0 and bound.norm1 > 0:
+            n_sub = max(1, int(np.ceil(bound.norm1 * dt / theta)))
+            h = dt / n_sub
+            for _ in range(n_sub):
+                y = acc
+                total = acc.copy()
+                for m in range(1, terms + 1):
+                    y = (h / m) * (bound.ell_val * y[bound.ell_idx]).sum(axis=0)
+                    total = total + y
+                acc = total
+        out.append(acc.copy())
+    return np.array(out)

@@ -16,4 +16,4 @@ t0 = time.perf_counter()
 for _ in range(5): once()
 print('e2e ms', (time.perf_counter() - t0) / 5 * 1e3)
 cProfile.run('once()', '/tmp/e2e.prof')
-pstats.Stats('/tmp/e2e.prof').sort_stats('cumtime').print_stats(22)
+pstats.Stats('/tmp/e2e.prof').sort_stats('cumtime').print_stats(45)
