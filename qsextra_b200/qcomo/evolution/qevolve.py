@@ -45,6 +45,98 @@ class CollisionCircuit:
         """Names of the engine operations of one step, in application order."""
         return self.program.bind(self.program.block(0, 0)).labels
 
+    @property
+    def num_qubits(self) -> int:
+        """Qubits of the circuit the reference builds: sys_e, the pseudomode registers, one collision ancilla when
+        there are collisions (qevolve.py:18-43)."""
+        return self.program.n_sites + self._mode_bits + (1 if self._collisions else 0)
+
+    @property
+    def _mode_bits(self) -> int:
+        return sum(len(bits) for bits in self.program.layout.mode.values())
+
+    @property
+    def _collisions(self) -> bool:
+        from ...engine.program import Damp, Dephase, Reset
+        return any(isinstance(t, (Damp, Dephase, Reset)) for t in self.program.terms)
+
+    def qasm(self, member: int = 0, measure: bool = False) -> str:
+        """OpenQASM 2.0 text of this circuit at gate level: state preparation (basis states only), then ``n_steps``
+        repetitions of the step -- every Pauli rotation exp(-i angle P) of the product formula as basis changes, a CX
+        ladder and one ``rz``; every collision as its two-qubit rotations on the ancilla followed by ``reset``
+        (qevolve.py:74-348).  Qubit numbering is the reference's: sys_e[i] -> i, pseudomode registers next, ancilla
+        last.  ``member`` selects the parameter set of a batched program."""
+        from ...engine.program import Damp, Dephase, Reset, Rot
+        prog = self.program
+        n = prog.n_sites
+        anc = n + self._mode_bits
+        lines = ['OPENQASM 2.0;', 'include "qelib1.inc";', 'qreg q[{}];'.format(self.num_qubits)]
+        if measure:
+            lines.append('creg c[{}];'.format(n))
+
+        def qubit_of_bit(bit):
+            return anc if bit == prog.layout.ancilla else n + bit
+
+        def rotation(paulis, angle):
+            """exp(-i angle P) for P = product of (qubit, 'X'|'Y'|'Z')."""
+            if not paulis or angle == 0.0:
+                return
+            for q, p in paulis:
+                if p == 'X':
+                    lines.append('h q[{}];'.format(q))
+                elif p == 'Y':
+                    lines.extend(['sdg q[{}];'.format(q), 'h q[{}];'.format(q)])
+            qs = [q for q, _ in paulis]
+            for a, b in zip(qs[:-1], qs[1:]):
+                lines.append('cx q[{}],q[{}];'.format(a, b))
+            lines.append('rz({!r}) q[{}];'.format(2.0 * float(angle), qs[-1]))
+            for a, b in reversed(list(zip(qs[:-1], qs[1:]))):
+                lines.append('cx q[{}],q[{}];'.format(a, b))
+            for q, p in paulis:
+                if p == 'X':
+                    lines.append('h q[{}];'.format(q))
+                elif p == 'Y':
+                    lines.extend(['h q[{}];'.format(q), 's q[{}];'.format(q)])
+
+        def letters(x, z, to_qubit, width):
+            out = []
+            for j in range(width):
+                xb, zb = (x >> j) & 1, (z >> j) & 1
+                if xb or zb:
+                    out.append((to_qubit(j), 'Y' if xb and zb else 'X' if xb else 'Z'))
+            return out
+
+        if self.initialize:
+            kind = getattr(self.system, 'state_type', None)
+            if kind == 'localized excitation':
+                lines.append('x q[{}];'.format(int(self.system.state)))
+            elif kind not in (None, 'ground'):
+                raise ValueError('OpenQASM 2.0 has no gate for an arbitrary state preparation; build the circuit with '
+                                 'initialize_circuit=False and prepare the {!r} state separately'.format(kind))
+        step = []
+        mark = len(lines)
+        for term in prog.terms:
+            if isinstance(term, Rot):
+                rotation(letters(term.xs, term.zs, lambda j: j, n) +
+                         letters(term.xb, term.zb, qubit_of_bit, prog.n_bits), term.angle[member])
+            elif isinstance(term, Dephase):                       # rzx(2 phi) on (site, ancilla), reset  (:292-305)
+                rotation([(term.site, 'Z'), (anc, 'X')], term.phi[member])
+                lines.append('reset q[{}];'.format(anc))
+            elif isinstance(term, Damp):                          # exp(-i phi/2 XX) exp(-i phi/2 YY), reset  (:307-348)
+                m = qubit_of_bit(term.bit)
+                rotation([(m, 'X'), (anc, 'X')], term.phi[member] / 2)
+                rotation([(m, 'Y'), (anc, 'Y')], term.phi[member] / 2)
+                lines.append('reset q[{}];'.format(anc))
+            elif isinstance(term, Reset):
+                lines.append('reset q[{}];'.format(qubit_of_bit(term.bit)))
+        step = lines[mark:]
+        lines.extend(step * (self.n_steps - 1) if self.n_steps > 0 else [])
+        if self.n_steps == 0:
+            del lines[mark:]
+        if measure:
+            lines.extend('measure q[{0}] -> c[{0}];'.format(i) for i in range(n))
+        return '\n'.join(lines) + '\n'
+
 
 class EvolutionResult:
     """Exact read-outs of the evolution (and sampled counts when ``shots`` > 0)."""
