@@ -36,6 +36,7 @@ class RRProgram:
     fold_classes: list = None         # [(slot of the cosine in op_params, exponent per physical element [E])]
     folded_slots: list = None         # op_params slots whose {cos, sin} become {cos, tan}
     _params: np.ndarray = None
+    _shared: dict = None              # results that depend on the structure only, shared by programs of equal structure
 
     @property
     def stride(self) -> int:
@@ -100,6 +101,15 @@ class RRProgram:
 
     def observables(self, ptr, idx, w):
         """CSR read-outs (logical indices) -> dense weights in physical order + per-read-out register masks."""
+        key = ('obs', np.asarray(ptr).tobytes(), np.asarray(idx).tobytes(), np.asarray(w, dtype=complex).tobytes())
+        if self._shared is not None and key in self._shared:
+            return self._shared[key]
+        out = self._observables(ptr, idx, w)
+        if self._shared is not None:
+            self._shared[key] = out
+        return out
+
+    def _observables(self, ptr, idx, w):
         E = self.block.size
         n_obs = len(ptr) - 1
         phys_of = np.empty(E, dtype=np.int64)
@@ -141,6 +151,15 @@ class RRProgram:
     def site_pieces(self, kind: int, n_sites: int):
         """(register mask, lane mask) pieces per site of the two known read-outs (1: populations, 2: emission
         trace), in the order the compile-time tables use (tools/gen_rr_programs.py), or None."""
+        key = ('pieces', kind, n_sites)
+        if self._shared is not None and key in self._shared:
+            return self._shared[key]
+        out = self._site_pieces(kind, n_sites)
+        if self._shared is not None:
+            self._shared[key] = out
+        return out
+
+    def _site_pieces(self, kind: int, n_sites: int):
         from .sectors import population_observables
         blk = self.block
         if kind == 1 and blk.ka == blk.kb:
@@ -175,7 +194,7 @@ class RRProgram:
         return out
 
 
-def _fold_cosines(ops, params, E, NR, has_table, shift):
+def _fold_cosines(ops, params, E, NR, has_table, shift, shared=None):
     """Tangent form where it is exact (engine/fold.py): the cos factors of the foldable rotations are to be multiplied
     into the first diagonal table, element by element following each rotation's participation mask, and those
     rotations become QSX_RR_ROTT: two fused multiply-adds per element and side instead of two multiplies and two.
@@ -202,7 +221,13 @@ def _fold_cosines(ops, params, E, NR, has_table, shift):
             info.append(dict(mixes=True, takes_part=clear, partner=partner, cls=None))
         else:
             info.append(dict(mixes=False, takes_part=np.zeros(E, bool), partner=phys, cls=None))
-    fold = foldable(E, info)
+    pattern = ('fold', tuple(op['cls'] for op in info))
+    if shared is not None and pattern in shared:
+        fold = set(shared[pattern])
+    else:
+        fold = foldable(E, info)
+        if shared is not None:
+            shared[pattern] = frozenset(fold)
     unfolded_slots = {ops[k][4] for k in rot_idx if k not in fold}
     fold = {k for k in fold if ops[k][4] not in unfolded_slots}        # a slot is either all tangent or all sine
     if not fold:
@@ -238,10 +263,9 @@ def eligible(program: StepProgram, block: Block, max_elements: int = 512) -> boo
     return n_diag <= 2
 
 
-def build(program: StepProgram, bound: BoundProgram, reg_bits: int | None = None) -> RRProgram | None:
+def _skeleton(program: StepProgram, bound: BoundProgram, reg_bits: int | None):
+    """Everything of the mapping that depends on the structure of the step only (not on parameter values)."""
     block = bound.block
-    if not eligible(program, block):
-        return None
     nb, cA, cB = block.n_bits, _log2(block.n_a), _log2(block.n_b)
     n = 2 * nb + cA + cB
     # logical bit numbers
@@ -253,7 +277,7 @@ def build(program: StepProgram, bound: BoundProgram, reg_bits: int | None = None
         reg_bits = min(4 if max(cA, cB) <= 1 else 3, n)
     reg_bits = min(reg_bits, n)
     if cA + cB > reg_bits or n - reg_bits > 5:
-        return None
+        return {'none': True}
     order = ket_cfg + bra_cfg                       # physical register bits, low to high
     rest = []
     for j in range(nb):
@@ -266,7 +290,7 @@ def build(program: StepProgram, bound: BoundProgram, reg_bits: int | None = None
     order += rest                                   # positions >= reg_bits are lane bits
     place = {lb: pos for pos, lb in enumerate(order)}
     if max(cA, cB) >= 2 and reg_bits > 3:
-        return None
+        return {'none': True}
     E, NR = block.size, 1 << reg_bits
     phys = np.arange(E)
     logical = np.zeros(E, dtype=np.int64)
@@ -346,8 +370,46 @@ def build(program: StepProgram, bound: BoundProgram, reg_bits: int | None = None
             ops.append([RR_AD, rx, la | lb, 0, shift + slot, 1, la, lb])
             labels.append('damp({})'.format(op.bit))
     if len(ops) > MAX_OPS:
+        return {'none': True}
+    return dict(ops=ops, tables=tables, labels=labels, logical=logical.astype(np.int32), a_of=a_of, b_of=b_of, shift=shift,
+                NR=NR, reg_bits=reg_bits, lane_bits=n - reg_bits, n_diag=n_diag, shared={})
+
+
+_SKELETONS: dict = {}
+
+
+def _structure_key(program: StepProgram):
+    sig = []
+    for op in program.lowered:
+        if isinstance(op, _Diag):
+            sig.append(('D', tuple((zs, zb) for zs, zb, _ in op.zterms), tuple(site for site, _ in op.deph)))
+        elif isinstance(op, _Hop):
+            sig.append(('H', op.i, op.j))
+        elif isinstance(op, _Prot):
+            sig.append(('P', op.xb, op.zb, op.site))
+        elif isinstance(op, Damp):
+            sig.append(('A', op.bit))
+        else:
+            sig.append((type(op).__name__, getattr(op, 'bit', None)))
+    return tuple(sig)
+
+
+def build(program: StepProgram, bound: BoundProgram, reg_bits: int | None = None) -> RRProgram | None:
+    block = bound.block
+    if not eligible(program, block):
         return None
-    fold_classes, folded_slots = _fold_cosines(ops, bound.params, E, NR, bool(tables), shift)
-    return RRProgram(block, reg_bits, n - reg_bits, n_diag, np.array(ops, dtype=np.int64).astype(np.uint32).view(np.int32).reshape(-1, 8),
-                     logical.astype(np.int32), labels, op_params=bound.params, diag_specs=tables, a_of=a_of, b_of=b_of,
-                     fold_classes=fold_classes, folded_slots=folded_slots)
+    key = (_structure_key(program), block, reg_bits)
+    sk = _SKELETONS.get(key)
+    if sk is None:
+        if len(_SKELETONS) > 256:
+            _SKELETONS.clear()
+        sk = _SKELETONS[key] = _skeleton(program, bound, reg_bits)
+    if sk.get('none'):
+        return None
+    ops = [list(op) for op in sk['ops']]
+    fold_classes, folded_slots = _fold_cosines(ops, bound.params, block.size, sk['NR'], bool(sk['tables']), sk['shift'],
+                                               sk['shared'])
+    return RRProgram(block, sk['reg_bits'], sk['lane_bits'], sk['n_diag'],
+                     np.array(ops, dtype=np.int64).astype(np.uint32).view(np.int32).reshape(-1, 8), sk['logical'],
+                     sk['labels'], op_params=bound.params, diag_specs=sk['tables'], a_of=sk['a_of'], b_of=sk['b_of'],
+                     fold_classes=fold_classes, folded_slots=folded_slots, _shared=sk['shared'])
