@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define QSX_ABI_VERSION 9
+#define QSX_ABI_VERSION 10
 
 enum {
     QSX_OK = 0,
@@ -248,6 +248,32 @@ int32_t qsx_evolve(const qsx_evolve_args* args, void* stream);
  * `mu` is DEVICE [N] doubles; blocks are [n_inst][D*D'] complex128. */
 int32_t qsx_apply_dipole(const qsx_block* in_blk, const qsx_block* out_blk, int32_t side, const double* mu,
                          int32_t n_inst, const double* sigma_in, double* sigma_out, void* stream);
+
+/* Parameter sets of the register-resident kernel assembled on the device from the per-set operation parameters
+ * (the angle tables StepProgram.bind produced): the diagonal tables in physical element order,
+ *   w[e] = GA[a_of[e]] * conj(GB[b_of[e]]) * T[cfg(a_of[e])][cfg(b_of[e])] * prod_c cos_c ^ count_c[e]   (first table),
+ * followed by the operation parameters with sin replaced by tan for the rotations run in tangent form.
+ * One launch; replaces the gather/multiply sequence the host used to issue op by op. */
+typedef struct {
+    int32_t n_sets;
+    int32_t n_elem;              /* E */
+    int32_t n_bits;              /* pseudomode bits per side */
+    int32_t n_cfg_b;             /* configurations on the bra side */
+    int32_t n_diag;              /* <= 2 */
+    int32_t slot_ga[2], slot_gb[2], slot_t[2];   /* into a row of op_params; slot_t = -1: no dephasing table */
+    int32_t n_classes;           /* <= 8 cosine classes folded into the first table */
+    int32_t class_slot[8];
+    const int8_t* class_count;   /* DEVICE [n_classes][E] exponents */
+    int32_t n_tangent;           /* <= 24 */
+    int32_t tangent_slot[24];    /* row[slot + 1] = sin / cos */
+    const int32_t* a_of;         /* DEVICE [E] */
+    const int32_t* b_of;         /* DEVICE [E] */
+    int32_t op_stride;           /* doubles per row of op_params */
+    const double* op_params;     /* DEVICE [n_sets][op_stride] */
+    double* out;                 /* DEVICE [n_sets][2*n_diag*E + op_stride] */
+} qsx_rr_tables_args;
+
+int32_t qsx_rr_tables(const qsx_rr_tables_args* args, void* stream);
 
 /* Lindblad limit of the collision model -- replaces the QuTiP solver calls of the comparison path
  * (qsextra/qcomo/evolution/clevolve.py:27-46 and :88-107: sesolve / mesolve(H, state, time, c_ops, e_ops)).

@@ -825,6 +825,43 @@ int32_t evolve_plan(const qsx_evolve_args* a, Plan* pl) {
 
 }  // namespace
 
+
+// Parameter sets of the register-resident kernel from the per-set operation parameters (see qsx_rr_tables_args).
+static __global__ void rr_tables_kernel(qsx_rr_tables_args a) {
+    const int E = a.n_elem;
+    const int n_table = a.n_diag * E;
+    const int out_stride = 2 * n_table + a.op_stride;
+    const int per_set = n_table + a.op_stride;                    // work items: one per table element, one per parameter
+    const long long total = (long long)a.n_sets * per_set;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / per_set), j = (int)(t % per_set);
+        const double* row = a.op_params + (size_t)b * a.op_stride;
+        double* out = a.out + (size_t)b * out_stride;
+        if (j < n_table) {
+            const int d = j / E, e = j % E;
+            const int ia = a.a_of[e], ib = a.b_of[e];
+            const double2 ga = make_double2(row[a.slot_ga[d] + 2 * ia], row[a.slot_ga[d] + 2 * ia + 1]);
+            const double2 gb = make_double2(row[a.slot_gb[d] + 2 * ib], row[a.slot_gb[d] + 2 * ib + 1]);
+            double2 w = make_double2(ga.x * gb.x + ga.y * gb.y, ga.y * gb.x - ga.x * gb.y);     // ga * conj(gb)
+            double f = 1.0;
+            if (a.slot_t[d] >= 0) f = row[a.slot_t[d] + (ia >> a.n_bits) * a.n_cfg_b + (ib >> a.n_bits)];
+            if (d == 0)
+                for (int c = 0; c < a.n_classes; ++c) {
+                    const double cs = row[a.class_slot[c]];
+                    for (int k = a.class_count[(size_t)c * E + e]; k > 0; --k) f *= cs;
+                }
+            out[2 * j] = w.x * f;
+            out[2 * j + 1] = w.y * f;
+        } else {
+            const int s_ = j - n_table;
+            double v = row[s_];
+            for (int k = 0; k < a.n_tangent; ++k)
+                if (a.tangent_slot[k] + 1 == s_) v = v / row[s_ - 1];
+            out[2 * n_table + s_] = v;
+        }
+    }
+}
+
 extern "C" {
 
 int32_t qsx_abi_version(void) { return QSX_ABI_VERSION; }
@@ -1043,6 +1080,33 @@ int32_t qsx_evolve_rrc(const qsx_rrc_args* a, void* stream) {
     int r = rrc::launch<0>(*a, sms, smem_max, (cudaStream_t)stream);
     if (r == 1) return fail(QSX_ERR_INVALID, "no compile-time program matches this block%s");
     if (r < 0) return fail(QSX_ERR_CUDA, "CUDA error: %s", cudaGetErrorString((cudaError_t)(-r)));
+    return QSX_OK;
+}
+
+int32_t qsx_rr_tables(const qsx_rr_tables_args* a, void* stream) {
+    if (!a) return fail(QSX_ERR_INVALID, "null args%s");
+    if (a->n_sets < 0 || a->n_elem < 1 || a->n_diag < 0 || a->n_diag > 2 || a->n_classes < 0 || a->n_classes > 8 ||
+        a->n_tangent < 0 || a->n_tangent > 24 || a->op_stride < 1 || a->n_bits < 0 || a->n_cfg_b < 1)
+        return fail(QSX_ERR_INVALID, "bad sizes%s");
+    if (a->n_sets == 0) return QSX_OK;
+    if (!a->op_params || !a->out || (a->n_diag > 0 && (!a->a_of || !a->b_of)) || (a->n_classes > 0 && !a->class_count))
+        return fail(QSX_ERR_INVALID, "null argument%s");
+    for (int d = 0; d < a->n_diag; ++d)
+        if (a->slot_ga[d] < 0 || a->slot_gb[d] < 0 || a->slot_ga[d] >= a->op_stride || a->slot_gb[d] >= a->op_stride ||
+            a->slot_t[d] >= a->op_stride)
+            return fail(QSX_ERR_INVALID, "table slot outside the parameter row%s");
+    for (int c = 0; c < a->n_classes; ++c)
+        if (a->class_slot[c] < 0 || a->class_slot[c] >= a->op_stride) return fail(QSX_ERR_INVALID, "class slot outside the row%s");
+    for (int k = 0; k < a->n_tangent; ++k)
+        if (a->tangent_slot[k] < 0 || a->tangent_slot[k] + 1 >= a->op_stride) return fail(QSX_ERR_INVALID, "tangent slot outside the row%s");
+    int sms = 0, smem_max = 0;
+    int32_t rc = device_limits(&sms, &smem_max);
+    if (rc) return rc;
+    long long total = (long long)a->n_sets * ((long long)a->n_diag * a->n_elem + a->op_stride);
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    rr_tables_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(*a);
+    QSX_CUDA(cudaGetLastError());
     return QSX_OK;
 }
 

@@ -11,10 +11,10 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libqsx.so')
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 EXPORTS = ('qsx_abi_version', 'qsx_last_error', 'qsx_device_info', 'qsx_evolve_workspace_bytes', 'qsx_evolve',
-           'qsx_evolve_rr', 'qsx_evolve_rrc', 'qsx_apply_dipole', 'qsx_rotating_frame', 'qsx_spectrum_shift',
+           'qsx_evolve_rr', 'qsx_rr_tables', 'qsx_evolve_rrc', 'qsx_apply_dipole', 'qsx_rotating_frame', 'qsx_spectrum_shift',
            'qsx_lindblad_workspace_bytes', 'qsx_lindblad_evolve',
            'qsx_fp64_peak')
 RR_MAX_OPS, RR_MAX_OBS, RR_MAX_ENTRIES = 24, 8, 4
@@ -86,6 +86,14 @@ class QsxRRCArgs(C.Structure):
 _lib = None
 
 
+class QsxRRTablesArgs(C.Structure):
+    _fields_ = [('n_sets', C.c_int32), ('n_elem', C.c_int32), ('n_bits', C.c_int32), ('n_cfg_b', C.c_int32),
+                ('n_diag', C.c_int32), ('slot_ga', C.c_int32 * 2), ('slot_gb', C.c_int32 * 2), ('slot_t', C.c_int32 * 2),
+                ('n_classes', C.c_int32), ('class_slot', C.c_int32 * 8), ('class_count', C.c_void_p),
+                ('n_tangent', C.c_int32), ('tangent_slot', C.c_int32 * 24), ('a_of', C.c_void_p), ('b_of', C.c_void_p),
+                ('op_stride', C.c_int32), ('op_params', C.c_void_p), ('out', C.c_void_p)]
+
+
 class QsxLindbladArgs(C.Structure):
     _fields_ = [('E', C.c_int32), ('width', C.c_int32), ('ell_idx', C.c_void_p), ('ell_val', C.c_void_p),
                 ('norm1', C.c_double), ('terms', C.c_int32), ('theta', C.c_double), ('n_inst', C.c_int32),
@@ -125,6 +133,8 @@ def load():
     lib.qsx_apply_dipole.argtypes = [C.POINTER(QsxBlock), C.POINTER(QsxBlock), C.c_int32, C.c_void_p, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
     lib.qsx_apply_dipole.restype = C.c_int32
+    lib.qsx_rr_tables.argtypes = [C.POINTER(QsxRRTablesArgs), C.c_void_p]
+    lib.qsx_rr_tables.restype = C.c_int32
     lib.qsx_lindblad_workspace_bytes.argtypes = [C.POINTER(QsxLindbladArgs)]
     lib.qsx_lindblad_workspace_bytes.restype = C.c_int64
     lib.qsx_lindblad_evolve.argtypes = [C.POINTER(QsxLindbladArgs), C.c_void_p]

@@ -70,30 +70,21 @@ class RRProgram:
         return self._params
 
     def device_params(self, eng):
-        """Same array as ``params`` built with device tensor ops from the small op-parameter array."""
+        """Same array as ``params`` assembled on the device by one ``qsx_rr_tables`` launch from the small
+        op-parameter array (index tables are uploaded once per structure)."""
         import torch
-        blk, nb, E = self.block, self.block.n_bits, self.block.size
-        P = eng.to_device(self.op_params, torch.float64)
-        B = P.shape[0]
-        a_of = torch.as_tensor(self.a_of, device=eng.device)
-        b_of = torch.as_tensor(self.b_of, device=eng.device)
-        parts = []
-        for d, (sa, sb, st) in enumerate(self.diag_specs):
-            ga = torch.view_as_complex(P[:, sa:sa + 2 * blk.dim_a].reshape(B, blk.dim_a, 2))
-            gb = torch.view_as_complex(P[:, sb:sb + 2 * blk.dim_b].reshape(B, blk.dim_b, 2))
-            w = ga[:, a_of] * gb.conj()[:, b_of]
-            if st >= 0:
-                t = P[:, st:st + blk.n_a * blk.n_b].reshape(B, blk.n_a, blk.n_b)
-                w = w * t[:, a_of >> nb, b_of >> nb]
-            if d == 0:
-                for slot, count in self.fold_classes:
-                    powers = torch.stack([P[:, slot] ** p for p in range(int(count.max()) + 1)], dim=1)
-                    w = w * powers[:, torch.as_tensor(count, device=eng.device)]
-            parts.append(torch.view_as_real(w).reshape(B, 2 * E))
-        P = P.clone()
-        for slot in self.folded_slots:
-            P[:, slot + 1] = P[:, slot + 1] / P[:, slot]
-        return torch.cat(parts + [P], dim=1).contiguous()
+        shared = self._shared if self._shared is not None else {}
+        key = ('dev', eng.device.index)
+        if key not in shared:
+            shared[key] = (eng.to_device(self.a_of, torch.int32), eng.to_device(self.b_of, torch.int32))
+        a_of, b_of = shared[key]
+        counts = None
+        if self.fold_classes:
+            ckey = ('dev_counts', eng.device.index, tuple(np.asarray(c).tobytes() for _, c in self.fold_classes))
+            if ckey not in shared:
+                shared[ckey] = eng.to_device(np.stack([c for _, c in self.fold_classes]).astype(np.int8), torch.int8)
+            counts = shared[ckey]
+        return eng.rr_tables(self, eng.to_device(self.op_params, torch.float64), a_of, b_of, counts)
 
     @property
     def team(self):

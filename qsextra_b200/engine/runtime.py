@@ -268,6 +268,32 @@ class Engine:
             self.launches += 1
         return out
 
+    def rr_tables(self, rrp, op_params: torch.Tensor, a_of: torch.Tensor, b_of: torch.Tensor, counts):
+        """Parameter sets [B, stride] of the register-resident kernel from the op parameters (``qsx_rr_tables``)."""
+        blk = rrp.block
+        B, S = op_params.shape
+        args = cabi.QsxRRTablesArgs()
+        args.n_sets, args.n_elem, args.n_bits, args.n_cfg_b = int(B), blk.size, blk.n_bits, blk.n_b
+        args.n_diag = len(rrp.diag_specs)
+        for d, (sa, sb, st) in enumerate(rrp.diag_specs):
+            args.slot_ga[d], args.slot_gb[d], args.slot_t[d] = int(sa), int(sb), int(st)
+        args.n_classes = len(rrp.fold_classes)
+        for c, (slot, _) in enumerate(rrp.fold_classes):
+            args.class_slot[c] = int(slot)
+        args.class_count = None if counts is None else counts.data_ptr()
+        args.n_tangent = len(rrp.folded_slots)
+        for k, slot in enumerate(rrp.folded_slots):
+            args.tangent_slot[k] = int(slot)
+        args.a_of, args.b_of = a_of.data_ptr(), b_of.data_ptr()
+        args.op_stride, args.op_params = int(S), op_params.data_ptr()
+        out = torch.empty((B, rrp.stride), dtype=torch.float64, device=self.device)
+        args.out = out.data_ptr()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            cabi.check(self.lib.qsx_rr_tables(C.byref(args), C.c_void_p(stream)))
+        self.aux_launches = getattr(self, 'aux_launches', 0) + 1
+        return out
+
     # ---- Lindblad limit ----------------------------------------------------------------------------
     def upload_lindblad(self, bound):
         """Device tables of a ``lindblad.BoundLindblad`` (ELL generator of one block)."""

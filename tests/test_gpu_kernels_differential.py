@@ -89,3 +89,29 @@ def test_all_kernel_families_agree_with_emulated_operations(engine, name, system
         assert any('[rr]' in s for s in seen)
     if name in ('trimer_modes', 'chain4_modes'):
         assert any('[rrc]' in s for s in seen)
+
+
+def test_parameter_sets_assembled_on_the_device_match_the_host_recipe(engine):
+    """qsx_rr_tables against RRProgram.params (NumPy) for a batch of random parameter sets, with and without folds."""
+    from qsextra_b200.engine import rr as rr_mod
+    from qsextra_b200.engine.program import StepProgram, SystemBatch
+    rng = np.random.default_rng(17)
+    B = 37
+    batch = SystemBatch(rng.uniform(1.4, 1.6, (B, 2)), np.broadcast_to(np.array([[0., -0.05], [-0.05, 0.]]), (B, 2, 2)).copy(),
+                        np.ones((B, 2)), rng.uniform(0.05, 0.2, (B, 1)), rng.uniform(0.05, 0.2, (B, 1)), (2,))
+    markov = SystemBatch(rng.uniform(1.4, 1.6, (B, 2)), np.broadcast_to(np.array([[0., -0.05], [-0.05, 0.]]), (B, 2, 2)).copy(),
+                         np.ones((B, 2)))
+    cases = [(StepProgram(batch, 0.15, 1, 1, rng.uniform(0.1, 0.4, (B, 1))), [(1, 1), (2, 1), (1, 0)]),
+             (StepProgram(markov, 0.15, 1, 1, rng.uniform(0.01, 0.1, B)), [(1, 1), (2, 1)])]
+    seen_fold = False
+    for prog, blocks in cases:
+        for ka, kb in blocks:
+            bound = prog.bind(prog.block(ka, kb), fused=False)
+            rrp = rr_mod.build(prog, bound)
+            assert rrp is not None
+            seen_fold |= bool(rrp.fold_classes)
+            got = rrp.device_params(engine).cpu().numpy()
+            want = rrp.params
+            assert got.shape == want.shape
+            assert np.abs(got - want).max() <= 2e-15 * max(1.0, np.abs(want).max())
+    assert seen_fold
