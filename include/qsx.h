@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define QSX_ABI_VERSION 10
+#define QSX_ABI_VERSION 11
 
 enum {
     QSX_OK = 0,
@@ -248,6 +248,15 @@ int32_t qsx_evolve(const qsx_evolve_args* args, void* stream);
  * `mu` is DEVICE [N] doubles; blocks are [n_inst][D*D'] complex128. */
 int32_t qsx_apply_dipole(const qsx_block* in_blk, const qsx_block* out_blk, int32_t side, const double* mu,
                          int32_t n_inst, const double* sigma_in, double* sigma_out, void* stream);
+
+/* Parameter rows of a bound step program evaluated on the device from the raw angles of the step (what
+ * StepProgram.bind computes on the host: the cos/sin pairs of every rotation and the phase tables of the merged Z
+ * rotations).  Column c of every row:  phase = sum_{t in [ptr[c], ptr[c+1])} coef[t] * angles[set][idx[t]];
+ *   kind 0: 0   1: cos(phase)   2: sin(phase)   3: -sin(phase)   4: sin(phase)^2
+ *   kind 5: prod_t (cos^2 - sin^2)(angles[set][idx[t]])          (dephasing factors)
+ * All pointers DEVICE; angles [n_sets][n_raw], out [n_sets][n_cols]. */
+int32_t qsx_bind_params(int32_t n_sets, int32_t n_cols, int32_t n_raw, const int32_t* kind, const int32_t* ptr,
+                        const int32_t* idx, const double* coef, const double* angles, double* out, void* stream);
 
 /* Parameter sets of the register-resident kernel assembled on the device from the per-set operation parameters
  * (the angle tables StepProgram.bind produced): the diagonal tables in physical element order,

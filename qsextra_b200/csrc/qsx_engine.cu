@@ -826,6 +826,34 @@ int32_t evolve_plan(const qsx_evolve_args* a, Plan* pl) {
 }  // namespace
 
 
+// Parameter rows from raw angles (see qsx_bind_params): one thread per (set, column).
+static __global__ void bind_params_kernel(int n_sets, int n_cols, int n_raw, const int* __restrict__ kind,
+                                          const int* __restrict__ ptr, const int* __restrict__ idx,
+                                          const double* __restrict__ coef, const double* __restrict__ angles, double* out) {
+    const long long total = (long long)n_sets * n_cols;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / n_cols), c = (int)(t % n_cols);
+        const double* row = angles + (size_t)b * n_raw;
+        const int k = kind[c];
+        double v = 0.0;
+        if (k == 5) {
+            v = 1.0;
+            for (int j = ptr[c]; j < ptr[c + 1]; ++j) {
+                double sn, cs;
+                sincos(row[idx[j]], &sn, &cs);
+                v *= cs * cs - sn * sn;
+            }
+        } else if (k != 0) {
+            double phase = 0.0;
+            for (int j = ptr[c]; j < ptr[c + 1]; ++j) phase += row[idx[j]] * coef[j];
+            double sn, cs;
+            sincos(phase, &sn, &cs);
+            v = k == 1 ? cs : k == 2 ? sn : k == 3 ? -sn : sn * sn;
+        }
+        out[t] = v;
+    }
+}
+
 // Parameter sets of the register-resident kernel from the per-set operation parameters (see qsx_rr_tables_args).
 static __global__ void rr_tables_kernel(qsx_rr_tables_args a) {
     const int E = a.n_elem;
@@ -1080,6 +1108,22 @@ int32_t qsx_evolve_rrc(const qsx_rrc_args* a, void* stream) {
     int r = rrc::launch<0>(*a, sms, smem_max, (cudaStream_t)stream);
     if (r == 1) return fail(QSX_ERR_INVALID, "no compile-time program matches this block%s");
     if (r < 0) return fail(QSX_ERR_CUDA, "CUDA error: %s", cudaGetErrorString((cudaError_t)(-r)));
+    return QSX_OK;
+}
+
+int32_t qsx_bind_params(int32_t n_sets, int32_t n_cols, int32_t n_raw, const int32_t* kind, const int32_t* ptr,
+                        const int32_t* idx, const double* coef, const double* angles, double* out, void* stream) {
+    if (n_sets < 0 || n_cols < 0 || n_raw < 1) return fail(QSX_ERR_INVALID, "bad sizes%s");
+    if (n_sets == 0 || n_cols == 0) return QSX_OK;
+    if (!kind || !ptr || !idx || !coef || !angles || !out) return fail(QSX_ERR_INVALID, "null argument%s");
+    int sms = 0, smem_max = 0;
+    int32_t rc = device_limits(&sms, &smem_max);
+    if (rc) return rc;
+    long long total = (long long)n_sets * n_cols;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    bind_params_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(n_sets, n_cols, n_raw, kind, ptr, idx, coef, angles, out);
+    QSX_CUDA(cudaGetLastError());
     return QSX_OK;
 }
 

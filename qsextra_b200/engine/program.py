@@ -409,16 +409,153 @@ def lower(terms, n_sites: int):
 # ---------------------------------------------------------------------------------------------
 # step program bound to a sector block
 # ---------------------------------------------------------------------------------------------
-@dataclass
+class ParamRecipe:
+    """The parameter row of a bound program as functions of the raw angles of the step:
+
+        column value = kind( sum_j coef_j * raw_j )        COS | SIN | NSIN (-sin) | SIN2 (sin squared)
+                     = prod_j (cos^2 - sin^2)(raw_j)       PRODCOS (dephasing factors)
+                     = 0                                   ZERO (padding that keeps slots 16-byte aligned)
+
+    Evaluated on the host (``evaluate``, NumPy) or on the device (``qsx_bind_params``) from the matrix of raw angles
+    [B, R]; both follow the same order of operations, column by column."""
+    ZERO, COS, SIN, NSIN, SIN2, PRODCOS = 0, 1, 2, 3, 4, 5
+
+    def __init__(self, n_sets: int):
+        self.n_sets = n_sets
+        self.raws, self._raw_id, self._angles = [], {}, None
+        self.kind, self.terms = [], []              # per column: kind, [(raw index, coefficient), ...]
+
+    def raw(self, values: np.ndarray) -> int:
+        key = id(values)
+        if key not in self._raw_id:
+            self._raw_id[key] = len(self.raws)
+            self._angles = None
+            self.raws.append(np.ascontiguousarray(values, dtype=np.float64).reshape(self.n_sets))
+        return self._raw_id[key]
+
+    def column(self, kind: int, terms=()) -> int:
+        self.kind.append(kind)
+        self.terms.append(list(terms))
+        return len(self.kind) - 1
+
+    def align(self):
+        if len(self.kind) % 2:
+            self.column(self.ZERO)
+
+    @property
+    def width(self) -> int:
+        return len(self.kind)
+
+    def angles(self) -> np.ndarray:
+        """[B, R] raw angles (R >= 1)."""
+        if self._angles is None:
+            self._angles = np.stack(self.raws, axis=1) if self.raws else np.zeros((self.n_sets, 1))
+        return self._angles
+
+    def tables(self):
+        """(kind [S] int32, ptr [S+1] int32, idx [nnz] int32, coef [nnz] float64) for the device evaluation."""
+        ptr = np.zeros(self.width + 1, dtype=np.int32)
+        ptr[1:] = np.cumsum([len(t) for t in self.terms])
+        idx = np.array([j for t in self.terms for j, _ in t], dtype=np.int32)
+        coef = np.array([c for t in self.terms for _, c in t], dtype=np.float64)
+        return np.array(self.kind, dtype=np.int32), ptr, idx, coef
+
+    def phases(self, columns) -> np.ndarray:
+        """[len(columns), B] phases of linear columns (no trigonometry)."""
+        out = np.zeros((len(columns), self.n_sets))
+        for r, c in enumerate(columns):
+            for j, coef in self.terms[c]:
+                out[r] += self.raws[j] * coef
+        return out
+
+    def evaluate(self, columns=None) -> np.ndarray:
+        """[B, S] on the host (or only ``columns``).  Works column-major ([S, B] rows are contiguous)."""
+        raws = self.raws
+        cols = list(range(self.width) if columns is None else columns)
+        kinds = np.array([self.kind[c] for c in cols], dtype=np.int64)
+        terms = [self.terms[c] for c in cols]
+        out = np.zeros((len(cols), self.n_sets))
+        linear = [k for k in range(len(cols)) if self.COS <= kinds[k] <= self.SIN2]
+        if linear:
+            # columns with the same term list share one phase (cos and -sin of a table entry, ket and bra tables of a
+            # diagonal block): evaluate every distinct phase, its cosine and its sine once
+            unique, phase_of = {}, []
+            for k in linear:
+                phase_of.append(unique.setdefault(tuple(terms[k]), len(unique)))
+            lists = list(unique)
+            phase = np.zeros((len(lists), self.n_sets))
+            for t in range(max(len(tl) for tl in lists)):        # term by term: identical term lists give identical bits
+                rows = [u for u, tl in enumerate(lists) if len(tl) > t]
+                src = np.stack([raws[lists[u][t][0]] for u in rows])
+                src *= np.array([lists[u][t][1] for u in rows])[:, None]
+                if len(rows) == len(lists):
+                    phase += src
+                else:
+                    phase[rows] += src
+            phase_of = np.array(phase_of)
+            lin_kinds = kinds[linear]
+            need_cos = np.unique(phase_of[lin_kinds == self.COS])
+            need_sin = np.unique(phase_of[lin_kinds != self.COS])
+            cosines = dict(zip(need_cos.tolist(), np.cos(phase[need_cos]))) if need_cos.size else {}
+            sines = dict(zip(need_sin.tolist(), np.sin(phase[need_sin]))) if need_sin.size else {}
+            for k, u, kind in zip(linear, phase_of.tolist(), lin_kinds.tolist()):
+                if kind == self.COS:
+                    out[k] = cosines[u]
+                elif kind == self.SIN:
+                    out[k] = sines[u]
+                elif kind == self.NSIN:
+                    np.negative(sines[u], out=out[k])
+                else:
+                    np.multiply(sines[u], sines[u], out=out[k])
+        for k in np.nonzero(kinds == self.PRODCOS)[0]:
+            value = np.ones(self.n_sets)
+            for j, _ in terms[k]:
+                c, s_ = np.cos(raws[j]), np.sin(raws[j])
+                value = value * (c * c - s_ * s_)
+            out[k] = value
+        return np.ascontiguousarray(out.T)
+
+
 class BoundProgram:
-    block: Block
-    ops: np.ndarray          # [n_ops, 8] int32 (qsx_op)
-    params: np.ndarray       # [B, stride] float64
-    labels: list             # human-readable op names, for reports
-    passes: np.ndarray = None    # [n_passes, 12] int32 (qsx_pass) or None: run the plain operation list
-    tiles: np.ndarray = None
-    hops: np.ndarray = None
-    team: int = 0                # threads per instance the pass tables were built for (0: library default)
+    """A step program bound to one (KA, KB) block: the qsx_op array, the parameter rows (evaluated from ``recipe`` on
+    first use, or handed in) and, when fused, the pass tables."""
+
+    def __init__(self, block: Block, ops: np.ndarray, params: np.ndarray = None, labels: list = None, passes=None,
+                 tiles=None, hops=None, team: int = 0, recipe: ParamRecipe = None):
+        self.block = block
+        self.ops = ops                   # [n_ops, 8] int32 (qsx_op)
+        self._params = params            # [B, stride] float64
+        self.labels = labels if labels is not None else []
+        self.passes = passes             # [n_passes, 12] int32 (qsx_pass) or None: run the plain operation list
+        self.tiles = tiles
+        self.hops = hops
+        self.team = team                 # threads per instance the pass tables were built for (0: library default)
+        self.recipe = recipe
+
+    @property
+    def params(self) -> np.ndarray:
+        if self._params is None:
+            self._params = self.recipe.evaluate() if self.recipe.width else np.zeros((self.recipe.n_sets, 2))
+        return self._params
+
+    @property
+    def n_sets(self) -> int:
+        return self._params.shape[0] if self._params is not None else self.recipe.n_sets
+
+    @property
+    def stride(self) -> int:
+        return self._params.shape[1] if self._params is not None else max(self.recipe.width, 2)
+
+    def phases(self, slots) -> np.ndarray:
+        """[len(slots), B] rotation angles behind the cos/sin columns ``slots`` (from the recipe, no trigonometry)."""
+        return self.recipe.phases(list(slots))
+
+    def columns(self, slots) -> np.ndarray:
+        """Some parameter columns [B, len(slots)] without evaluating the whole row."""
+        slots = list(slots)
+        if self._params is not None:
+            return self._params[:, slots]
+        return self.recipe.evaluate(slots)
 
 
 class StepProgram:
@@ -446,71 +583,70 @@ class StepProgram:
         """Angle tables, qsx_op array and (``fused``) the equivalent pass program for one (KA, KB) block."""
         B = self.batch.batch
         nb = block.n_bits
-        chunks, ops, labels = [], [], []
+        ops, labels = [], []
         op_slots = []                                # per lowered op: (index in ops, {name: parameter slot})
-        cursor = 0
-
-        def push(arr):                               # arr [B, n] doubles; slots are kept even (16-byte aligned)
-            nonlocal cursor
-            slot = cursor
-            arr = np.ascontiguousarray(arr, dtype=np.float64).reshape(B, -1)
-            if arr.shape[1] % 2:
-                arr = np.concatenate([arr, np.zeros((B, 1))], axis=1)
-            chunks.append(arr)
-            cursor += arr.shape[1]
-            return slot
-
+        recipe = ParamRecipe(B)
+        R = ParamRecipe
         bits_of = np.arange(1 << nb, dtype=np.int64)
-        table_cache = {}
 
-        def side_table(cfgs, zterms, key):
-            """exp(-i phase) of the merged Z rotations for every (configuration, mode bits) of one side, [B, 2*dim]."""
-            if (key, tuple(cfgs)) in table_cache:                # ket and bra sides share the table when KA == KB
-                return table_cache[key, tuple(cfgs)]
+        def side_table(cfgs, zterms):
+            """exp(-i phase) of the merged Z rotations for every (configuration, mode bits) of one side: 2*dim
+            columns (cos, -sin); returns the slot."""
+            recipe.align()
+            slot = recipe.width
             masks = np.array(cfgs, dtype=np.int64)
-            phase = np.zeros((B, len(cfgs), 1 << nb))
+            signs = []
             for zs, zb, ang in zterms:
                 par = (_popcount_array(masks & zs)[:, None] + _popcount_array(bits_of & zb)[None, :]) & 1
-                phase += ang[:, None, None] * (1 - 2 * par)[None]
-            out = np.empty((B, len(cfgs) << nb, 2))
-            flat = phase.reshape(B, -1)
-            np.cos(flat, out=out[:, :, 0])
-            np.sin(flat, out=out[:, :, 1])
-            np.negative(out[:, :, 1], out=out[:, :, 1])
-            table_cache[key, tuple(cfgs)] = out = out.reshape(B, -1)
-            return out
+                signs.append((recipe.raw(ang), (1.0 - 2.0 * par).reshape(-1)))
+            for e in range(len(cfgs) << nb):
+                terms = [(j, sg[e]) for j, sg in signs]
+                recipe.column(R.COS, terms)
+                recipe.column(R.NSIN, terms)
+            return slot
 
         for op in self.lowered:
             if isinstance(op, _Diag):
-                slot_a = push(side_table(block.cfg_a, op.zterms, id(op)))
-                slot_b = push(side_table(block.cfg_b, op.zterms, id(op)))
+                slot_a = side_table(block.cfg_a, op.zterms)
+                slot_b = side_table(block.cfg_b, op.zterms)
                 slot_t = -1
                 if op.deph:
-                    t = np.ones((B, block.n_a, block.n_b))
-                    differs = np.array([[[(ca >> s) & 1 != (cb >> s) & 1 for cb in block.cfg_b] for ca in block.cfg_a]
-                                        for s in range(self.n_sites)])
-                    for site, phi in op.deph:
-                        c, s = np.cos(phi), np.sin(phi)
-                        t = t * np.where(differs[site][None], (c * c - s * s)[:, None, None], 1.0)
-                    slot_t = push(t)
+                    recipe.align()
+                    slot_t = recipe.width
+                    for ca in block.cfg_a:
+                        for cb in block.cfg_b:
+                            recipe.column(R.PRODCOS, [(recipe.raw(phi), 2.0) for site, phi in op.deph
+                                                      if (ca >> site) & 1 != (cb >> site) & 1])
                 op_slots.append((len(ops), dict(ga=slot_a, gb=slot_b, t=slot_t)))
                 ops.append([OP_DIAG, slot_a, slot_b, slot_t, 0, 0, 0, 0])
                 labels.append('diag')
             elif isinstance(op, _Hop):
-                slot = push(np.stack([np.cos(2 * op.xx), np.sin(2 * op.xx)], axis=1))
+                recipe.align()
+                slot = recipe.width
+                j = recipe.raw(op.xx)
+                recipe.column(R.COS, [(j, 2.0)])
+                recipe.column(R.SIN, [(j, 2.0)])
                 op_slots.append((len(ops), dict(cs=slot)))
                 ops.append([OP_HOP, op.i, op.j, 0, 0, 0, slot, 0])
                 labels.append('hop({},{})'.format(op.i, op.j))
             elif isinstance(op, _Prot):
-                th0, th1 = op.plain + op.signed, op.plain - op.signed      # Z_site = +1 (empty) / -1 (occupied)
-                skip0 = int(op.site >= 0 and not np.any(th0 != 0))
-                slot = push(np.stack([np.cos(th0), np.sin(th0), np.cos(th1), np.sin(th1)], axis=1))
+                skip0 = int(op.site >= 0 and not np.any(op.plain + op.signed != 0))   # Z_site = +1 (empty) / -1 (occupied)
+                recipe.align()
+                slot = recipe.width
+                jp, js = recipe.raw(op.plain), recipe.raw(op.signed)
+                for sign in (1.0, -1.0):
+                    recipe.column(R.COS, [(jp, 1.0), (js, sign)])
+                    recipe.column(R.SIN, [(jp, 1.0), (js, sign)])
                 ny = _popcount(op.xb & op.zb) & 3
                 op_slots.append((len(ops), dict(cs=slot, skip0=skip0)))
                 ops.append([OP_PROT, op.xb, op.zb, ny, op.site, skip0, slot, 0])
                 labels.append('prot(x={:b},z={:b},site={})'.format(op.xb, op.zb, op.site))
             elif isinstance(op, Damp):
-                slot = push(np.stack([np.cos(op.phi), np.sin(op.phi) ** 2], axis=1))
+                recipe.align()
+                slot = recipe.width
+                j = recipe.raw(op.phi)
+                recipe.column(R.COS, [(j, 1.0)])
+                recipe.column(R.SIN2, [(j, 1.0)])
                 op_slots.append((len(ops), dict(cs=slot)))
                 ops.append([OP_AD, op.bit, 0, 0, 0, 0, slot, 0])
                 labels.append('damp({})'.format(op.bit))
@@ -518,8 +654,8 @@ class StepProgram:
                 op_slots.append((len(ops), {}))
                 ops.append([OP_RESET, op.bit, 0, 0, 0, 0, 0, 0])
                 labels.append('reset({})'.format(op.bit))
-        params = np.concatenate(chunks, axis=1) if chunks else np.zeros((B, 2))
-        bound = BoundProgram(block, np.array(ops, dtype=np.int32).reshape(-1, 8), params, labels)
+        recipe.align()
+        bound = BoundProgram(block, np.array(ops, dtype=np.int32).reshape(-1, 8), None, labels, recipe=recipe)
         if fused and self.lowered and block.size * 16 <= 220 * 1024:      # larger blocks stream through global memory
             from .passes import build_passes, default_team
             bound.team = team or default_team(block)

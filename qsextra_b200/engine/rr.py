@@ -29,7 +29,7 @@ class RRProgram:
     logical_index: np.ndarray   # [E] int32: physical -> logical
     labels: list
     # recipe of the parameter sets: n_diag tables (physical order) followed by the op parameters
-    op_params: np.ndarray = None      # [B, S] float64 as bound by StepProgram.bind (cos/sin pairs, GA/GB tables)
+    bound: BoundProgram = None        # source of op_params: [B, S] float64 (cos/sin pairs, GA/GB tables), evaluated lazily
     diag_specs: list = None           # per diagonal table: (slot GA, slot GB, slot T or -1) into op_params
     a_of: np.ndarray = None           # [E] ket index of every physical element
     b_of: np.ndarray = None
@@ -39,8 +39,12 @@ class RRProgram:
     _shared: dict = None              # results that depend on the structure only, shared by programs of equal structure
 
     @property
+    def op_params(self) -> np.ndarray:
+        return self.bound.params
+
+    @property
     def stride(self) -> int:
-        return 2 * self.n_diag * self.block.size + self.op_params.shape[1]
+        return 2 * self.n_diag * self.block.size + self.bound.stride
 
     @property
     def params(self) -> np.ndarray:
@@ -84,7 +88,7 @@ class RRProgram:
             if ckey not in shared:
                 shared[ckey] = eng.to_device(np.stack([c for _, c in self.fold_classes]).astype(np.int8), torch.int8)
             counts = shared[ckey]
-        return eng.rr_tables(self, eng.to_device(self.op_params, torch.float64), a_of, b_of, counts)
+        return eng.rr_tables(self, eng.bind_params(self.bound), a_of, b_of, counts)
 
     @property
     def team(self):
@@ -185,13 +189,14 @@ class RRProgram:
         return out
 
 
-def _fold_cosines(ops, params, E, NR, has_table, shift, shared=None):
+def _fold_cosines(ops, phases, E, NR, has_table, shift, shared=None):
     """Tangent form where it is exact (engine/fold.py): the cos factors of the foldable rotations are to be multiplied
     into the first diagonal table, element by element following each rotation's participation mask, and those
     rotations become QSX_RR_ROTT: two fused multiply-adds per element and side instead of two multiplies and two.
-    ``params`` is the op-parameter array (slots relative to it = op slot - shift).  Returns (fold_classes,
+    ``phases(slots)`` gives the rotation angles [len(slots), B] behind op-parameter columns (slots relative to the op
+    parameters = op slot - shift); cosines are compared and bounded through the angles, without trigonometry.  Returns (fold_classes,
     folded_slots): [(cosine slot, exponent per element)] and the slots whose sine becomes a tangent.  Nothing is folded
-    when the step has no diagonal table; rotations with some |cos| < 0.5 are never folded."""
+    when the step has no diagonal table; rotations with some |angle| > pi/3 (|cos| < 0.5) are never folded."""
     from .fold import foldable, value_classes
     if not has_table or not any(op[0] == RR_ROT for op in ops):
         return [], []
@@ -199,12 +204,15 @@ def _fold_cosines(ops, params, E, NR, has_table, shift, shared=None):
     reg, lane = phys & (NR - 1), phys // NR
     rot_idx = [k for k, op in enumerate(ops) if op[0] == RR_ROT]
     col = lambda op: op[4] - shift
-    cls_of = dict(zip(rot_idx, value_classes([params[:, col(ops[k])] for k in rot_idx])))
+    angles = np.abs(phases([col(ops[k]) for k in rot_idx]))            # cos is even: +-angle give the same cosine
+    cls_of = dict(zip(rot_idx, value_classes(list(angles))))
+    # |angle| <= pi/3 guarantees |cos| >= 0.5 (larger angles are simply not folded)
+    well = {k: bool(angles[pos].max() <= np.pi / 3) for pos, k in enumerate(rot_idx)}
     info = []
     for k, op in enumerate(ops):
         partner = ((lane ^ op[2]) * NR) | (reg ^ op[1])
         if op[0] == RR_ROT:
-            ok = not np.any(np.abs(params[:, col(op)]) < 0.5)
+            ok = well[k]
             info.append(dict(mixes=True, takes_part=((op[3] >> reg) & 1).astype(bool), partner=partner,
                              cls=cls_of[k] if ok else None))
         elif op[0] == RR_AD:
@@ -302,7 +310,6 @@ def _skeleton(program: StepProgram, bound: BoundProgram, reg_bits: int | None):
             out |= ((np.arange(NR) >> place[lb]) & 1) << k
         return out
 
-    B = bound.params.shape[0]
     base = 0                                        # filled below: tables come first
     tables, ops, labels = [], [], []
     ranks = (sector_rank(block.n_sites, block.ka), sector_rank(block.n_sites, block.kb))
@@ -398,9 +405,9 @@ def build(program: StepProgram, bound: BoundProgram, reg_bits: int | None = None
     if sk.get('none'):
         return None
     ops = [list(op) for op in sk['ops']]
-    fold_classes, folded_slots = _fold_cosines(ops, bound.params, block.size, sk['NR'], bool(sk['tables']), sk['shift'],
+    fold_classes, folded_slots = _fold_cosines(ops, bound.phases, block.size, sk['NR'], bool(sk['tables']), sk['shift'],
                                                sk['shared'])
     return RRProgram(block, sk['reg_bits'], sk['lane_bits'], sk['n_diag'],
                      np.array(ops, dtype=np.int64).astype(np.uint32).view(np.int32).reshape(-1, 8), sk['logical'],
-                     sk['labels'], op_params=bound.params, diag_specs=sk['tables'], a_of=sk['a_of'], b_of=sk['b_of'],
+                     sk['labels'], bound=bound, diag_specs=sk['tables'], a_of=sk['a_of'], b_of=sk['b_of'],
                      fold_classes=fold_classes, folded_slots=folded_slots, _shared=sk['shared'])

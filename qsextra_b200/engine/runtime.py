@@ -43,6 +43,8 @@ class Engine:
             raise cabi.QsxError('no CUDA device: the qsextra_b200 engine has no CPU fallback')
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self._blocks: dict[Block, DeviceBlock] = {}
+        self._recipes: dict = {}              # device copies of parameter recipes, by content
+        self.aux_launches = 0                 # table-assembly kernels (qsx_bind_params, qsx_rr_tables)
         self.launches = 0                     # kernels enqueued through this engine (bench bookkeeping)
         self.h2d_bytes = 0                    # bytes copied host -> device through to_device()
         with torch.cuda.device(self.device):
@@ -77,8 +79,8 @@ class Engine:
         dev = dict(block=self.device_block(bound.block),
                    ops=self.to_device(bound.ops, torch.int32),
                    params=None if rr_entries else self.to_device(bound.params, torch.float64),
-                   bound=bound, n_ops=int(bound.ops.shape[0]), stride=int(bound.params.shape[1]),
-                   n_sets=int(bound.params.shape[0]), n_passes=0, team=0)
+                   bound=bound, n_ops=int(bound.ops.shape[0]), stride=int(bound.stride),
+                   n_sets=int(bound.n_sets), n_passes=0, team=0)
         if bound.passes is not None and len(bound.passes):
             dev.update(n_passes=int(bound.passes.shape[0]), team=int(bound.team),
                        passes=self.to_device(bound.passes, torch.int32),
@@ -268,6 +270,32 @@ class Engine:
             self.launches += 1
         return out
 
+    def bind_params(self, bound):
+        """Parameter rows [B, stride] of a bound program on the device: evaluated there from the raw angles of the
+        step (``qsx_bind_params``) when the program carries its recipe, else uploaded."""
+        if bound.recipe is None or bound._params is not None or not bound.recipe.width:
+            return self.to_device(bound.params, torch.float64)
+        recipe = bound.recipe
+        kind, ptr, idx, coef = recipe.tables()
+        key = (kind.tobytes(), ptr.tobytes(), idx.tobytes(), coef.tobytes())
+        tabs = self._recipes.get(key)
+        if tabs is None:
+            if len(self._recipes) > 256:
+                self._recipes.clear()
+            tabs = self._recipes[key] = (self.to_device(kind, torch.int32), self.to_device(ptr, torch.int32),
+                                         self.to_device(idx if idx.size else np.zeros(1, np.int32), torch.int32),
+                                         self.to_device(coef if coef.size else np.zeros(1)))
+        angles = self.to_device(recipe.angles())
+        out = torch.empty((recipe.n_sets, recipe.width), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            cabi.check(self.lib.qsx_bind_params(recipe.n_sets, recipe.width, int(angles.shape[1]),
+                                                C.c_void_p(tabs[0].data_ptr()), C.c_void_p(tabs[1].data_ptr()),
+                                                C.c_void_p(tabs[2].data_ptr()), C.c_void_p(tabs[3].data_ptr()),
+                                                C.c_void_p(angles.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(stream)))
+        self.aux_launches += 1
+        return out
+
     def rr_tables(self, rrp, op_params: torch.Tensor, a_of: torch.Tensor, b_of: torch.Tensor, counts):
         """Parameter sets [B, stride] of the register-resident kernel from the op parameters (``qsx_rr_tables``)."""
         blk = rrp.block
@@ -291,7 +319,7 @@ class Engine:
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             cabi.check(self.lib.qsx_rr_tables(C.byref(args), C.c_void_p(stream)))
-        self.aux_launches = getattr(self, 'aux_launches', 0) + 1
+        self.aux_launches += 1
         return out
 
     # ---- Lindblad limit ----------------------------------------------------------------------------

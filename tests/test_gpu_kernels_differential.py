@@ -115,3 +115,16 @@ def test_parameter_sets_assembled_on_the_device_match_the_host_recipe(engine):
             assert got.shape == want.shape
             assert np.abs(got - want).max() <= 2e-15 * max(1.0, np.abs(want).max())
     assert seen_fold
+
+
+@pytest.mark.parametrize('name,system,kw,blocks', CASES, ids=[c[0] for c in CASES])
+def test_parameter_rows_evaluated_on_the_device_match_the_host(engine, name, system, kw, blocks):
+    """qsx_bind_params against ParamRecipe.evaluate (NumPy): same recipe, device sincos instead of libm."""
+    tn = kw.get('Trotter_number', 1)
+    prog = _program_for(system, 0.15, 0.15 / tn, tn, kw.get('Trotter_order', 1), kw.get('coll_rates'))
+    for ka, kb in blocks:
+        bound = prog.bind(prog.block(ka, kb), fused=False)
+        assert bound._params is None                       # nothing evaluated on the host yet
+        got = engine.bind_params(bound).cpu().numpy()
+        want = bound.params
+        assert got.shape == want.shape and np.abs(got - want).max() < 1e-15
