@@ -323,13 +323,12 @@ def _popcount(v: int) -> int:
     return bin(v).count('1')
 
 
+_POP16 = np.array([bin(v).count('1') for v in range(1 << 16)], dtype=np.int64)
+
+
 def _popcount_array(values: np.ndarray) -> np.ndarray:
-    out = np.zeros(values.shape, dtype=np.int64)
     v = values.astype(np.int64)
-    while np.any(v):
-        out += v & 1
-        v = v >> 1
-    return out
+    return _POP16[v & 0xffff] + _POP16[(v >> 16) & 0xffff] + _POP16[(v >> 32) & 0xffff]
 
 
 def _z_commutes(op, zs: int, zb: int) -> bool:
@@ -409,6 +408,10 @@ def lower(terms, n_sites: int):
 # ---------------------------------------------------------------------------------------------
 # step program bound to a sector block
 # ---------------------------------------------------------------------------------------------
+_SIGN_TABLES: dict = {}
+_PASS_TABLES: dict = {}
+
+
 class ParamRecipe:
     """The parameter row of a bound program as functions of the raw angles of the step:
 
@@ -416,35 +419,43 @@ class ParamRecipe:
                      = prod_j (cos^2 - sin^2)(raw_j)       PRODCOS (dephasing factors)
                      = 0                                   ZERO (padding that keeps slots 16-byte aligned)
 
-    Evaluated on the host (``evaluate``, NumPy) or on the device (``qsx_bind_params``) from the matrix of raw angles
-    [B, R]; both follow the same order of operations, column by column."""
+    Columns come in blocks: ``pairs`` adds n entries of (cos, second) column pairs that share a phase -- the (cos, -sin)
+    phase tables of the merged Z rotations, the (cos, sin) of a rotation, the (cos, sin^2) of a damping.  Evaluated on
+    the host (``evaluate``, NumPy) or on the device (``qsx_bind_params``) from the raw angles [B, R]; both follow the
+    same order of operations."""
     ZERO, COS, SIN, NSIN, SIN2, PRODCOS = 0, 1, 2, 3, 4, 5
 
     def __init__(self, n_sets: int):
         self.n_sets = n_sets
         self.raws, self._raw_id, self._angles = [], {}, None
-        self.kind, self.terms = [], []              # per column: kind, [(raw index, coefficient), ...]
+        self.blocks = []                 # dict(slot, second, idx [n, depth], coef [n, depth], share) | dict(slot, products)
+        self.width = 0
+        self._shared = {}
 
     def raw(self, values: np.ndarray) -> int:
         key = id(values)
         if key not in self._raw_id:
             self._raw_id[key] = len(self.raws)
-            self._angles = None
             self.raws.append(np.ascontiguousarray(values, dtype=np.float64).reshape(self.n_sets))
+            self._angles = None
         return self._raw_id[key]
 
-    def column(self, kind: int, terms=()) -> int:
-        self.kind.append(kind)
-        self.terms.append(list(terms))
-        return len(self.kind) - 1
+    def pairs(self, second: int, idx, coef, share=None) -> int:
+        """n entries -> 2n columns (COS, ``second``) of phase_e = sum_t coef[e, t] * raw[idx[e, t]]; returns the slot.
+        Blocks with the same ``share`` key have identical content and are evaluated once."""
+        idx = np.asarray(idx, dtype=np.int32).reshape(len(coef), -1)
+        coef = np.asarray(coef, dtype=np.float64).reshape(idx.shape)
+        slot = self.width
+        self.blocks.append(dict(slot=slot, second=second, idx=idx, coef=coef, share=share))
+        self.width += 2 * idx.shape[0]
+        return slot
 
-    def align(self):
-        if len(self.kind) % 2:
-            self.column(self.ZERO)
-
-    @property
-    def width(self) -> int:
-        return len(self.kind)
+    def products(self, term_lists) -> int:
+        """One PRODCOS column per entry of ``term_lists`` (raw indices), padded to an even width."""
+        slot = self.width
+        self.blocks.append(dict(slot=slot, products=[list(t) for t in term_lists]))
+        self.width += len(term_lists) + len(term_lists) % 2
+        return slot
 
     def angles(self) -> np.ndarray:
         """[B, R] raw angles (R >= 1)."""
@@ -454,66 +465,91 @@ class ParamRecipe:
 
     def tables(self):
         """(kind [S] int32, ptr [S+1] int32, idx [nnz] int32, coef [nnz] float64) for the device evaluation."""
+        kinds, counts, idxs, coefs = [], [], [], []
+        for blk in self.blocks:
+            if 'products' in blk:
+                n = len(blk['products'])
+                kinds.append(np.array([self.PRODCOS] * n + [self.ZERO] * (n % 2), dtype=np.int32))
+                counts.append(np.array([len(t) for t in blk['products']] + [0] * (n % 2), dtype=np.int32))
+                idxs.append(np.array([j for t in blk['products'] for j in t], dtype=np.int32))
+                coefs.append(np.full(idxs[-1].size, 2.0))
+            else:
+                n, depth = blk['idx'].shape
+                kinds.append(np.tile(np.array([self.COS, blk['second']], dtype=np.int32), n))
+                counts.append(np.full(2 * n, depth, dtype=np.int32))
+                idxs.append(np.repeat(blk['idx'], 2, axis=0).reshape(-1))
+                coefs.append(np.repeat(blk['coef'], 2, axis=0).reshape(-1))
         ptr = np.zeros(self.width + 1, dtype=np.int32)
-        ptr[1:] = np.cumsum([len(t) for t in self.terms])
-        idx = np.array([j for t in self.terms for j, _ in t], dtype=np.int32)
-        coef = np.array([c for t in self.terms for _, c in t], dtype=np.float64)
-        return np.array(self.kind, dtype=np.int32), ptr, idx, coef
+        if kinds:
+            ptr[1:] = np.cumsum(np.concatenate(counts))
+            return (np.concatenate(kinds), ptr, np.concatenate(idxs).astype(np.int32), np.concatenate(coefs))
+        return np.zeros(0, np.int32), ptr, np.zeros(0, np.int32), np.zeros(0)
+
+    def _block_phase(self, blk) -> np.ndarray:
+        """[n, B] phases of a pair block, accumulated term by term (identical term lists give identical bits)."""
+        idx, coef = blk['idx'], blk['coef']
+        raws = self.angles().T if self.n_sets == 1 else None
+        phase = np.zeros((idx.shape[0], self.n_sets))
+        for t in range(idx.shape[1]):
+            if raws is not None:
+                phase += raws[idx[:, t]] * coef[:, t, None]
+            else:
+                same = idx[0, t]
+                if np.all(idx[:, t] == same):                    # one raw angle for the whole block (phase tables)
+                    phase += self.raws[same][None, :] * coef[:, t, None]
+                else:
+                    phase += np.stack([self.raws[j] for j in idx[:, t]]) * coef[:, t, None]
+        return phase
 
     def phases(self, columns) -> np.ndarray:
         """[len(columns), B] phases of linear columns (no trigonometry)."""
         out = np.zeros((len(columns), self.n_sets))
         for r, c in enumerate(columns):
-            for j, coef in self.terms[c]:
-                out[r] += self.raws[j] * coef
+            for blk in self.blocks:
+                n_cols = self.blocks_width(blk)
+                if blk['slot'] <= c < blk['slot'] + n_cols and 'products' not in blk:
+                    e = (c - blk['slot']) // 2
+                    for t in range(blk['idx'].shape[1]):
+                        out[r] += self.raws[blk['idx'][e, t]] * blk['coef'][e, t]
         return out
 
-    def evaluate(self, columns=None) -> np.ndarray:
-        """[B, S] on the host (or only ``columns``).  Works column-major ([S, B] rows are contiguous)."""
-        raws = self.raws
-        cols = list(range(self.width) if columns is None else columns)
-        kinds = np.array([self.kind[c] for c in cols], dtype=np.int64)
-        terms = [self.terms[c] for c in cols]
-        out = np.zeros((len(cols), self.n_sets))
-        linear = [k for k in range(len(cols)) if self.COS <= kinds[k] <= self.SIN2]
-        if linear:
-            # columns with the same term list share one phase (cos and -sin of a table entry, ket and bra tables of a
-            # diagonal block): evaluate every distinct phase, its cosine and its sine once
-            unique, phase_of = {}, []
-            for k in linear:
-                phase_of.append(unique.setdefault(tuple(terms[k]), len(unique)))
-            lists = list(unique)
-            phase = np.zeros((len(lists), self.n_sets))
-            for t in range(max(len(tl) for tl in lists)):        # term by term: identical term lists give identical bits
-                rows = [u for u, tl in enumerate(lists) if len(tl) > t]
-                src = np.stack([raws[lists[u][t][0]] for u in rows])
-                src *= np.array([lists[u][t][1] for u in rows])[:, None]
-                if len(rows) == len(lists):
-                    phase += src
-                else:
-                    phase[rows] += src
-            phase_of = np.array(phase_of)
-            lin_kinds = kinds[linear]
-            need_cos = np.unique(phase_of[lin_kinds == self.COS])
-            need_sin = np.unique(phase_of[lin_kinds != self.COS])
-            cosines = dict(zip(need_cos.tolist(), np.cos(phase[need_cos]))) if need_cos.size else {}
-            sines = dict(zip(need_sin.tolist(), np.sin(phase[need_sin]))) if need_sin.size else {}
-            for k, u, kind in zip(linear, phase_of.tolist(), lin_kinds.tolist()):
-                if kind == self.COS:
-                    out[k] = cosines[u]
-                elif kind == self.SIN:
-                    out[k] = sines[u]
-                elif kind == self.NSIN:
-                    np.negative(sines[u], out=out[k])
-                else:
-                    np.multiply(sines[u], sines[u], out=out[k])
-        for k in np.nonzero(kinds == self.PRODCOS)[0]:
-            value = np.ones(self.n_sets)
-            for j, _ in terms[k]:
-                c, s_ = np.cos(raws[j]), np.sin(raws[j])
-                value = value * (c * c - s_ * s_)
-            out[k] = value
-        return np.ascontiguousarray(out.T)
+    @staticmethod
+    def blocks_width(blk) -> int:
+        if 'products' in blk:
+            return len(blk['products']) + len(blk['products']) % 2
+        return 2 * blk['idx'].shape[0]
+
+    def evaluate(self) -> np.ndarray:
+        """[B, S] on the host."""
+        out = np.zeros((self.n_sets, max(self.width, 0)))
+        done = {}
+        for blk in self.blocks:
+            slot = blk['slot']
+            if 'products' in blk:
+                for k, term in enumerate(blk['products']):
+                    value = np.ones(self.n_sets)
+                    for j in term:
+                        c, s_ = np.cos(self.raws[j]), np.sin(self.raws[j])
+                        value = value * (c * c - s_ * s_)
+                    out[:, slot + k] = value
+                continue
+            n = blk['idx'].shape[0]
+            key = blk['share']
+            if key is not None and key in done:
+                out[:, slot:slot + 2 * n] = out[:, done[key]:done[key] + 2 * n]
+                continue
+            phase = self._block_phase(blk)
+            pair = out[:, slot:slot + 2 * n].reshape(self.n_sets, n, 2)
+            pair[:, :, 0] = np.cos(phase).T
+            sines = np.sin(phase).T
+            if blk['second'] == self.NSIN:
+                np.negative(sines, out=sines)
+            elif blk['second'] == self.SIN2:
+                sines = sines ** 2
+            pair[:, :, 1] = sines
+            if key is not None:
+                done[key] = slot
+        return out
 
 
 class BoundProgram:
@@ -551,11 +587,8 @@ class BoundProgram:
         return self.recipe.phases(list(slots))
 
     def columns(self, slots) -> np.ndarray:
-        """Some parameter columns [B, len(slots)] without evaluating the whole row."""
-        slots = list(slots)
-        if self._params is not None:
-            return self._params[:, slots]
-        return self.recipe.evaluate(slots)
+        """Some parameter columns [B, len(slots)]."""
+        return self.params[:, list(slots)]
 
 
 class StepProgram:
@@ -575,9 +608,30 @@ class StepProgram:
             dt_trotter = dt / Trotter_number
         self.terms = step_terms(batch, self.layout, dt, dt_trotter, Trotter_number, Trotter_order, rates)
         self.lowered = lower(self.terms, batch.n_sites)
+        self._structure_key = None
 
     def block(self, ka: int, kb: int) -> Block:
         return Block(self.n_sites, self.n_bits, ka, kb)
+
+    def structure_key(self) -> tuple:
+        """The lowered step without its parameter values: programs with equal keys share every table that depends on
+        the structure only (pass tables, register-resident mappings)."""
+        if self._structure_key is None:
+            sig = []
+            for op in self.lowered:
+                if isinstance(op, _Diag):
+                    sig.append(('D', tuple((zs, zb) for zs, zb, _ in op.zterms), tuple(site for site, _ in op.deph)))
+                elif isinstance(op, _Hop):
+                    sig.append(('H', op.i, op.j))
+                elif isinstance(op, _Prot):
+                    sig.append(('P', op.xb, op.zb, op.site))
+                elif isinstance(op, Damp):
+                    sig.append(('A', op.bit))
+                else:
+                    sig.append((type(op).__name__, getattr(op, 'bit', None)))
+            modes = tuple((key, tuple(bits)) for key, bits in sorted(self.layout.mode.items()))
+            self._structure_key = (self.n_sites, self.n_bits, modes, self.layout.ancilla, tuple(sig))
+        return self._structure_key
 
     def bind(self, block: Block, fused: bool = True, team: int | None = None, kb: int | None = None) -> BoundProgram:
         """Angle tables, qsx_op array and (``fused``) the equivalent pass program for one (KA, KB) block."""
@@ -589,64 +643,49 @@ class StepProgram:
         R = ParamRecipe
         bits_of = np.arange(1 << nb, dtype=np.int64)
 
-        def side_table(cfgs, zterms):
+        def side_table(cfgs, zterms, key):
             """exp(-i phase) of the merged Z rotations for every (configuration, mode bits) of one side: 2*dim
             columns (cos, -sin); returns the slot."""
-            recipe.align()
-            slot = recipe.width
-            masks = np.array(cfgs, dtype=np.int64)
-            signs = []
-            for zs, zb, ang in zterms:
-                par = (_popcount_array(masks & zs)[:, None] + _popcount_array(bits_of & zb)[None, :]) & 1
-                signs.append((recipe.raw(ang), (1.0 - 2.0 * par).reshape(-1)))
-            for e in range(len(cfgs) << nb):
-                terms = [(j, sg[e]) for j, sg in signs]
-                recipe.column(R.COS, terms)
-                recipe.column(R.NSIN, terms)
-            return slot
+            sign_key = (tuple(cfgs), nb, tuple((zs, zb) for zs, zb, _ in zterms))
+            coef = _SIGN_TABLES.get(sign_key)                  # +-1 per (entry, Z term): structure only
+            if coef is None:
+                masks = np.array(cfgs, dtype=np.int64)
+                coef = np.empty((len(cfgs) << nb, len(zterms)))
+                for t, (zs, zb, _) in enumerate(zterms):
+                    par = (_popcount_array(masks & zs)[:, None] + _popcount_array(bits_of & zb)[None, :]) & 1
+                    coef[:, t] = (1.0 - 2.0 * par).reshape(-1)
+                if len(_SIGN_TABLES) > 512:
+                    _SIGN_TABLES.clear()
+                _SIGN_TABLES[sign_key] = coef
+            idx = np.tile(np.array([recipe.raw(ang) for _, _, ang in zterms], dtype=np.int32), (coef.shape[0], 1))
+            return recipe.pairs(R.NSIN, idx, coef, share=(key, tuple(cfgs)))       # ket and bra sides share when KA == KB
 
         for op in self.lowered:
             if isinstance(op, _Diag):
-                slot_a = side_table(block.cfg_a, op.zterms)
-                slot_b = side_table(block.cfg_b, op.zterms)
+                slot_a = side_table(block.cfg_a, op.zterms, id(op))
+                slot_b = side_table(block.cfg_b, op.zterms, id(op))
                 slot_t = -1
                 if op.deph:
-                    recipe.align()
-                    slot_t = recipe.width
-                    for ca in block.cfg_a:
-                        for cb in block.cfg_b:
-                            recipe.column(R.PRODCOS, [(recipe.raw(phi), 2.0) for site, phi in op.deph
-                                                      if (ca >> site) & 1 != (cb >> site) & 1])
+                    slot_t = recipe.products([[recipe.raw(phi) for site, phi in op.deph if (ca >> site) & 1 != (cb >> site) & 1]
+                                              for ca in block.cfg_a for cb in block.cfg_b])
                 op_slots.append((len(ops), dict(ga=slot_a, gb=slot_b, t=slot_t)))
                 ops.append([OP_DIAG, slot_a, slot_b, slot_t, 0, 0, 0, 0])
                 labels.append('diag')
             elif isinstance(op, _Hop):
-                recipe.align()
-                slot = recipe.width
-                j = recipe.raw(op.xx)
-                recipe.column(R.COS, [(j, 2.0)])
-                recipe.column(R.SIN, [(j, 2.0)])
+                slot = recipe.pairs(R.SIN, [[recipe.raw(op.xx)]], [[2.0]])
                 op_slots.append((len(ops), dict(cs=slot)))
                 ops.append([OP_HOP, op.i, op.j, 0, 0, 0, slot, 0])
                 labels.append('hop({},{})'.format(op.i, op.j))
             elif isinstance(op, _Prot):
                 skip0 = int(op.site >= 0 and not np.any(op.plain + op.signed != 0))   # Z_site = +1 (empty) / -1 (occupied)
-                recipe.align()
-                slot = recipe.width
                 jp, js = recipe.raw(op.plain), recipe.raw(op.signed)
-                for sign in (1.0, -1.0):
-                    recipe.column(R.COS, [(jp, 1.0), (js, sign)])
-                    recipe.column(R.SIN, [(jp, 1.0), (js, sign)])
+                slot = recipe.pairs(R.SIN, [[jp, js], [jp, js]], [[1.0, 1.0], [1.0, -1.0]])
                 ny = _popcount(op.xb & op.zb) & 3
                 op_slots.append((len(ops), dict(cs=slot, skip0=skip0)))
                 ops.append([OP_PROT, op.xb, op.zb, ny, op.site, skip0, slot, 0])
                 labels.append('prot(x={:b},z={:b},site={})'.format(op.xb, op.zb, op.site))
             elif isinstance(op, Damp):
-                recipe.align()
-                slot = recipe.width
-                j = recipe.raw(op.phi)
-                recipe.column(R.COS, [(j, 1.0)])
-                recipe.column(R.SIN2, [(j, 1.0)])
+                slot = recipe.pairs(R.SIN2, [[recipe.raw(op.phi)]], [[1.0]])
                 op_slots.append((len(ops), dict(cs=slot)))
                 ops.append([OP_AD, op.bit, 0, 0, 0, 0, slot, 0])
                 labels.append('damp({})'.format(op.bit))
@@ -654,13 +693,18 @@ class StepProgram:
                 op_slots.append((len(ops), {}))
                 ops.append([OP_RESET, op.bit, 0, 0, 0, 0, 0, 0])
                 labels.append('reset({})'.format(op.bit))
-        recipe.align()
         bound = BoundProgram(block, np.array(ops, dtype=np.int32).reshape(-1, 8), None, labels, recipe=recipe)
         if fused and self.lowered and block.size * 16 <= 220 * 1024:      # larger blocks stream through global memory
             from .passes import build_passes, default_team
             bound.team = team or default_team(block)
-            bit_site = {bit: site for (site, _), bits in self.layout.mode.items() for bit in bits}
-            bound.passes, bound.tiles, bound.hops = build_passes(self.lowered, op_slots, block, bit_site, bound.team, kb)
+            key = (self.structure_key(), block, bound.team, kb, tuple(slots.get('skip0') for _, slots in op_slots))
+            tables = _PASS_TABLES.get(key)                     # structure only: shared by programs of equal structure
+            if tables is None:
+                bit_site = {bit: site for (site, _), bits in self.layout.mode.items() for bit in bits}
+                if len(_PASS_TABLES) > 256:
+                    _PASS_TABLES.clear()
+                tables = _PASS_TABLES[key] = build_passes(self.lowered, op_slots, block, bit_site, bound.team, kb)
+            bound.passes, bound.tiles, bound.hops = tables
         return bound
 
 

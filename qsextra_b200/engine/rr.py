@@ -376,27 +376,11 @@ def _skeleton(program: StepProgram, bound: BoundProgram, reg_bits: int | None):
 _SKELETONS: dict = {}
 
 
-def _structure_key(program: StepProgram):
-    sig = []
-    for op in program.lowered:
-        if isinstance(op, _Diag):
-            sig.append(('D', tuple((zs, zb) for zs, zb, _ in op.zterms), tuple(site for site, _ in op.deph)))
-        elif isinstance(op, _Hop):
-            sig.append(('H', op.i, op.j))
-        elif isinstance(op, _Prot):
-            sig.append(('P', op.xb, op.zb, op.site))
-        elif isinstance(op, Damp):
-            sig.append(('A', op.bit))
-        else:
-            sig.append((type(op).__name__, getattr(op, 'bit', None)))
-    return tuple(sig)
-
-
 def build(program: StepProgram, bound: BoundProgram, reg_bits: int | None = None) -> RRProgram | None:
     block = bound.block
     if not eligible(program, block):
         return None
-    key = (_structure_key(program), block, reg_bits)
+    key = (program.structure_key(), block, reg_bits)
     sk = _SKELETONS.get(key)
     if sk is None:
         if len(_SKELETONS) > 256:
