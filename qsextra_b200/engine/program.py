@@ -16,6 +16,7 @@ All parameters carry a leading batch axis so one compile serves many parameter s
 """
 from __future__ import annotations
 
+import functools
 import itertools
 from dataclasses import dataclass, field
 
@@ -128,6 +129,7 @@ def _projector_terms(u: int, v: int, nq: int):
     return out
 
 
+@functools.lru_cache(maxsize=None)
 def mode_operator_terms(d_k: int):
     """Ordered {(xmask, zmask): coeff} of a, a^dagger, a + a^dagger and a^dagger a; level l sits on the basis
     state whose bits are Gray(l) = l ^ (l >> 1)."""
@@ -211,6 +213,14 @@ def _simplify(terms):
     return [(k, sums[k]) for k in order if not np.isclose(sums[k], 0, atol=1e-8, rtol=1e-5)]
 
 
+@functools.lru_cache(maxsize=None)
+def _coupling_terms(d_k: int):
+    """Simplified Pauli sum of (a + a^dagger) (1 - Z_site)/2 for a d_k-level pseudomode: [((x, z, zs), coeff)]."""
+    _, _, a_plus_adag, _ = mode_operator_terms(d_k)
+    both = [((x, z, zs), c * cz) for (x, z), c in a_plus_adag.items() for zs, cz in ((0, 0.5), (1, -0.5))]
+    return tuple(_simplify(both))
+
+
 def _place(mask: int, positions: list[int]) -> int:
     out = 0
     for j, pos in enumerate(positions):
@@ -250,8 +260,7 @@ def step_terms(batch: SystemBatch, layout: BitLayout, dt: float, dt_trotter: flo
                 terms = [((x, z), omega * np.real(c)) for (x, z), c in num.items()]
                 mode_rot = product_formula(terms, dt_trotter, order)
             if np.any(g != 0):
-                both = [((x, z, zs), c * cz) for (x, z), c in a_plus_adag.items() for zs, cz in ((0, 0.5), (1, -0.5))]
-                terms = [(key, g * np.real(c)) for key, c in _simplify(both)]
+                terms = [(key, g * np.real(c)) for key, c in _coupling_terms(d_k)]
                 int_rot = product_formula(terms, dt_trotter, order)
             for i in range(n):
                 pos = layout.mode[(i, k)]

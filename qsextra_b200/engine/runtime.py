@@ -74,10 +74,13 @@ class Engine:
             from . import rr as rr_mod
             rrp = rr_mod.build(program, bound, reg_bits=reg_bits)
             if rrp is not None:
-                rr_entries = dict(rr=rrp, rr_params=rrp.device_params(self),
-                                  logical=self.to_device(rrp.logical_index, torch.int32))
+                shared = rrp._shared if rrp._shared is not None else {}
+                lkey = ('dev_logical', self.device.index)
+                if lkey not in shared:
+                    shared[lkey] = self.to_device(rrp.logical_index, torch.int32)
+                rr_entries = dict(rr=rrp, rr_params=rrp.device_params(self), logical=shared[lkey])
         dev = dict(block=self.device_block(bound.block),
-                   ops=self.to_device(bound.ops, torch.int32),
+                   ops=None if rr_entries else self.to_device(bound.ops, torch.int32),
                    params=None if rr_entries else self.to_device(bound.params, torch.float64),
                    bound=bound, n_ops=int(bound.ops.shape[0]), stride=int(bound.stride),
                    n_sets=int(bound.n_sets), n_passes=0, team=0)
@@ -224,6 +227,7 @@ class Engine:
             out_snap = torch.empty((n_inst, n_emit, E), dtype=torch.complex128, device=self.device)
         if prog['params'] is None:                    # the register-resident path was planned but cannot serve this call
             prog['params'] = self.to_device(prog['bound'].params, torch.float64)
+            prog['ops'] = self.to_device(prog['bound'].ops, torch.int32)
         args = cabi.QsxEvolveArgs()
         args.block = blk.c
         args.n_ops, args.ops = prog['n_ops'], prog['ops'].data_ptr()

@@ -341,7 +341,7 @@ def qevolve_batch(systems, time, Trotter_number: int = 1, Trotter_order: int = 1
         if not batch.chromophore:
             rates = rates.reshape(B)
     dt, dt_trotter, Trotter_number, counts = resolve_time_grid(time, dt, Trotter_number)
-    steps = np.unique(counts).tolist()
+    steps = counts.tolist() if np.all(np.diff(counts) > 0) else np.unique(counts).tolist()
 
     rank, size = qdist.world() if shard else (0, 1)
     lo, hi = qdist.shard_bounds(B, rank, size)

@@ -34,10 +34,17 @@ def once():
     mark('api returned')
     pinned.copy_(res, non_blocking=True); mark('copy queued')
     torch.cuda.synchronize(); mark('synced')
-for _ in range(4): once()
-t0 = marks[0][1]
-for label, t in marks:
-    print('%8.3f ms  %s' % ((t - t0) * 1e3, label))
+for _ in range(5): once()
+import collections
+acc = collections.OrderedDict()
+N = 40
+for _ in range(N):
+    once()
+    t0 = marks[0][1]
+    for label, t in marks:
+        acc[label] = acc.get(label, 0.0) + (t - t0)
+for label, t in acc.items():
+    print('%8.3f ms  %s   (mean of %d calls)' % (t / N * 1e3, label, N))
 # device-side: kernel alone and copy alone
 res = qevolve_batch(batch, tg, dt=DT, coll_rates=params['rates'], device_output=True, shard=False)
 torch.cuda.synchronize()
