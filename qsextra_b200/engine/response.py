@@ -126,4 +126,6 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
                 table = table.index_select(axis, torch.as_tensor(inv, device=eng.device))
         return table.reshape(shape).contiguous()
     table = out.cpu().numpy().reshape([len(u) for u in uniq])
+    if all(len(inv) == len(u) and np.array_equal(inv, np.arange(len(inv))) for inv, u in zip(inverse, uniq)):
+        return table                                    # delays were ascending and distinct: nothing to reorder
     return table[np.ix_(*inverse)].reshape(shape)

@@ -33,13 +33,14 @@ _RESERVED = ('system', 'time', 'shots', 'initialize_circuit', 'verbose')
 
 def delay_step_counts(delay_time, dt, Trotter_number):
     """Integer step count of every delay (each delay goes through qevolve's own dt logic, qspectroscopy.py:133-139)."""
-    counts, grid = [], None
-    for delays in delay_time:
-        row = []
-        for t in delays:
-            grid = resolve_time_grid(t, dt, Trotter_number)
-            row.append(int(grid[3][0]))
-        counts.append(row)
+    counts = []
+    grid = resolve_time_grid(0.0, dt, Trotter_number)
+    for delays in delay_time:                           # dt is given, so every delay resolves against the same grid
+        if len(delays) == 0:
+            counts.append([])
+            continue
+        grid = resolve_time_grid(np.asarray(delays, dtype=float), dt, Trotter_number)
+        counts.append([int(c) for c in grid[3]])
     return counts, grid
 
 
