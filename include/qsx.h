@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define QSX_ABI_VERSION 11
+#define QSX_ABI_VERSION 13
 
 enum {
     QSX_OK = 0,
@@ -62,8 +62,16 @@ typedef struct qsx_op {
     int32_t type;
     int32_t i0, i1, i2, i3, i4;
     int32_t p;          /* slot (in doubles) into the parameter-set table */
-    int32_t reserved;
+    int32_t flags;      /* QSX_OPF_* */
 } qsx_op;
+
+/* The operation is replaced by its transpose with respect to the pairing <W, sigma> = sum_ab W[a][b] sigma[a][b]:
+ * a step program run backwards with transposed operations propagates a read-out W instead of the state
+ * (<W, Phi^n sigma> = <(Phi^T)^n W, sigma>; used for the last delay of a response function, where one propagation of
+ * the emission read-out replaces one propagation per (t1, t2) chain).  DIAG and HOP are their own transposes; PROT
+ * changes the sign of its angle when nY is odd; AD becomes W'[11] = cos^2 W[11] + sin^2 W[00], W'[00] = W[00],
+ * W'[01], W'[10] scaled by cos (RESET: cos = 0, sin^2 = 1). */
+#define QSX_OPF_TRANSPOSE 1
 
 /* Fused passes.  A pass program is an equivalent regrouping of the step's operations into sweeps over sigma in
  * which every thread keeps a small tile in registers and applies several operations to it ("passes"):
@@ -283,6 +291,13 @@ typedef struct {
 } qsx_rr_tables_args;
 
 int32_t qsx_rr_tables(const qsx_rr_tables_args* args, void* stream);
+
+/* Signal of the last delay from the propagated read-outs (engine/response.py, Heisenberg picture):
+ *   out[i][k] = sum_e sigma[i][e] * readout[k][e]      (no conjugation)
+ * sigma [n_inst][E], readout [n_emit][E], out [n_inst][n_emit], all complex128 DEVICE arrays.  It stands for the
+ * accumulation `signal[*time_indices] += ...` over the estimator values at qspectroscopy.py:180-183. */
+int32_t qsx_readout_gemm(int32_t n_inst, int32_t n_emit, int32_t n_elem, const double* sigma, const double* readout,
+                         double* out, void* stream);
 
 /* Lindblad limit of the collision model -- replaces the QuTiP solver calls of the comparison path
  * (qsextra/qcomo/evolution/clevolve.py:27-46 and :88-107: sesolve / mesolve(H, state, time, c_ops, e_ops)).

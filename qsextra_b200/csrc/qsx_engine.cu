@@ -159,7 +159,8 @@ __device__ void sweep_prot(double2* s, const EvolveParams& k, const qsx_op& op, 
     const int pivot = xm & -xm;
     const int nb = k.a.block.n_bits, DB = k.DB;
     const int upow = (op.i2 + 3) & 3;                 // -i * i^nY = i^(nY+3)
-    const double c0 = P[op.p], s0 = P[op.p + 1], c1 = P[op.p + 2], s1 = P[op.p + 3];
+    const double flip = ((op.flags & QSX_OPF_TRANSPOSE) && (op.i2 & 1)) ? -1.0 : 1.0;   // P^T = (-1)^nY P
+    const double c0 = P[op.p], s0 = flip * P[op.p + 1], c1 = P[op.p + 2], s1 = flip * P[op.p + 3];
     // ket side: new_a = c sig_a + (-i s) P[a,a2] sig_a2,  P[a,a2] = i^nY (-1)^{|a2 & z|}
     for (int e = t.tid; e < k.E && (sides & 1); e += t.n) {
         int a = e / DB, b = e - a * DB;
@@ -206,10 +207,14 @@ __device__ void sweep_ad_or_reset(double2* s, const EvolveParams& k, const qsx_o
         if ((a & m) || (b & m)) continue;
         int e01 = e + m, e10 = e + m * DB, e11 = e10 + m;
         double2 v00 = s[e], v01 = s[e01], v10 = s[e10], v11 = s[e11];
-        s[e] = make_double2(fma(s2, v11.x, v00.x), fma(s2, v11.y, v00.y));
+        if (op.flags & QSX_OPF_TRANSPOSE) {
+            s[e11] = make_double2(fma(s2, v00.x, cc * v11.x), fma(s2, v00.y, cc * v11.y));
+        } else {
+            s[e] = make_double2(fma(s2, v11.x, v00.x), fma(s2, v11.y, v00.y));
+            s[e11] = make_double2(cc * v11.x, cc * v11.y);
+        }
         s[e01] = make_double2(c * v01.x, c * v01.y);
         s[e10] = make_double2(c * v10.x, c * v10.y);
-        s[e11] = make_double2(cc * v11.x, cc * v11.y);
     }
     t.sync();
 }
@@ -826,6 +831,60 @@ int32_t evolve_plan(const qsx_evolve_args* a, Plan* pl) {
 }  // namespace
 
 
+// out[m][n] = sum_k A[m][k] * B[n][k] (complex128, both operands contiguous in k): the signal of the last delay from
+// the chains' blocks A = sigma and the propagated read-outs B.  FP64 CUDA-core GEMM: CTA tile 32 x 64, k-step 16,
+// 128 threads with a 4 x 4 register tile each (rows ty + 8 i, columns tx + 16 j, so shared-memory reads of a quarter
+// warp are consecutive); 16 complex multiply-adds (64 DFMA) per 8 shared-memory loads.
+constexpr int RG_TM = 32, RG_TN = 64, RG_TK = 16;
+
+static __global__ void __launch_bounds__(128) readout_gemm_kernel(int M, int N, int K, const double2* __restrict__ A,
+                                                                  const double2* __restrict__ B, double2* __restrict__ C) {
+    __shared__ double2 As[RG_TK][RG_TM + 1];
+    __shared__ double2 Bs[RG_TK][RG_TN + 1];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * RG_TM, n0 = blockIdx.x * RG_TN;
+    double2 acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = make_double2(0.0, 0.0);
+    const double2 zero = make_double2(0.0, 0.0);
+    for (int k0 = 0; k0 < K; k0 += RG_TK) {
+        for (int q = tid; q < RG_TM * RG_TK; q += 128) {               // consecutive threads read consecutive k
+            const int r = q / RG_TK, c = q % RG_TK;
+            As[c][r] = (m0 + r < M && k0 + c < K) ? A[(size_t)(m0 + r) * K + k0 + c] : zero;
+        }
+        for (int q = tid; q < RG_TN * RG_TK; q += 128) {
+            const int r = q / RG_TK, c = q % RG_TK;
+            Bs[c][r] = (n0 + r < N && k0 + c < K) ? B[(size_t)(n0 + r) * K + k0 + c] : zero;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < RG_TK; ++kk) {
+            double2 a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty + 8 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[i][j].x = fma(a[i].x, b[j].x, fma(-a[i].y, b[j].y, acc[i][j].x));
+                    acc[i][j].y = fma(a[i].x, b[j].y, fma(a[i].y, b[j].x, acc[i][j].y));
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = m0 + ty + 8 * i, n = n0 + tx + 16 * j;
+            if (m < M && n < N) C[(size_t)m * N + n] = acc[i][j];
+        }
+}
+
 // Parameter rows from raw angles (see qsx_bind_params): one thread per (set, column).
 static __global__ void bind_params_kernel(int n_sets, int n_cols, int n_raw, const int* __restrict__ kind,
                                           const int* __restrict__ ptr, const int* __restrict__ idx,
@@ -1108,6 +1167,21 @@ int32_t qsx_evolve_rrc(const qsx_rrc_args* a, void* stream) {
     int r = rrc::launch<0>(*a, sms, smem_max, (cudaStream_t)stream);
     if (r == 1) return fail(QSX_ERR_INVALID, "no compile-time program matches this block%s");
     if (r < 0) return fail(QSX_ERR_CUDA, "CUDA error: %s", cudaGetErrorString((cudaError_t)(-r)));
+    return QSX_OK;
+}
+
+int32_t qsx_readout_gemm(int32_t n_inst, int32_t n_emit, int32_t n_elem, const double* sigma, const double* readout,
+                         double* out, void* stream) {
+    if (n_inst < 0 || n_emit < 0 || n_elem < 0) return fail(QSX_ERR_INVALID, "bad sizes%s");
+    if (n_inst == 0 || n_emit == 0) return QSX_OK;
+    if (!out || (n_elem > 0 && (!sigma || !readout))) return fail(QSX_ERR_INVALID, "null argument%s");
+    dim3 grid((n_emit + RG_TN - 1) / RG_TN, (n_inst + RG_TM - 1) / RG_TM);
+    if (grid.y > 65535u) return fail(QSX_ERR_INVALID, "more than 2097120 chains in one call%s");
+    readout_gemm_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(n_inst, n_emit, n_elem,
+                                                                 reinterpret_cast<const double2*>(sigma),
+                                                                 reinterpret_cast<const double2*>(readout),
+                                                                 reinterpret_cast<double2*>(out));
+    QSX_CUDA(cudaGetLastError());
     return QSX_OK;
 }
 

@@ -14,7 +14,7 @@ template <int PID>
 struct BigProg;
 #include "qsx_rrc_programs.inc"
 
-enum { OP_DIAG = 0, OP_HOPK = 1, OP_HOPB = 2, OP_ROTK = 3, OP_ROTB = 4, OP_AD = 5 };
+enum { OP_DIAG = 0, OP_HOPK = 1, OP_HOPB = 2, OP_ROTK = 3, OP_ROTB = 4, OP_AD = 5, OP_ADT = 6 };
 
 struct Params {
     qsx_rrc_args a;
@@ -138,24 +138,30 @@ __device__ __forceinline__ void big_op(double2 (&v)[BigProg<PID>::NA][BigProg<PI
         const int cid = remove_bit(remove_bit(tid, hi), lo);
         constexpr int grp = hi >= 5 ? hi - 5 : G::NWB;              // exchanges inside a warp use the last buffer pair
         double2* buf = xbuf + (2 * grp + which[grp]) * G::BUF;
-        if (la & lb) {
+        // forward: the (1,1) threads of the bit pair hand their tile to the (0,0) threads; transposed (OP_ADT, the
+        // read-out is propagated): the (0,0) threads hand theirs to the (1,1) threads
+        constexpr bool fwd = kind == OP_AD;
+        const bool giver = fwd ? (la & lb) : !(la | lb), taker = fwd ? !(la | lb) : (la & lb);
+        if (giver) {
 #pragma unroll
             for (int i = 0; i < NA; ++i)
 #pragma unroll
                 for (int j = 0; j < NB; ++j) buf[(i * NB + j) * (NT / 4) + cid] = v[i][j];
         }
         pair_sync<PID, hi>(tid);
-        if (!(la | lb)) {
+        const double cc = cs.x * cs.x;
+        if (taker) {
+            const double keep = fwd ? 1.0 : cc;
 #pragma unroll
             for (int i = 0; i < NA; ++i)
 #pragma unroll
                 for (int j = 0; j < NB; ++j) {
                     const double2 p = buf[(i * NB + j) * (NT / 4) + cid];
-                    v[i][j].x = fma(cs.y, p.x, v[i][j].x);
-                    v[i][j].y = fma(cs.y, p.y, v[i][j].y);
+                    v[i][j].x = fma(cs.y, p.x, keep * v[i][j].x);
+                    v[i][j].y = fma(cs.y, p.y, keep * v[i][j].y);
                 }
-        } else {
-            const double f = (la & lb) ? cs.x * cs.x : cs.x;
+        } else if (!giver || fwd) {
+            const double f = giver ? cc : cs.x;
 #pragma unroll
             for (int i = 0; i < NA; ++i)
 #pragma unroll

@@ -25,6 +25,7 @@ import numpy as np
 from .sectors import Block
 
 OP_DIAG, OP_HOP, OP_PROT, OP_AD, OP_RESET = 0, 1, 2, 3, 4
+OPF_TRANSPOSE = 1                          # qsx_op.flags: the operation is replaced by its transpose (include/qsx.h)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -576,6 +577,7 @@ class BoundProgram:
         self.hops = hops
         self.team = team                 # threads per instance the pass tables were built for (0: library default)
         self.recipe = recipe
+        self.is_transposed = False
 
     @property
     def params(self) -> np.ndarray:
@@ -590,6 +592,17 @@ class BoundProgram:
     @property
     def stride(self) -> int:
         return self._params.shape[1] if self._params is not None else max(self.recipe.width, 2)
+
+    def transposed(self) -> "BoundProgram":
+        """The step that propagates a read-out W instead of the state: <W, Phi sigma> = <Phi^T W, sigma>.  Operations
+        in reverse order, each flagged as its transpose (include/qsx.h QSX_OPF_TRANSPOSE); same parameter rows.  The
+        pass tables regroup the forward order, so the transposed program runs as a plain operation list."""
+        ops = self.ops[::-1].copy()
+        ops[:, 7] |= OPF_TRANSPOSE
+        out = BoundProgram(self.block, np.ascontiguousarray(ops), self._params, self.labels[::-1], recipe=self.recipe)
+        out.is_transposed = True
+        out._forward = self
+        return out
 
     def phases(self, slots) -> np.ndarray:
         """[len(slots), B] rotation angles behind the cos/sin columns ``slots`` (from the recipe, no trigonometry)."""

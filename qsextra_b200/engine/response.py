@@ -17,6 +17,8 @@ the signal.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -107,6 +109,17 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
         if level < len(plan) - 2:
             _, snap = propagate(dev, sigma, n_local, emit, snapshots=True)
             sigma = snap.reshape(n_local * len(emit), block.size)
+        elif (not continuous and 'rr' not in dev and n_local >= int(os.environ.get('QSX_HEISENBERG_MIN', '8'))
+              and not os.environ.get('QSX_DISABLE_HEISENBERG')):
+            # Last delay in the Heisenberg picture: <W, Phi^n sigma> = <(Phi^T)^n W, sigma>.  ONE propagation of the
+            # emission read-out W with the transposed step replaces one propagation per chain; the signal is then the
+            # product [chains x E] . [E x emissions] (qsx_readout_gemm).
+            ptr, idx, w = block.emission_observable(np.asarray(mu, dtype=float))
+            readout = np.zeros(block.size, dtype=complex)
+            np.add.at(readout, np.asarray(idx[ptr[0]:ptr[1]]), np.asarray(w[ptr[0]:ptr[1]]))
+            back = eng.upload_program(program.bind(block, fused=False).transposed(), program)
+            _, snap = eng.evolve(back, eng.to_device(readout.reshape(1, -1)), 1, int(emit.max()), emit, snapshots=True)
+            out = eng.readout_gemm(sigma.reshape(n_local, block.size).contiguous(), snap[0].contiguous())
         else:
             obs = eng.upload_observables(*block.emission_observable(np.asarray(mu, dtype=float)), kind='emission', mu=mu)
             out, _ = propagate(dev, sigma, n_local, emit, obs=obs)

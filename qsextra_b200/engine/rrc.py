@@ -16,7 +16,7 @@ import numpy as np
 from .program import BoundProgram, Damp, StepProgram, _Diag, _Hop, _Prot
 from .sectors import Block, sector_rank
 
-OP_DIAG, OP_HOPK, OP_HOPB, OP_ROTK, OP_ROTB, OP_AD = 0, 1, 2, 3, 4, 5      # ROT*: tangent form; HOP*: (cos, sin)
+OP_DIAG, OP_HOPK, OP_HOPB, OP_ROTK, OP_ROTB, OP_AD, OP_ADT = 0, 1, 2, 3, 4, 5, 6   # ROT*: tangent form; HOP*: (cos, sin)
 
 
 @dataclass
@@ -48,6 +48,12 @@ class RRCProgram:
 
 
 def build(program: StepProgram, bound: BoundProgram) -> RRCProgram | None:
+    """``bound`` may be the transposed program (``BoundProgram.transposed()``): the operation list is then reversed and
+    the dampings become OP_ADT; hops, tangent-form rotations and the diagonal table are their own transposes, and the
+    folded cosines are one scalar per sector, so their position in the step does not matter."""
+    transposed = bool(getattr(bound, 'is_transposed', False))
+    if transposed:
+        bound = bound._forward
     block = bound.block
     nb, n_sites = block.n_bits, block.n_sites
     if nb < 3 or nb > 4 or nb != n_sites or block.n_a * block.n_b > 32:
@@ -130,6 +136,8 @@ def build(program: StepProgram, bound: BoundProgram) -> RRCProgram | None:
     params[:, n_w + 2 * (1 << nb):shift] = np.ascontiguousarray(gm_b).view(np.float64)
     for op in ops:
         op[4] += shift if op[0] != OP_DIAG else 0
+    if transposed:
+        ops = [[OP_ADT if op[0] == OP_AD else op[0]] + op[1:] for op in reversed(ops)]
     emission = []
     if abs(block.ka - block.kb) == 1:
         for j, mask_b in enumerate(block.cfg_b):

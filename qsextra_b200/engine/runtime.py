@@ -70,7 +70,8 @@ class Engine:
         """-> dict of device tensors for a bound program (ops + parameter sets).  With ``program`` (the StepProgram
         it was bound from) small power-of-two blocks are additionally mapped onto the register-resident kernel."""
         rr_entries = {}
-        if program is not None and use_rr and not os.environ.get('QSX_DISABLE_RR'):
+        transposed = bool(getattr(bound, 'is_transposed', False))      # only the CTA-wide kernel and the op list run it
+        if program is not None and use_rr and not transposed and not os.environ.get('QSX_DISABLE_RR'):
             from . import rr as rr_mod
             rrp = rr_mod.build(program, bound, reg_bits=reg_bits)
             if rrp is not None:
@@ -402,6 +403,22 @@ class Engine:
             cabi.check(self.lib.qsx_spectrum_shift(C.c_void_p(data.data_ptr()), C.c_void_p(out.data_ptr()), m1, m3,
                                                    s1 % max(m1, 1), s3 % max(m3, 1), float(scale), C.c_void_p(stream)))
         if out.numel():
+            self.launches += 1
+        return out
+
+    def readout_gemm(self, sigma: torch.Tensor, readouts: torch.Tensor) -> torch.Tensor:
+        """out[i, k] = sum_e sigma[i, e] readouts[k, e] (complex128, no conjugation; ``qsx_readout_gemm``)."""
+        assert sigma.dtype == readouts.dtype == torch.complex128 and sigma.is_contiguous() and readouts.is_contiguous()
+        n_inst, E = sigma.shape
+        n_emit = readouts.shape[0]
+        assert readouts.shape[1] == E
+        out = torch.empty((n_inst, n_emit), dtype=torch.complex128, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            cabi.check(self.lib.qsx_readout_gemm(n_inst, n_emit, E, C.c_void_p(sigma.data_ptr()),
+                                                 C.c_void_p(readouts.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                 C.c_void_p(stream)))
+        if n_inst > 0 and n_emit > 0:
             self.launches += 1
         return out
 

@@ -29,7 +29,8 @@ def apply_step(sigma, bound, set_index=0):
     bits = (1 << nb) - 1
     sigma = sigma.copy()
     for op in bound.ops:
-        typ, i0, i1, i2, i3, i4, p, _ = (int(v) for v in op)
+        typ, i0, i1, i2, i3, i4, p, flags = (int(v) for v in op)
+        transposed = bool(flags & 1)                 # QSX_OPF_TRANSPOSE
         if typ == OP_DIAG:
             ga = P[i0:i0 + 2 * DA].reshape(DA, 2) @ [1, 1j]
             gb = P[i1:i1 + 2 * DB].reshape(DB, 2) @ [1, 1j]
@@ -57,6 +58,8 @@ def apply_step(sigma, bound, set_index=0):
                 occ = ((cfg >> site) & 1) if site >= 0 else np.zeros_like(cfg)
                 c = np.where(occ == 1, P[p + 2], P[p])
                 s = np.where(occ == 1, P[p + 3], P[p + 1])
+                if transposed and ny & 1:             # P^T = (-1)^nY P
+                    s = -s
                 if skip0:
                     c, s = np.where(occ == 1, c, 1.0), np.where(occ == 1, s, 0.0)
                 sign = 1 - 2 * (_popc((idx ^ xm) & zm) & 1)       # (-1)^{|a2 & z|}, a2 = a ^ x
@@ -70,10 +73,14 @@ def apply_step(sigma, bound, set_index=0):
             c, s2 = (0.0, 1.0) if typ == OP_RESET else (P[p], P[p + 1])
             a0, b0 = ia[(ia & m) == 0], ib[(ib & m) == 0]
             new = np.zeros_like(sigma)
-            new[np.ix_(a0, b0)] = sigma[np.ix_(a0, b0)] + s2 * sigma[np.ix_(a0 | m, b0 | m)]
+            if transposed:
+                new[np.ix_(a0, b0)] = sigma[np.ix_(a0, b0)]
+                new[np.ix_(a0 | m, b0 | m)] = c * c * sigma[np.ix_(a0 | m, b0 | m)] + s2 * sigma[np.ix_(a0, b0)]
+            else:
+                new[np.ix_(a0, b0)] = sigma[np.ix_(a0, b0)] + s2 * sigma[np.ix_(a0 | m, b0 | m)]
+                new[np.ix_(a0 | m, b0 | m)] = c * c * sigma[np.ix_(a0 | m, b0 | m)]
             new[np.ix_(a0, b0 | m)] = c * sigma[np.ix_(a0, b0 | m)]
             new[np.ix_(a0 | m, b0)] = c * sigma[np.ix_(a0 | m, b0)]
-            new[np.ix_(a0 | m, b0 | m)] = c * c * sigma[np.ix_(a0 | m, b0 | m)]
             sigma = new
         else:
             raise ValueError(typ)
@@ -290,6 +297,11 @@ def apply_rrc_program(sigma, prog, set_index=0):
             ha, hb = ((m >> a) & 1)[:, None], ((m >> a) & 1)[None, :]
             partner = v[:, :, m ^ (1 << a), :][:, :, :, m ^ (1 << a)]
             v = np.where((ha == 0) & (hb == 0), v + s2 * partner, np.where(ha != hb, c * v, c * c * v))
+        elif kind == K.OP_ADT:                       # transposed damping: the (0,0) elements feed the (1,1) elements
+            s2 = t
+            ha, hb = ((m >> a) & 1)[:, None], ((m >> a) & 1)[None, :]
+            partner = v[:, :, m ^ (1 << a), :][:, :, :, m ^ (1 << a)]
+            v = np.where((ha == 1) & (hb == 1), c * c * v + s2 * partner, np.where(ha != hb, c * v, v))
     return v.transpose(0, 2, 1, 3).reshape(sigma.shape)
 
 

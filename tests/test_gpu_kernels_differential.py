@@ -128,3 +128,39 @@ def test_parameter_rows_evaluated_on_the_device_match_the_host(engine, name, sys
         got = engine.bind_params(bound).cpu().numpy()
         want = bound.params
         assert got.shape == want.shape and np.abs(got - want).max() < 1e-15
+
+
+@pytest.mark.parametrize('name,system,kw,blocks', CASES, ids=[c[0] for c in CASES])
+def test_transposed_programs_agree_with_emulated_operations(engine, name, system, kw, blocks):
+    """The step run backwards with transposed operations (read-out propagation, QSX_OPF_TRANSPOSE): operation list
+    and, where a compile-time program exists, the CTA-wide kernel, against the emulation."""
+    dt = 0.15
+    tn = kw.get('Trotter_number', 1)
+    prog = _program_for(system, dt, dt / tn, tn, kw.get('Trotter_order', 1), kw.get('coll_rates'))
+    rng = np.random.default_rng(zlib.crc32(name.encode()) + 1)
+    seen = set()
+    for ka, kb in blocks:
+        blk = prog.block(ka, kb)
+        w0 = rng.normal(size=(blk.dim_a, blk.dim_b)) + 1j * rng.normal(size=(blk.dim_a, blk.dim_b))
+        back = prog.bind(blk, fused=False).transposed()
+        want = [w0]
+        for _ in range(STEPS):
+            want.append(emulator.apply_step(want[-1], back))
+        want = np.array(want)
+        for label, env in (('op list', {'QSX_DISABLE_RRC': '1'}), ('best', None)):
+            got, dev = run_engine(engine, prog, back, w0, True, env)
+            assert 'rr' not in dev
+            assert np.abs(got - want).max() < 1e-12 * np.abs(want).max(), (name, (ka, kb), label)
+            seen.add('rrc' if dev.get('rrc') is not None else 'ops')
+    if name in ('trimer_modes', 'chain4_modes'):
+        assert 'rrc' in seen
+
+
+@pytest.mark.parametrize('m,n,k', [(1, 1, 1), (7, 5, 3), (33, 65, 17), (64, 128, 1024), (100, 3, 6144), (2048, 128, 96)])
+def test_readout_gemm_against_numpy(engine, m, n, k):
+    rng = np.random.default_rng(m * 7 + n * 3 + k)
+    a = rng.normal(size=(m, k)) + 1j * rng.normal(size=(m, k))
+    b = rng.normal(size=(n, k)) + 1j * rng.normal(size=(n, k))
+    got = engine.readout_gemm(torch.as_tensor(a, device='cuda'), torch.as_tensor(b, device='cuda')).cpu().numpy()
+    want = a @ b.T
+    assert got.shape == want.shape and np.abs(got - want).max() < 1e-12 * np.sqrt(k) * max(1.0, np.abs(want).max())

@@ -118,3 +118,36 @@ def test_restart_from_reference_checkpoint(engine, tmp_path, monkeypatch):
     again = qspectroscopy(s, spec, verbose=False, checkpoint=True, **kw)
     close(again, full)
     assert [d for d in os.listdir('.') if os.path.isdir(d)] == []
+
+
+@pytest.mark.parametrize('name', golden_names('qspectroscopy_'))
+def test_qspectroscopy_golden_with_the_last_delay_in_the_heisenberg_picture(engine, name, monkeypatch):
+    """Same goldens with the read-out propagated backwards for the last delay (engine/response.py), which the big
+    grids use; forced here for every grid size and with the register-resident forward path switched off."""
+    monkeypatch.setenv('QSX_HEISENBERG_MIN', '1')
+    monkeypatch.setenv('QSX_DISABLE_RR', '1')
+    meta, arrays = load_golden(name)
+    system = build_system(meta['system'])
+    spec = build_spectroscopy(meta['label'], meta['delay_time'])
+    signal = qspectroscopy(system, spec, shots=0, verbose=False, **dict(meta['kwargs']))
+    assert signal.shape == arrays['signal'].shape
+    close(signal, arrays['signal'], scale=max(1.0, np.abs(arrays['signal']).max()))
+
+
+def test_heisenberg_and_forward_agree_on_a_chain_with_pseudomodes(engine, monkeypatch):
+    from qsextra_b200 import ChromophoreSystem
+    from qsextra_b200.spectroscopy import FeynmanDiagram
+    J = np.zeros((4, 4))
+    for i in range(3):
+        J[i, i + 1] = J[i + 1, i] = -0.01 * (1 + 0.3 * i)
+    s = ChromophoreSystem(energies=[1.55, 1.50, 1.46, 1.52], couplings=J, dipole_moments=[1., 0.8, -0.6, 1.1],
+                          frequencies_pseudomode=0.02, levels_pseudomode=2, couplings_ep=0.054)
+    dt = 0.15
+    delays = [(dt * 3 * np.arange(6)).tolist(), (dt * 5 * np.arange(3)).tolist(), (dt * 3 * np.arange(7)).tolist()]
+    for label in ('esa', 'se', 'gsb'):
+        spec = FeynmanDiagram(label, delays)
+        backward = qspectroscopy(s, spec, shots=0, verbose=False, dt=dt, coll_rates=[0.2])      # 18 chains >= 8
+        monkeypatch.setenv('QSX_DISABLE_HEISENBERG', '1')
+        forward = qspectroscopy(s, spec, shots=0, verbose=False, dt=dt, coll_rates=[0.2])
+        monkeypatch.delenv('QSX_DISABLE_HEISENBERG')
+        close(backward, forward, scale=max(1.0, np.abs(forward).max()))

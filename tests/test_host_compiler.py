@@ -174,6 +174,9 @@ def test_register_resident_programs_equal_operation_list():
             assert big is not None and big.threads == 4 ** n
             sig = rng.normal(size=(blk.dim_a, blk.dim_b)) + 1j * rng.normal(size=(blk.dim_a, blk.dim_b))
             assert np.abs(emulator.apply_step(sig, bound) - emulator.apply_rrc_program(sig, big)).max() < 1e-13
+            back = RRC.build(progn, bound.transposed())        # the read-out propagated backwards
+            assert back is not None and [o[0] for o in back.ops].count(RRC.OP_ADT) == n and back.ops[-1][0] == RRC.OP_DIAG
+            assert np.abs(emulator.apply_step(sig, bound.transposed()) - emulator.apply_rrc_program(sig, back)).max() < 1e-13
 
 
 def test_generated_program_tables_are_current():
@@ -191,3 +194,32 @@ def test_generated_program_tables_are_current():
             mod.main()
         after = open(path).read()
         assert before == after, inc + ' is stale: run python tools/' + tool
+
+
+@pytest.mark.parametrize('sysdef,kw,blocks', [
+    (dict(energies=[1.5, 1.4], couplings=-0.1, dipole_moments=[1., 1.], frequencies_pseudomode=[0.2], levels_pseudomode=[2],
+          couplings_ep=[0.3]), dict(coll_rates=[0.4]), [(1, 1), (2, 1), (1, 0)]),
+    (dict(energies=[1.5, 1.4, 1.6], couplings=[[0, .1, .05], [.1, 0, .2], [.05, .2, 0]], dipole_moments=[1.] * 3),
+     dict(coll_rates=0.2, Trotter_order=2), [(1, 1), (2, 1)]),
+    (dict(energies=[1.5, 1.4], couplings=-0.1, dipole_moments=[1., 1.], frequencies_pseudomode=[0.2], levels_pseudomode=[3],
+          couplings_ep=[0.3]), dict(coll_rates=[0.4]), [(1, 1), (1, 0)]),           # Y rotations and resets
+])
+def test_transposed_program_propagates_the_read_out(sysdef, kw, blocks):
+    """<W, Phi^n sigma> = <(Phi^T)^n W, sigma> with the transposed program (reverse order, QSX_OPF_TRANSPOSE)."""
+    from qsextra_b200.qcomo.evolution.qevolve import _program_for
+    system = build_system(sysdef)
+    tn = kw.get('Trotter_number', 1)
+    prog = _program_for(system, 0.2, 0.2 / tn, tn, kw.get('Trotter_order', 1), kw.get('coll_rates'))
+    rng = np.random.default_rng(8)
+    for ka, kb in blocks:
+        blk = prog.block(ka, kb)
+        fwd = prog.bind(blk, fused=False)
+        bwd = fwd.transposed()
+        assert bwd.passes is None and np.all(bwd.ops[:, 7] == 1) and np.array_equal(bwd.ops[::-1, :7], fwd.ops[:, :7])
+        sigma = rng.normal(size=(blk.dim_a, blk.dim_b)) + 1j * rng.normal(size=(blk.dim_a, blk.dim_b))
+        w = rng.normal(size=(blk.dim_a, blk.dim_b)) + 1j * rng.normal(size=(blk.dim_a, blk.dim_b))
+        s3, w3 = sigma, w
+        for _ in range(3):
+            s3 = emulator.apply_step(s3, fwd)
+            w3 = emulator.apply_step(w3, bwd)
+        assert abs(np.sum(w * s3) - np.sum(w3 * sigma)) < 1e-12 * np.abs(w).sum()

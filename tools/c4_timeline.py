@@ -25,7 +25,7 @@ def info(name, a, k):
         return 'block %s inst %d steps %d emits %d %s' % ((prog['block'].block.ka, prog['block'].block.kb), a[3], a[4], len(a[5]),
                                                            'rrc' if prog.get('rrc') is not None else 'rr' if 'rr' in prog else 'pass')
     return ''
-for name in ('evolve', 'apply_dipole', 'upload_program', 'upload_observables'):
+for name in ('evolve', 'apply_dipole', 'upload_program', 'upload_observables', 'readout_gemm'):
     wrap(type(eng), name)
 wrap(StepProgram, 'bind')
 system, kw, delays = systems(sys.argv[1] if len(sys.argv) > 1 else 'c4')
