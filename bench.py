@@ -207,16 +207,15 @@ def spectroscopy_extras(world, rank, barrier):
         for name, (system, kw, delays) in configs.items():
             try:
                 specs = [FeynmanDiagram(lab, delays) for lab in ('gsb', 'se', 'esa')]
-                if name.startswith('C3'):
-                    for sp in specs:
-                        qspectroscopy(system, sp, verbose=False, **kw)          # warm-up
+                for sp in specs:
+                    qspectroscopy(system, sp, verbose=False, **kw)              # warm-up (module loads, caches)
                 barrier()
                 t0 = time.perf_counter()
                 sigs = [qspectroscopy(system, sp, verbose=False, **kw) for sp in specs]
                 barrier()
                 sec = time.perf_counter() - t0
                 points = 3 * int(np.prod([len(d) for d in delays]))
-                out[name] = dict(grid_points=points, seconds=sec, grid_points_per_s=points / sec,
+                out[name] = dict(grid_points=points, seconds=sec, grid_points_per_s=points / sec, warmup_runs=1,
                                  checksum=float(sum(np.abs(s_).sum() for s_ in sigs)))
                 if name.startswith('C4'):
                     # the full 2-D spectra (every t2 slice, pad_extension 3) with the signal kept on the device from

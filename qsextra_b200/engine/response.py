@@ -46,6 +46,27 @@ def interaction_plan(side_seq: str, direction_seq: str):
     return plan
 
 
+def _last_level(program, plan, uniq, rank, size):
+    """(block of the last delay or None if a sector is empty, chains this rank holds there) -- the bookkeeping of
+    ``response_function`` without any propagation."""
+    ka = kb = 0
+    n_global, local, sharded = 1, 1, False
+    block = None
+    for level, (side, kind) in enumerate(plan[:-1]):
+        delta = +1 if kind == 'X' or (kind == 'raise') == (side == 'k') else -1
+        ka, kb = (ka + delta, kb) if side == 'k' else (ka, kb + delta)
+        block = Block(program.n_sites, program.n_bits, ka, kb)
+        if not block.valid():
+            return None, 0
+        if not sharded and size > 1 and n_global >= size:
+            lo, hi = qdist.shard_bounds(n_global, rank, size)
+            local, sharded = hi - lo, True
+        if level < len(plan) - 2:
+            n_global *= len(uniq[level])
+            local *= len(uniq[level])
+    return block, local if sharded else n_global
+
+
 def response_function(program: StepProgram, mu, side_seq: str, direction_seq: str, step_counts, engine=None,
                       device_output: bool = False):
     """Signal over the delay grid.  ``step_counts``: one integer list per delay (any order, duplicates allowed); for
@@ -80,6 +101,30 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
     mu_dev = eng.to_device(np.asarray(mu, dtype=np.float64), torch.float64)
     rank, size = qdist.world()
 
+    # Last delay in the Heisenberg picture: <W, Phi^n sigma> = <(Phi^T)^n W, sigma>.  ONE propagation of the emission
+    # read-out W with the transposed step replaces one propagation per chain; the signal is then the product
+    # [chains x E] . [E x emissions] (qsx_readout_gemm).  The read-out does not depend on the chains, so it is
+    # propagated on a side stream while the earlier delays run.
+    readouts = side_stream = None
+    last_block, chains = _last_level(program, plan, uniq, rank, size)
+    if (not continuous and last_block is not None and chains >= int(os.environ.get('QSX_HEISENBERG_MIN', '8'))
+            and not os.environ.get('QSX_DISABLE_HEISENBERG')):
+        back = program.bind(last_block, fused=False)
+        from . import rr as rr_mod
+        small = not os.environ.get('QSX_DISABLE_RR') and rr_mod.build(program, back) is not None
+        if not small:                                   # the register-resident small-block kernel is faster forwards
+            ptr, idx, w = last_block.emission_observable(np.asarray(mu, dtype=float))
+            readout = np.zeros(last_block.size, dtype=complex)
+            np.add.at(readout, np.asarray(idx[ptr[0]:ptr[1]]), np.asarray(w[ptr[0]:ptr[1]]))
+            emit = uniq[-1]
+            side_stream = torch.cuda.Stream(device=eng.device)
+            side_stream.wait_stream(torch.cuda.current_stream(eng.device))
+            with torch.cuda.stream(side_stream):
+                dev_back = eng.upload_program(back.transposed(), program)
+                _, snap = eng.evolve(dev_back, eng.to_device(readout.reshape(1, -1)), 1, int(emit.max()), emit,
+                                     snapshots=True)
+                readouts = snap[0]
+
     ka = kb = 0
     block = program.block(0, 0)
     sigma = torch.zeros((1, block.size), dtype=torch.complex128, device=eng.device)
@@ -103,23 +148,18 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
             sharded, shard_units = True, n_global
         sigma = eng.apply_dipole(block, new_block, 0 if side == 'k' else 1, mu_dev, sigma)
         block, ka, kb = new_block, nka, nkb
-        dev = upload(block)
+        last = level == len(plan) - 2
+        dev = None if last and readouts is not None else upload(block)
         n_local = sigma.shape[0]
         emit = uniq[level]
         if level < len(plan) - 2:
             _, snap = propagate(dev, sigma, n_local, emit, snapshots=True)
             sigma = snap.reshape(n_local * len(emit), block.size)
-        elif (not continuous and 'rr' not in dev and n_local >= int(os.environ.get('QSX_HEISENBERG_MIN', '8'))
-              and not os.environ.get('QSX_DISABLE_HEISENBERG')):
-            # Last delay in the Heisenberg picture: <W, Phi^n sigma> = <(Phi^T)^n W, sigma>.  ONE propagation of the
-            # emission read-out W with the transposed step replaces one propagation per chain; the signal is then the
-            # product [chains x E] . [E x emissions] (qsx_readout_gemm).
-            ptr, idx, w = block.emission_observable(np.asarray(mu, dtype=float))
-            readout = np.zeros(block.size, dtype=complex)
-            np.add.at(readout, np.asarray(idx[ptr[0]:ptr[1]]), np.asarray(w[ptr[0]:ptr[1]]))
-            back = eng.upload_program(program.bind(block, fused=False).transposed(), program)
-            _, snap = eng.evolve(back, eng.to_device(readout.reshape(1, -1)), 1, int(emit.max()), emit, snapshots=True)
-            out = eng.readout_gemm(sigma.reshape(n_local, block.size).contiguous(), snap[0].contiguous())
+        elif readouts is not None:
+            main = torch.cuda.current_stream(eng.device)
+            main.wait_stream(side_stream)
+            readouts.record_stream(main)
+            out = eng.readout_gemm(sigma.reshape(n_local, block.size).contiguous(), readouts.contiguous())
         else:
             obs = eng.upload_observables(*block.emission_observable(np.asarray(mu, dtype=float)), kind='emission', mu=mu)
             out, _ = propagate(dev, sigma, n_local, emit, obs=obs)
