@@ -117,7 +117,7 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
             readout = np.zeros(last_block.size, dtype=complex)
             np.add.at(readout, np.asarray(idx[ptr[0]:ptr[1]]), np.asarray(w[ptr[0]:ptr[1]]))
             emit = uniq[-1]
-            side_stream = torch.cuda.Stream(device=eng.device)
+            side_stream = eng.side_stream
             side_stream.wait_stream(torch.cuda.current_stream(eng.device))
             with torch.cuda.stream(side_stream):
                 dev_back = eng.upload_program(back.transposed(), program)

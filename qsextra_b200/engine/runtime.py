@@ -44,6 +44,7 @@ class Engine:
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self._blocks: dict[Block, DeviceBlock] = {}
         self._recipes: dict = {}              # device copies of parameter recipes, by content
+        self._side_stream = None
         self.aux_launches = 0                 # table-assembly kernels (qsx_bind_params, qsx_rr_tables)
         self.launches = 0                     # kernels enqueued through this engine (bench bookkeeping)
         self.h2d_bytes = 0                    # bytes copied host -> device through to_device()
@@ -53,6 +54,14 @@ class Engine:
         self.sm_count, self.smem_optin, self.cc = sm.value, smem.value, cc.value
 
     # ---- helpers --------------------------------------------------------------------------
+    @property
+    def side_stream(self):
+        """One extra stream per engine for work that is independent of the main sequence (kept, so that the caching
+        allocator reuses its blocks from call to call)."""
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        return self._side_stream
+
     def device_block(self, block: Block) -> DeviceBlock:
         db = self._blocks.get(block)
         if db is None:

@@ -14,5 +14,5 @@ for rep in range(3):
     torch.cuda.synchronize()
     print('rep %d: %.3f ms per spectrum' % (rep, (time.perf_counter() - t0) / 16 * 1e3))
 import cProfile, pstats
-cProfile.run('postprocessing(spec, sig, RF_freq=1.5, damping_rate=0.005, pad_extension=3, T2_index=3); torch.cuda.synchronize()', '/tmp/p.prof')
-pstats.Stats('/tmp/p.prof').sort_stats('cumtime').print_stats(18)
+cProfile.run('for i in range(16): postprocessing(spec, sig, RF_freq=1.5, damping_rate=0.005, pad_extension=3, T2_index=i)\ntorch.cuda.synchronize()', '/tmp/p.prof')
+pstats.Stats('/tmp/p.prof').sort_stats('tottime').print_stats(14)
