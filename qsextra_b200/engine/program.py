@@ -608,9 +608,6 @@ class BoundProgram:
         """[len(slots), B] rotation angles behind the cos/sin columns ``slots`` (from the recipe, no trigonometry)."""
         return self.recipe.phases(list(slots))
 
-    def columns(self, slots) -> np.ndarray:
-        """Some parameter columns [B, len(slots)]."""
-        return self.params[:, list(slots)]
 
 
 class StepProgram:

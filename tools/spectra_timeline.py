@@ -29,3 +29,18 @@ def post():
         postprocessing(specs[0], sigs[0], RF_freq=1.5, damping_rate=0.005, pad_extension=3, T2_index=idx)
     torch.cuda.synchronize()
 cProfile.run('post()', '/tmp/q.prof'); pstats.Stats('/tmp/q.prof').sort_stats('tottime').print_stats(8)
+print('--- interleaved: simulate one diagram, transform its 16 slices, next diagram')
+for rep in range(4):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    total = torch.zeros((), dtype=torch.float64, device='cuda')
+    marks = []
+    for sp in specs:
+        ta = time.perf_counter()
+        sig = qspectroscopy(system, sp, verbose=False, device_output=True, **kw)
+        tb = time.perf_counter()
+        for idx in range(len(delays[1])):
+            _, spectrum = postprocessing(sp, sig, RF_freq=1.5, damping_rate=0.005, pad_extension=3, T2_index=idx)
+            total += spectrum.abs().sum()
+        marks.append(((tb - ta) * 1e3, (time.perf_counter() - tb) * 1e3))
+    total = float(total)
+    print('rep %d: %.1f ms' % (rep, (time.perf_counter() - t0) * 1e3), ['sim %.1f post %.1f' % m for m in marks])
