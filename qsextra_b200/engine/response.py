@@ -17,6 +17,7 @@ the signal.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 
 import numpy as np
@@ -117,9 +118,11 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
             readout = np.zeros(last_block.size, dtype=complex)
             np.add.at(readout, np.asarray(idx[ptr[0]:ptr[1]]), np.asarray(w[ptr[0]:ptr[1]]))
             emit = uniq[-1]
-            side_stream = eng.side_stream
-            side_stream.wait_stream(torch.cuda.current_stream(eng.device))
-            with torch.cuda.stream(side_stream):
+            on_gpu = eng.device.type == 'cuda'           # (the CPU stand-in of the tests has no streams)
+            side_stream = eng.side_stream if on_gpu else None
+            if on_gpu:
+                side_stream.wait_stream(torch.cuda.current_stream(eng.device))
+            with (torch.cuda.stream(side_stream) if on_gpu else contextlib.nullcontext()):
                 dev_back = eng.upload_program(back.transposed(), program)
                 _, snap = eng.evolve(dev_back, eng.to_device(readout.reshape(1, -1)), 1, int(emit.max()), emit,
                                      snapshots=True)
@@ -156,9 +159,10 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
             _, snap = propagate(dev, sigma, n_local, emit, snapshots=True)
             sigma = snap.reshape(n_local * len(emit), block.size)
         elif readouts is not None:
-            main = torch.cuda.current_stream(eng.device)
-            main.wait_stream(side_stream)
-            readouts.record_stream(main)
+            if side_stream is not None:
+                main = torch.cuda.current_stream(eng.device)
+                main.wait_stream(side_stream)
+                readouts.record_stream(main)
             out = eng.readout_gemm(sigma.reshape(n_local, block.size).contiguous(), readouts.contiguous())
         else:
             obs = eng.upload_observables(*block.emission_observable(np.asarray(mu, dtype=float)), kind='emission', mu=mu)

@@ -1,0 +1,119 @@
+"""The response tree (engine/response.py: levels, prefix sharing, sharding over ranks, read-out propagation for the last
+delay, gather) run on the CPU with a NumPy stand-in for the engine (tests/emulator.py emulates each kernel), alone and
+under a world_size-2 gloo group, against the goldens of the unmodified reference."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import emulator
+from helpers import build_spectroscopy, build_system, load_golden
+from qsextra_b200.engine.response import response_function
+from qsextra_b200.qcomo.evolution.qevolve import _program_for, _validate_rates
+from qsextra_b200.spectroscopy.simulation.qspectroscopy import delay_step_counts
+
+CASES = ['qspectroscopy_esa_dimer_markov', 'qspectroscopy_se_dimer_t2', 'qspectroscopy_custom_kbkk_dimer',
+         'qspectroscopy_gsb_dimer_modes', 'qspectroscopy_se_trimer_markov']
+
+
+class NumpyEngine:
+    """The part of ``runtime.Engine`` the response tree uses, with every kernel replaced by its NumPy emulation."""
+
+    def __init__(self):
+        self.device = torch.device('cpu')
+        self.transposed_runs = 0
+
+    def to_device(self, array, dtype=None):
+        t = torch.as_tensor(np.ascontiguousarray(array))
+        return t if dtype is None else t.to(dtype)
+
+    def apply_dipole(self, in_block, out_block, side, mu, sigma):
+        rows = sigma.numpy().reshape(-1, in_block.dim_a, in_block.dim_b)
+        out = [emulator.apply_dipole(r, in_block, out_block, side, mu.numpy()) for r in rows]
+        return torch.as_tensor(np.array(out).reshape(len(out), -1))
+
+    def upload_program(self, bound, program=None):
+        return dict(bound=bound)
+
+    def upload_observables(self, ptr, idx, w, kind=None, mu=None):
+        return dict(host=(np.asarray(ptr), np.asarray(idx), np.asarray(w)))
+
+    def evolve(self, prog, sigma_in, n_inst, n_steps, emit_steps, obs=None, snapshots=False, **_):
+        bound = prog['bound']
+        self.transposed_runs += int(bound.is_transposed)
+        blk = bound.block
+        emit = [int(e) for e in np.asarray(emit_steps)]
+        rows = sigma_in.numpy().reshape(-1, blk.dim_a, blk.dim_b)
+        snaps = np.zeros((n_inst, len(emit), blk.size), dtype=complex)
+        for i in range(n_inst):
+            sigma = rows[i]
+            for step in range(n_steps + 1):
+                if step:
+                    sigma = emulator.apply_step(sigma, bound)
+                for k, e in enumerate(emit):
+                    if e == step:
+                        snaps[i, k] = sigma.reshape(-1)
+        out_obs = None
+        if obs is not None:
+            ptr, idx, w = obs['host']
+            out_obs = torch.as_tensor((snaps[:, :, idx[ptr[0]:ptr[1]]] * w[ptr[0]:ptr[1]]).sum(-1)[:, :, None])
+        return out_obs, (torch.as_tensor(snaps) if snapshots else None)
+
+    def readout_gemm(self, sigma, readouts):
+        return sigma @ readouts.transpose(0, 1)
+
+
+def signal_of(name, engine):
+    meta, arrays = load_golden(name)
+    system = build_system(meta['system'])
+    spec = build_spectroscopy(meta['label'], meta['delay_time'])
+    kw = dict(meta['kwargs'])
+    counts, (dt, dt_trotter, tn, _) = delay_step_counts(spec.delay_time, kw['dt'], kw.get('Trotter_number', 1))
+    program = _program_for(system, dt, dt_trotter, tn, kw.get('Trotter_order', 1), _validate_rates(system, kw.get('coll_rates')))
+    got = response_function(program, np.asarray(system.dipole_moments, dtype=float), spec.side_seq, spec.direction_seq,
+                            counts, engine=engine)
+    return got, arrays['signal']
+
+
+@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('heisenberg', [False, True])
+def test_tree_on_the_cpu_stand_in(name, heisenberg, monkeypatch):
+    monkeypatch.setenv('QSX_DISABLE_RR', '1')
+    monkeypatch.setenv('QSX_HEISENBERG_MIN', '1' if heisenberg else '1000000')
+    engine = NumpyEngine()
+    got, want = signal_of(name, engine)
+    assert got.shape == want.shape and np.abs(got - want).max() < 1e-10 * max(1.0, np.abs(want).max())
+    assert (engine.transposed_runs > 0) == heisenberg
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, size, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), QSX_DISABLE_RR='1', QSX_HEISENBERG_MIN='2')
+    dist.init_process_group('gloo', rank=rank, world_size=size)
+    try:
+        worst, transposed = 0.0, 0
+        for name in ('qspectroscopy_esa_dimer_t2', 'qspectroscopy_se_trimer_markov'):
+            engine = NumpyEngine()
+            got, want = signal_of(name, engine)
+            worst = max(worst, float(np.abs(got - want).max()))
+            transposed += engine.transposed_runs
+        np.save(os.path.join(out_dir, 'r%d.npy' % rank), np.array([worst, transposed]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('size', [2, 3])
+def test_tree_sharded_over_a_gloo_group(tmp_path, size):
+    mp.spawn(_worker, args=(size, _free_port(), str(tmp_path)), nprocs=size, join=True)
+    for r in range(size):
+        worst, transposed = np.load(os.path.join(str(tmp_path), 'r%d.npy' % r))
+        assert worst < 1e-10                                  # every rank holds the full, correct signal
