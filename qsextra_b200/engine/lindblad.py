@@ -188,8 +188,11 @@ class LindbladProgram:
         gen.eliminate_zeros()
         return gen
 
-    def bind(self, block: Block, **_ignored) -> BoundLindblad:
-        return _to_ell(self.generator(block), block)
+    def bind(self, block: Block, transposed: bool = False, **_ignored) -> BoundLindblad:
+        """ELL tables of the generator; ``transposed``: of L^T, which propagates a read-out W instead of the state
+        (<W, e^{Lt} sigma> = <e^{L^T t} W, sigma>, pairing without conjugation)."""
+        gen = self.generator(block)
+        return _to_ell(gen.T if transposed else gen, block)
 
     def bind_ket(self, k_exc: int) -> BoundLindblad:
         """Schroedinger generator -iH of one exciton-number sector (a ket evolves as a one-column block)."""

@@ -108,12 +108,14 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
     # propagated on a side stream while the earlier delays run.
     readouts = side_stream = None
     last_block, chains = _last_level(program, plan, uniq, rank, size)
-    if (not continuous and last_block is not None and chains >= int(os.environ.get('QSX_HEISENBERG_MIN', '8'))
+    if (last_block is not None and chains >= int(os.environ.get('QSX_HEISENBERG_MIN', '8'))
             and not os.environ.get('QSX_DISABLE_HEISENBERG')):
-        back = program.bind(last_block, fused=False)
-        from . import rr as rr_mod
-        small = not os.environ.get('QSX_DISABLE_RR') and rr_mod.build(program, back) is not None
-        if not small:                                   # the register-resident small-block kernel is faster forwards
+        small = False
+        if not continuous:                              # the register-resident small-block kernel is faster forwards
+            from . import rr as rr_mod
+            back = program.bind(last_block, fused=False)
+            small = not os.environ.get('QSX_DISABLE_RR') and rr_mod.build(program, back) is not None
+        if not small:
             ptr, idx, w = last_block.emission_observable(np.asarray(mu, dtype=float))
             readout = np.zeros(last_block.size, dtype=complex)
             np.add.at(readout, np.asarray(idx[ptr[0]:ptr[1]]), np.asarray(w[ptr[0]:ptr[1]]))
@@ -123,9 +125,14 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
             if on_gpu:
                 side_stream.wait_stream(torch.cuda.current_stream(eng.device))
             with (torch.cuda.stream(side_stream) if on_gpu else contextlib.nullcontext()):
-                dev_back = eng.upload_program(back.transposed(), program)
-                _, snap = eng.evolve(dev_back, eng.to_device(readout.reshape(1, -1)), 1, int(emit.max()), emit,
-                                     snapshots=True)
+                start = eng.to_device(readout.reshape(1, -1))
+                if continuous:
+                    from .lindblad import segments_from_times
+                    dev_back = eng.upload_lindblad(program.bind(last_block, transposed=True))
+                    _, snap = eng.evolve_lindblad(dev_back, start, 1, segments_from_times(emit), snapshots=True)
+                else:
+                    dev_back = eng.upload_program(back.transposed(), program)
+                    _, snap = eng.evolve(dev_back, start, 1, int(emit.max()), emit, snapshots=True)
                 readouts = snap[0]
 
     ka = kb = 0

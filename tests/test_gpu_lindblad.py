@@ -142,3 +142,18 @@ def test_argument_errors(engine):
         engine.evolve_lindblad(dev, sigma, 1, [-0.1], snapshots=True)
     with pytest.raises(cabi.QsxError, match='Taylor'):
         engine.evolve_lindblad(dev, sigma, 1, [0.1], snapshots=True, terms=1)
+
+
+def test_clspectroscopy_goldens_with_the_read_out_propagated(engine, monkeypatch):
+    """Same goldens with the last delay in the Heisenberg picture (generator transposed), forced for every grid."""
+    monkeypatch.setenv('QSX_HEISENBERG_MIN', '1')
+    seen = 0
+    for path in sorted(glob.glob(os.path.join(GOLDEN, 'qspectroscopy_*.npz'))):
+        meta, g = load_golden(os.path.basename(path)[:-4])
+        if 'signal_cl' not in g:
+            continue
+        got = clspectroscopy(build_system(meta['system']), spectroscopy_of(meta), verbose=False,
+                             rates=meta['kwargs'].get('coll_rates'))
+        assert np.abs(got - g['signal_cl']).max() < TOL * max(1.0, np.abs(g['signal_cl']).max()), path
+        seen += 1
+    assert seen >= 10
