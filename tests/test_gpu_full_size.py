@@ -95,7 +95,7 @@ def test_c3_dimer_2des_full_grid(engine):
 
 def test_c4_chain_with_pseudomodes_reduced_grid(engine):
     """BASELINE configs[3] geometry (4 sites, one pseudomode each) on a reduced grid: all block shapes of the full run
-    (16x64, 64x64, 16x16, 64x16, 96x64) through the shared-memory pass kernel, against the oracle on a corner."""
+    (16x64, 64x64, 16x16, 64x16, 96x64) through the kernels the full run uses, against the oracle on a corner."""
     J = np.zeros((4, 4))
     for i in range(3):
         J[i, i + 1] = J[i + 1, i] = -0.01
@@ -145,3 +145,27 @@ def test_c5_eight_site_aggregate_streaming_path(engine):
         sig = emulator.apply_step(sig, bound)
         want = [np.real(np.diag(sig)).reshape(n, -1)[i].sum() for i in range(n)]
         assert np.abs(pops[step] - want).max() < 1e-12
+
+
+def test_c5_collision_model_against_master_equation(engine):
+    """BASELINE configs[4] as stated: the 8-site aggregate with 2-level pseudomodes, collision-model dynamics (qevolve,
+    streaming path) cross-checked with the master equation (clevolve -> qsx_lindblad_evolve on the same 2048 x 2048
+    single-exciton block, 4.2 M elements, generator of 63 M entries).  The gap is the O(dt) discretisation of the
+    collision model: it halves when dt halves."""
+    from qsextra_b200.qcomo import clevolve
+    n = 8
+    J = np.zeros((n, n))
+    for i in range(n - 1):
+        J[i, i + 1] = J[i + 1, i] = -0.01
+    eps = [1.55, 1.50, 1.46, 1.52, 1.49, 1.53, 1.47, 1.51]
+    s = ChromophoreSystem(energies=eps, couplings=J, dipole_moments=[1.] * n, frequencies_pseudomode=0.02,
+                          levels_pseudomode=2, couplings_ep=float(np.sqrt(GAMMA * 0.1 / 2)))
+    s.set_state('localized excitation', 0)
+    t = np.arange(0, 61, 20) * DT
+    cl = np.array(clevolve(s, t, rates=[0.2], verbose=False).expect).T
+    assert cl.shape == (4, n) and np.abs(cl.sum(1) - 1).max() < 1e-10 and cl.min() > -1e-12
+    gaps = []
+    for sub in (1, 2):
+        q = qevolve(s, t, shots=0, dt=DT / sub, coll_rates=[0.2], verbose=False).populations
+        gaps.append(np.abs(q - cl).max())
+    assert gaps[0] < 2e-3 and 1.7 < gaps[0] / gaps[1] < 2.3, gaps
