@@ -10,7 +10,11 @@ X/Y circuits, each re-evolved from t = 0.  Because everything is linear in sigma
   * <X_kb> + i<Y_kb> of the ketbra ancilla (:90-91, :180-183) is the trace of the block after the emission
     operator (a read-out of ``qsx_evolve``);
   * chains that share a prefix along t1 -> t2 -> t3 are evolved once: level n evolves every instance produced by
-    level n-1 and snapshots it at each distinct step count of the n-th delay list.
+    level n-1 and snapshots it at each distinct step count of the n-th delay list;
+  * the LAST delay is evaluated in the Heisenberg picture when it holds many chains: <W, Phi^n sigma> =
+    <(Phi^T)^n W, sigma>, so the emission read-out W is propagated once with the transposed step (on a side stream,
+    while the earlier delays run) and the signal is one [chains x E] . [E x emissions] product
+    (``qsx_readout_gemm``) instead of one propagation per chain.
 
 Independent chains are sharded over ranks at the first level that has enough of them; one all-gather assembles
 the signal.
