@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define QSX_ABI_VERSION 13
+#define QSX_ABI_VERSION 14
 
 enum {
     QSX_OK = 0,
@@ -224,9 +224,10 @@ typedef struct qsx_rrc_args {
     const double* sigma_in;      /* DEVICE [n_src][DA*DB] complex128, logical order */
     int32_t n_steps, n_emit;
     const int32_t* emit_steps;   /* DEVICE */
-    int32_t emit_trace;          /* 1: out_obs[inst][emit] = Tr[(sum_s mu_s X_s) sigma] (complex128) */
+    int32_t emit_trace;          /* 1: out_obs[inst][emit] = Tr[(sum_s mu_s X_s) sigma] (complex128), KB = KA -+ 1 blocks;
+                                  * 2: out_obs[inst][emit][site] = population of the site (float64), KA = KB blocks */
     double mu[16];
-    double* out_obs;             /* DEVICE [n_inst][n_emit] complex128 or NULL */
+    double* out_obs;             /* DEVICE [n_inst][n_emit] complex128 / [n_inst][n_emit][n_sites] float64, or NULL */
     double* out_snap;            /* DEVICE [n_inst][n_emit][DA*DB] complex128, logical order, or NULL */
 } qsx_rrc_args;
 

@@ -1159,6 +1159,7 @@ int32_t qsx_evolve_rrc(const qsx_rrc_args* a, void* stream) {
     if (a->n_inst < 0 || a->n_steps < 0 || a->n_emit < 0) return fail(QSX_ERR_INVALID, "negative count%s");
     if (!a->params || (a->n_inst > 0 && !a->sigma_in) || (a->n_emit > 0 && !a->emit_steps))
         return fail(QSX_ERR_INVALID, "null table%s");
+    if (a->emit_trace < 0 || a->emit_trace > 2) return fail(QSX_ERR_INVALID, "emit_trace must be 0, 1 or 2%s");
     if (a->emit_trace && !a->out_obs) return fail(QSX_ERR_INVALID, "null read-out buffer%s");
     if (a->n_inst == 0 || a->n_emit == 0) return QSX_OK;
     int sms = 0, smem_max = 0;

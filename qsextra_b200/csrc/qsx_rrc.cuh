@@ -182,17 +182,21 @@ __device__ __forceinline__ void big_step(double2 (&v)[BigProg<PID>::NA][BigProg<
     (big_op<PID, Os>(v, w, P, xbuf, which, tid), ...);
 }
 
+// Read-outs: per-site sums over the compile-time pairs em[][] = (i, j, site) of the threads with m_a == m_b --
+// (KA, KB = KA -+ 1) blocks: the pairs whose configurations differ in `site` (emission Tr[(sum_s mu_s X_s) sigma]);
+// (KA, KA) blocks: the diagonal pairs (i, i) with `site` occupied (populations).
 template <int PID, int E>
-__device__ __forceinline__ void trace_term(const double2 (&v)[BigProg<PID>::NA][BigProg<PID>::NB], const double (&mu)[16],
-                                           double& re, double& im) {
+__device__ __forceinline__ void trace_term(const double2 (&v)[BigProg<PID>::NA][BigProg<PID>::NB],
+                                           double (&re)[BigProg<PID>::NBITS], double (&im)[BigProg<PID>::NBITS]) {
     constexpr int i = BigProg<PID>::em[E][0], j = BigProg<PID>::em[E][1], s = BigProg<PID>::em[E][2];
-    re = fma(mu[s], v[i][j].x, re);
-    im = fma(mu[s], v[i][j].y, im);
+    re[s] += v[i][j].x;
+    im[s] += v[i][j].y;
 }
 template <int PID, int... Es>
-__device__ __forceinline__ void big_trace(const double2 (&v)[BigProg<PID>::NA][BigProg<PID>::NB], const double (&mu)[16],
-                                          double& re, double& im, std::integer_sequence<int, Es...>) {
-    (trace_term<PID, Es>(v, mu, re, im), ...);
+__device__ __forceinline__ void big_trace(const double2 (&v)[BigProg<PID>::NA][BigProg<PID>::NB],
+                                          double (&re)[BigProg<PID>::NBITS], double (&im)[BigProg<PID>::NBITS],
+                                          std::integer_sequence<int, Es...>) {
+    (trace_term<PID, Es>(v, re, im), ...);
 }
 
 // (table entries are copied into constexpr locals: indexing a constexpr array with anything else odr-uses it in device code)
@@ -260,24 +264,36 @@ __global__ void __launch_bounds__(1 << (2 * BigProg<PID>::NBITS)) evolve_rrc_ker
             if (step) big_step<PID>(v, w, P, xbuf, which, tid, std::make_integer_sequence<int, BP::NOPS>{});
             if (step == next_emit) {
                 if (a.emit_trace) {
-                    double re = 0.0, im = 0.0;
+                    double re[NBITS], im[NBITS];                 // one pseudomode per site: NBITS = number of sites
+#pragma unroll
+                    for (int s = 0; s < NBITS; ++s) re[s] = im[s] = 0.0;
                     if constexpr (BP::NEM > 0) {
-                        if (ma == mb) big_trace<PID>(v, mu, re, im, std::make_integer_sequence<int, BP::NEM>{});
+                        if (ma == mb) big_trace<PID>(v, re, im, std::make_integer_sequence<int, BP::NEM>{});
                     }
 #pragma unroll
-                    for (int off = 16; off; off >>= 1) {
-                        re += __shfl_xor_sync(0xffffffffu, re, off);
-                        im += __shfl_xor_sync(0xffffffffu, im, off);
+                    for (int s = 0; s < NBITS; ++s) {
+#pragma unroll
+                        for (int off = 16; off; off >>= 1) {
+                            re[s] += __shfl_xor_sync(0xffffffffu, re[s], off);
+                            im[s] += __shfl_xor_sync(0xffffffffu, im[s], off);
+                        }
+                        if ((tid & 31) == 0) red[(tid >> 5) * NBITS + s] = make_double2(re[s], im[s]);
                     }
-                    if ((tid & 31) == 0) red[tid >> 5] = make_double2(re, im);
                     __syncthreads();
                     if (tid == 0) {
                         double sr = 0.0, si = 0.0;
-                        for (int wv = 0; wv < (NT + 31) / 32; ++wv) {
-                            sr += red[wv].x;
-                            si += red[wv].y;
+                        for (int s = 0; s < NBITS; ++s) {
+                            double pr = 0.0, pi = 0.0;
+                            for (int wv = 0; wv < (NT + 31) / 32; ++wv) {
+                                pr += red[wv * NBITS + s].x;
+                                pi += red[wv * NBITS + s].y;
+                            }
+                            if (a.emit_trace == 2) a.out_obs[((size_t)inst * a.n_emit + slot) * NBITS + s] = pr;
+                            sr = fma(mu[s], pr, sr);
+                            si = fma(mu[s], pi, si);
                         }
-                        reinterpret_cast<double2*>(a.out_obs)[(size_t)inst * a.n_emit + slot] = make_double2(sr, si);
+                        if (a.emit_trace == 1)
+                            reinterpret_cast<double2*>(a.out_obs)[(size_t)inst * a.n_emit + slot] = make_double2(sr, si);
                     }
                     __syncthreads();
                 }

@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libqsx.so')
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 EXPORTS = ('qsx_abi_version', 'qsx_last_error', 'qsx_device_info', 'qsx_evolve_workspace_bytes', 'qsx_evolve',
            'qsx_evolve_rr', 'qsx_bind_params', 'qsx_rr_tables', 'qsx_evolve_rrc', 'qsx_apply_dipole', 'qsx_readout_gemm', 'qsx_rotating_frame', 'qsx_spectrum_shift',

@@ -28,7 +28,7 @@ class RRCProgram:
     ket_pos: list            # thread-bit position of ket pseudomode bit k
     bra_pos: list
     ops: list                # [kind, a, b, mask, slot]  (HOP: a=p, b=q; ROT: a=bit, mask=rows/cols; AD: a=bit)
-    emission: list           # [(i, j, site)] pairs of the trace read-out (threads with m_a == m_b)
+    emission: list           # [(i, j, site)] pairs of the read-out (threads with m_a == m_b): emission trace or populations
     params: np.ndarray       # [B, stride]: Wcfg (2 nA nB) | gmA (2 * 2^nb) | gmB (2 * 2^nb) | op parameters
     shift: int               # offset of the op parameters
 
@@ -145,4 +145,7 @@ def build(program: StepProgram, bound: BoundProgram) -> RRCProgram | None:
                 i = ranks[0][mask_b ^ (1 << s)]
                 if i >= 0:
                     emission.append((int(i), j, s))
+    elif block.ka == block.kb:                        # populations: diagonal pairs (i, i) with site s occupied
+        for i, mask in enumerate(block.cfg_a):
+            emission += [(i, i, s) for s in range(n_sites) if (mask >> s) & 1]
     return RRCProgram(block, block.n_a, block.n_b, nb, ket_pos, bra_pos, ops, emission, params, shift)

@@ -132,7 +132,11 @@ class Engine:
         args.sigma_in = sigma_in.data_ptr()
         args.n_steps, args.n_emit, args.emit_steps = int(n_steps), n_emit, emit.data_ptr()
         out_obs = out_snap = None
-        if obs is not None:
+        if obs is not None and obs.get('kind') == 1:            # populations of a (KA, KA) block
+            args.emit_trace = 2
+            out_obs = torch.empty((n_inst, n_emit, big.block.n_sites), dtype=torch.float64, device=self.device)
+            args.out_obs = out_obs.data_ptr()
+        elif obs is not None:
             args.emit_trace = 1
             for i, m in enumerate(obs['mu'][:16]):
                 args.mu[i] = float(m)
@@ -224,7 +228,10 @@ class Engine:
         assert sigma_in.dtype == torch.complex128 and sigma_in.is_contiguous() and sigma_in.numel() % E == 0
         if 'rr' in prog and (obs is None or obs['n'] <= cabi.RR_MAX_OBS):
             return self._evolve_rr(prog, sigma_in, n_inst, n_steps, emit, obs, obs_real, snapshots, inst_set, inst_src)
-        if prog.get('rrc') is not None and not obs_real and (obs is None or (obs.get('kind') == 2 and obs['n'] == 1)):
+        blk_ = blk.block
+        rrc_serves = ((not obs_real and (obs is None or (obs.get('kind') == 2 and obs['n'] == 1))) or
+                      (obs_real and obs is not None and obs.get('kind') == 1 and obs['n'] == blk_.n_sites and blk_.ka == blk_.kb))
+        if prog.get('rrc') is not None and rrc_serves:
             done = self._evolve_rrc(prog, sigma_in, n_inst, n_steps, emit, obs, snapshots, inst_set, inst_src)
             if done is not None:
                 return done

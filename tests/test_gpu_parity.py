@@ -151,3 +151,32 @@ def test_heisenberg_and_forward_agree_on_a_chain_with_pseudomodes(engine, monkey
         forward = qspectroscopy(s, spec, shots=0, verbose=False, dt=dt, coll_rates=[0.2])
         monkeypatch.delenv('QSX_DISABLE_HEISENBERG')
         close(backward, forward, scale=max(1.0, np.abs(forward).max()))
+
+
+def test_populations_of_a_chain_with_pseudomodes_use_the_cta_wide_kernel(engine):
+    """qevolve / qevolve_batch on the single-exciton block of 3- and 4-site chains with one pseudomode per site: the
+    population read-out of the CTA-wide register-resident kernel against the oracle, several parameter sets at once."""
+    from qsextra_b200 import ChromophoreSystem
+    from qsextra_b200.engine.runtime import get_engine
+    rng = np.random.default_rng(21)
+    eng = get_engine()
+    for n in (3, 4):
+        systems, rates = [], []
+        for _ in range(3):
+            J = np.zeros((n, n))
+            for i in range(n - 1):
+                J[i, i + 1] = J[i + 1, i] = rng.uniform(-0.05, 0.05)
+            s = ChromophoreSystem(energies=rng.uniform(1.4, 1.6, n).tolist(), couplings=J, dipole_moments=[1.] * n,
+                                  frequencies_pseudomode=float(rng.uniform(0.01, 0.2)), levels_pseudomode=2,
+                                  couplings_ep=float(rng.uniform(0.02, 0.08)))
+            s.set_state('localized excitation', int(rng.integers(n)))
+            systems.append(s)
+            rates.append([float(rng.uniform(0.1, 0.4))])
+        dt = 0.15
+        time = np.arange(0, 31, 5) * dt
+        before = eng.launches
+        pops = qevolve_batch(systems, time, dt=dt, coll_rates=np.array(rates))
+        assert pops.shape == (3, 7, n) and eng.launches == before + 1          # one launch for the whole batch
+        for b in range(3):
+            ref = R.qevolve_exact(systems[b], time, dt=dt, coll_rates=rates[b])
+            close(pops[b], ref['populations'])
