@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define QSX_ABI_VERSION 14
+#define QSX_ABI_VERSION 15
 
 enum {
     QSX_OK = 0,
@@ -296,9 +296,12 @@ int32_t qsx_rr_tables(const qsx_rr_tables_args* args, void* stream);
 /* Signal of the last delay from the propagated read-outs (engine/response.py, Heisenberg picture):
  *   out[i][k] = sum_e sigma[i][e] * readout[k][e]      (no conjugation)
  * sigma [n_inst][E], readout [n_emit][E], out [n_inst][n_emit], all complex128 DEVICE arrays.  It stands for the
- * accumulation `signal[*time_indices] += ...` over the estimator values at qspectroscopy.py:180-183. */
+ * accumulation `signal[*time_indices] += ...` over the estimator values at qspectroscopy.py:180-183.
+ * The sums over e are split over several CTAs when the output alone is too small to fill the GPU; `workspace` (DEVICE,
+ * qsx_readout_gemm_workspace_bytes bytes, may be NULL: no split) holds the partial sums, added in a fixed order. */
+int64_t qsx_readout_gemm_workspace_bytes(int32_t n_inst, int32_t n_emit, int32_t n_elem);
 int32_t qsx_readout_gemm(int32_t n_inst, int32_t n_emit, int32_t n_elem, const double* sigma, const double* readout,
-                         double* out, void* stream);
+                         double* out, double* workspace, void* stream);
 
 /* Lindblad limit of the collision model -- replaces the QuTiP solver calls of the comparison path
  * (qsextra/qcomo/evolution/clevolve.py:27-46 and :88-107: sesolve / mesolve(H, state, time, c_ops, e_ops)).

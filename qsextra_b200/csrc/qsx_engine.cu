@@ -837,26 +837,33 @@ int32_t evolve_plan(const qsx_evolve_args* a, Plan* pl) {
 // warp are consecutive); 16 complex multiply-adds (64 DFMA) per 8 shared-memory loads.
 constexpr int RG_TM = 32, RG_TN = 64, RG_TK = 16;
 
-static __global__ void __launch_bounds__(128) readout_gemm_kernel(int M, int N, int K, const double2* __restrict__ A,
+// blockIdx.z selects a k-range of k_chunk elements (split-K: the output is small, 2048 x 128 for C4, so splitting the
+// 6144-long sums is what fills the GPU); partial sums go to C + z * M * N and reduce_splits_kernel adds them in a fixed
+// order (deterministic).
+static __global__ void __launch_bounds__(128) readout_gemm_kernel(int M, int N, int K, int k_chunk,
+                                                                  const double2* __restrict__ A,
                                                                   const double2* __restrict__ B, double2* __restrict__ C) {
     __shared__ double2 As[RG_TK][RG_TM + 1];
     __shared__ double2 Bs[RG_TK][RG_TN + 1];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * RG_TM, n0 = blockIdx.x * RG_TN;
+    const int k_begin = blockIdx.z * k_chunk;
+    const int k_end = min(K, k_begin + k_chunk);
+    C += (size_t)blockIdx.z * M * N;
     double2 acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = make_double2(0.0, 0.0);
     const double2 zero = make_double2(0.0, 0.0);
-    for (int k0 = 0; k0 < K; k0 += RG_TK) {
+    for (int k0 = k_begin; k0 < k_end; k0 += RG_TK) {
         for (int q = tid; q < RG_TM * RG_TK; q += 128) {               // consecutive threads read consecutive k
             const int r = q / RG_TK, c = q % RG_TK;
-            As[c][r] = (m0 + r < M && k0 + c < K) ? A[(size_t)(m0 + r) * K + k0 + c] : zero;
+            As[c][r] = (m0 + r < M && k0 + c < k_end) ? A[(size_t)(m0 + r) * K + k0 + c] : zero;
         }
         for (int q = tid; q < RG_TN * RG_TK; q += 128) {
             const int r = q / RG_TK, c = q % RG_TK;
-            Bs[c][r] = (n0 + r < N && k0 + c < K) ? B[(size_t)(n0 + r) * K + k0 + c] : zero;
+            Bs[c][r] = (n0 + r < N && k0 + c < k_end) ? B[(size_t)(n0 + r) * K + k0 + c] : zero;
         }
         __syncthreads();
 #pragma unroll
@@ -883,6 +890,18 @@ static __global__ void __launch_bounds__(128) readout_gemm_kernel(int M, int N, 
             const int m = m0 + ty + 8 * i, n = n0 + tx + 16 * j;
             if (m < M && n < N) C[(size_t)m * N + n] = acc[i][j];
         }
+}
+
+static __global__ void reduce_splits_kernel(size_t n, int splits, const double2* __restrict__ parts, double2* __restrict__ out) {
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        double2 sum = parts[e];
+        for (int z = 1; z < splits; ++z) {
+            const double2 p = parts[(size_t)z * n + e];
+            sum.x += p.x;
+            sum.y += p.y;
+        }
+        out[e] = sum;
+    }
 }
 
 // Parameter rows from raw angles (see qsx_bind_params): one thread per (set, column).
@@ -1171,17 +1190,45 @@ int32_t qsx_evolve_rrc(const qsx_rrc_args* a, void* stream) {
     return QSX_OK;
 }
 
+static int readout_splits(int n_inst, int n_emit, int n_elem, int sms) {
+    const long long tiles = (long long)((n_emit + RG_TN - 1) / RG_TN) * ((n_inst + RG_TM - 1) / RG_TM);
+    int splits = 1;
+    while (splits < 16 && tiles * splits < 4LL * sms && n_elem / (splits * 2) >= 256) splits *= 2;
+    return splits;
+}
+
+int64_t qsx_readout_gemm_workspace_bytes(int32_t n_inst, int32_t n_emit, int32_t n_elem) {
+    if (n_inst < 0 || n_emit < 0 || n_elem < 0) return fail(QSX_ERR_INVALID, "bad sizes%s");
+    int sms = 0, smem_max = 0;
+    int32_t rc = device_limits(&sms, &smem_max);
+    if (rc) return rc;
+    const int splits = readout_splits(n_inst, n_emit, n_elem, sms);
+    return splits > 1 ? (int64_t)splits * n_inst * n_emit * (int64_t)sizeof(double2) : 0;
+}
+
 int32_t qsx_readout_gemm(int32_t n_inst, int32_t n_emit, int32_t n_elem, const double* sigma, const double* readout,
-                         double* out, void* stream) {
+                         double* out, double* workspace, void* stream) {
     if (n_inst < 0 || n_emit < 0 || n_elem < 0) return fail(QSX_ERR_INVALID, "bad sizes%s");
     if (n_inst == 0 || n_emit == 0) return QSX_OK;
     if (!out || (n_elem > 0 && (!sigma || !readout))) return fail(QSX_ERR_INVALID, "null argument%s");
-    dim3 grid((n_emit + RG_TN - 1) / RG_TN, (n_inst + RG_TM - 1) / RG_TM);
+    int sms = 0, smem_max = 0;
+    int32_t rc = device_limits(&sms, &smem_max);
+    if (rc) return rc;
+    int splits = workspace ? readout_splits(n_inst, n_emit, n_elem, sms) : 1;     // without scratch: one pass, no split
+    dim3 grid((n_emit + RG_TN - 1) / RG_TN, (n_inst + RG_TM - 1) / RG_TM, splits);
     if (grid.y > 65535u) return fail(QSX_ERR_INVALID, "more than 2097120 chains in one call%s");
-    readout_gemm_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(n_inst, n_emit, n_elem,
+    int k_chunk = ((n_elem + splits - 1) / splits + RG_TK - 1) / RG_TK * RG_TK;
+    if (k_chunk < RG_TK) k_chunk = RG_TK;
+    double2* target = splits > 1 ? reinterpret_cast<double2*>(workspace) : reinterpret_cast<double2*>(out);
+    readout_gemm_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(n_inst, n_emit, n_elem, k_chunk,
                                                                  reinterpret_cast<const double2*>(sigma),
-                                                                 reinterpret_cast<const double2*>(readout),
-                                                                 reinterpret_cast<double2*>(out));
+                                                                 reinterpret_cast<const double2*>(readout), target);
+    if (splits > 1) {
+        const size_t n = (size_t)n_inst * n_emit;
+        size_t blocks = (n + 255) / 256;
+        if (blocks > (size_t)sms * 8) blocks = (size_t)sms * 8;
+        reduce_splits_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(n, splits, target, reinterpret_cast<double2*>(out));
+    }
     QSX_CUDA(cudaGetLastError());
     return QSX_OK;
 }

@@ -430,9 +430,13 @@ class Engine:
         assert readouts.shape[1] == E
         out = torch.empty((n_inst, n_emit), dtype=torch.complex128, device=self.device)
         with torch.cuda.device(self.device):
+            ws_bytes = self.lib.qsx_readout_gemm_workspace_bytes(n_inst, n_emit, E)
+            cabi.check(ws_bytes)
+            workspace = torch.empty(ws_bytes // 8, dtype=torch.float64, device=self.device) if ws_bytes else None
             stream = torch.cuda.current_stream(self.device).cuda_stream
             cabi.check(self.lib.qsx_readout_gemm(n_inst, n_emit, E, C.c_void_p(sigma.data_ptr()),
                                                  C.c_void_p(readouts.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                 C.c_void_p(workspace.data_ptr() if workspace is not None else None),
                                                  C.c_void_p(stream)))
         if n_inst > 0 and n_emit > 0:
             self.launches += 1
