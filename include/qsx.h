@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define QSX_ABI_VERSION 15
+#define QSX_ABI_VERSION 16
 
 enum {
     QSX_OK = 0,
@@ -232,6 +232,10 @@ typedef struct qsx_rrc_args {
 } qsx_rrc_args;
 
 int32_t qsx_evolve_rrc(const qsx_rrc_args* args, void* stream);
+
+/* Index of the compile-time program of qsx_evolve_rrc with this signature (HOST int32 vector), or -1 when the call
+ * would answer "no compile-time program matches"; lets the host plan before it enqueues anything. */
+int32_t qsx_rrc_find_program(const int32_t* signature, int32_t n_signature);
 
 int32_t qsx_abi_version(void);
 

@@ -1172,6 +1172,15 @@ int32_t qsx_evolve_rr(const qsx_rr_args* a, void* stream) {
     return QSX_OK;
 }
 
+int32_t qsx_rrc_find_program(const int32_t* signature, int32_t n_signature) {
+    if (!signature || n_signature <= 0) return fail(QSX_ERR_INVALID, "missing program signature%s");
+    qsx_rrc_args a;
+    memset(&a, 0, sizeof(a));
+    a.signature = signature;
+    a.n_signature = n_signature;
+    return rrc::find<0>(a);
+}
+
 int32_t qsx_evolve_rrc(const qsx_rrc_args* a, void* stream) {
     if (!a) return fail(QSX_ERR_INVALID, "null args%s");
     if (a->n_signature <= 0 || !a->signature) return fail(QSX_ERR_INVALID, "missing program signature%s");

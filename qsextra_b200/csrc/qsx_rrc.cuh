@@ -321,6 +321,16 @@ bool matches(const qsx_rrc_args& a) {
     return true;
 }
 
+// index of the compile-time program with this signature, or -1
+template <int PID>
+int find(const qsx_rrc_args& a) {
+    if constexpr (PID >= kNumBigProgs) {
+        return -1;
+    } else {
+        return matches<PID>(a) ? PID : find<PID + 1>(a);
+    }
+}
+
 // 0: launched, 1: no compile-time program matches, < 0: CUDA error code (negated)
 template <int PID>
 int launch(const qsx_rrc_args& a, int sms, int smem_max, cudaStream_t stream) {

@@ -11,10 +11,10 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libqsx.so')
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 EXPORTS = ('qsx_abi_version', 'qsx_last_error', 'qsx_device_info', 'qsx_evolve_workspace_bytes', 'qsx_evolve',
-           'qsx_evolve_rr', 'qsx_bind_params', 'qsx_rr_tables', 'qsx_evolve_rrc', 'qsx_apply_dipole', 'qsx_readout_gemm_workspace_bytes', 'qsx_readout_gemm', 'qsx_rotating_frame', 'qsx_spectrum_shift',
+           'qsx_evolve_rr', 'qsx_bind_params', 'qsx_rr_tables', 'qsx_evolve_rrc', 'qsx_rrc_find_program', 'qsx_apply_dipole', 'qsx_readout_gemm_workspace_bytes', 'qsx_readout_gemm', 'qsx_rotating_frame', 'qsx_spectrum_shift',
            'qsx_lindblad_workspace_bytes', 'qsx_lindblad_evolve',
            'qsx_fp64_peak')
 RR_MAX_OPS, RR_MAX_OBS, RR_MAX_ENTRIES = 24, 8, 4
@@ -130,6 +130,8 @@ def load():
     lib.qsx_evolve_rr.restype = C.c_int32
     lib.qsx_evolve_rrc.argtypes = [C.POINTER(QsxRRCArgs), C.c_void_p]
     lib.qsx_evolve_rrc.restype = C.c_int32
+    lib.qsx_rrc_find_program.argtypes = [C.c_void_p, C.c_int32]
+    lib.qsx_rrc_find_program.restype = C.c_int32
     lib.qsx_apply_dipole.argtypes = [C.POINTER(QsxBlock), C.POINTER(QsxBlock), C.c_int32, C.c_void_p, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
     lib.qsx_apply_dipole.restype = C.c_int32

@@ -134,10 +134,19 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
                     from .lindblad import segments_from_times
                     dev_back = eng.upload_lindblad(program.bind(last_block, transposed=True))
                     _, snap = eng.evolve_lindblad(dev_back, start, 1, segments_from_times(emit), snapshots=True)
+                    readouts = snap[0]
                 else:
                     dev_back = eng.upload_program(back.transposed(), program)
-                    _, snap = eng.evolve(dev_back, start, 1, int(emit.max()), emit, snapshots=True)
-                readouts = snap[0]
+                    # One read-out walks the steps alone (latency-bound); the chains walk them side by side.  Without a
+                    # compile-time program the transposed step is a plain operation list, several times slower per
+                    # step than the fused forward passes: then it only pays once the chains outnumber the SMs.
+                    fast = (bool(os.environ.get('QSX_HEISENBERG_ALWAYS')) or
+                            getattr(eng, 'has_static_rrc', lambda p: True)(dev_back))
+                    if fast or chains >= 4 * getattr(eng, 'sm_count', 1):
+                        _, snap = eng.evolve(dev_back, start, 1, int(emit.max()), emit, snapshots=True)
+                        readouts = snap[0]
+            if readouts is None:
+                side_stream = None
 
     ka = kb = 0
     block = program.block(0, 0)

@@ -116,6 +116,16 @@ class Engine:
                     w=self.to_device(np.asarray(w, dtype=np.complex128)), host=(np.asarray(ptr), np.asarray(idx), np.asarray(w)),
                     kind={'populations': 1, 'emission': 2}.get(kind, 0), mu=None if mu is None else np.asarray(mu, dtype=float))
 
+    def has_static_rrc(self, prog: dict) -> bool:
+        """Does a compile-time program of the CTA-wide kernel exist for this uploaded program?"""
+        if prog.get('rrc') is None:
+            return False
+        sig = prog['rrc_signature']
+        found = self.lib.qsx_rrc_find_program(C.c_void_p(sig.ctypes.data), int(sig.size))
+        if found < 0:
+            prog['rrc'] = None
+        return found >= 0
+
     def _evolve_rrc(self, prog, sigma_in, n_inst, n_steps, emit, obs, snapshots, inst_set, inst_src):
         """CTA-wide register-resident kernel (compile-time programs only).  Returns None when no compile-time program
         matches, so that the caller falls back to the shared-memory pass kernel."""

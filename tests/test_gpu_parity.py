@@ -125,6 +125,7 @@ def test_qspectroscopy_golden_with_the_last_delay_in_the_heisenberg_picture(engi
     """Same goldens with the read-out propagated backwards for the last delay (engine/response.py), which the big
     grids use; forced here for every grid size and with the register-resident forward path switched off."""
     monkeypatch.setenv('QSX_HEISENBERG_MIN', '1')
+    monkeypatch.setenv('QSX_HEISENBERG_ALWAYS', '1')
     monkeypatch.setenv('QSX_DISABLE_RR', '1')
     meta, arrays = load_golden(name)
     system = build_system(meta['system'])
