@@ -51,6 +51,27 @@ def interaction_plan(side_seq: str, direction_seq: str):
     return plan
 
 
+def _fingerprint(program) -> bytes:
+    """Digest of everything a propagation depends on: the structure of the step and every parameter value."""
+    import hashlib
+    h = hashlib.sha1()
+    if getattr(program, 'continuous', False):
+        for part in (program.energies, program.couplings, program.omega, program.coupl_ep, program.rates, program.levels):
+            h.update(repr(None if part is None else np.asarray(part).tolist()).encode())
+        return b'L' + h.digest()
+    h.update(repr(program.structure_key()).encode())
+    for op in program.lowered:
+        for value in vars(op).values():
+            if isinstance(value, np.ndarray):
+                h.update(np.ascontiguousarray(value).tobytes())
+            elif isinstance(value, (list, tuple)):
+                for item in value:
+                    for piece in (item if isinstance(item, (list, tuple)) else (item,)):
+                        if isinstance(piece, np.ndarray):
+                            h.update(np.ascontiguousarray(piece).tobytes())
+    return b'S' + h.digest()
+
+
 def _last_level(program, plan, uniq, rank, size):
     """(block of the last delay or None if a sector is empty, chains this rank holds there) -- the bookkeeping of
     ``response_function`` without any propagation."""
@@ -72,13 +93,103 @@ def _last_level(program, plan, uniq, rank, size):
     return block, local if sharded else n_global
 
 
+def _propagate_readout(eng, program, mu, last_block, chains, emit, continuous, stream_index):
+    """Enqueue the propagation of the emission read-out of ``last_block`` on a side stream, if the Heisenberg picture
+    is planned for this level.  -> (read-outs [n_emit, E] on the device, completion event | None) or None."""
+    if (last_block is None or chains < int(os.environ.get('QSX_HEISENBERG_MIN', '8'))
+            or os.environ.get('QSX_DISABLE_HEISENBERG')):
+        return None
+    back = None
+    if not continuous:                                  # the register-resident small-block kernel is faster forwards
+        from . import rr as rr_mod
+        back = program.bind(last_block, fused=False)
+        if not os.environ.get('QSX_DISABLE_RR') and rr_mod.build(program, back) is not None:
+            return None
+    ptr, idx, w = last_block.emission_observable(np.asarray(mu, dtype=float))
+    readout = np.zeros(last_block.size, dtype=complex)
+    np.add.at(readout, np.asarray(idx[ptr[0]:ptr[1]]), np.asarray(w[ptr[0]:ptr[1]]))
+    on_gpu = eng.device.type == 'cuda'                   # (the CPU stand-in of the tests has no streams)
+    side_stream = eng.side_stream_of(stream_index) if on_gpu else None
+    if on_gpu:
+        side_stream.wait_stream(torch.cuda.current_stream(eng.device))
+    readouts = None
+    with (torch.cuda.stream(side_stream) if on_gpu else contextlib.nullcontext()):
+        start = eng.to_device(readout.reshape(1, -1))
+        if continuous:
+            from .lindblad import segments_from_times
+            dev_back = eng.upload_lindblad(program.bind(last_block, transposed=True))
+            _, snap = eng.evolve_lindblad(dev_back, start, 1, segments_from_times(emit), snapshots=True)
+            readouts = snap[0]
+        else:
+            dev_back = eng.upload_program(back.transposed(), program)
+            # One read-out walks the steps alone (latency-bound); the chains walk them side by side.  Without a
+            # compile-time program the transposed step is a plain operation list, several times slower per step than
+            # the fused forward passes: then it only pays once the chains outnumber the SMs.
+            fast = (bool(os.environ.get('QSX_HEISENBERG_ALWAYS')) or
+                    getattr(eng, 'has_static_rrc', lambda p: True)(dev_back))
+            if fast or chains >= 4 * getattr(eng, 'sm_count', 1):
+                _, snap = eng.evolve(dev_back, start, 1, int(emit.max()), emit, snapshots=True)
+                readouts = snap[0]
+    if readouts is None:
+        return None
+    ready = None
+    if side_stream is not None:
+        ready = torch.cuda.Event()
+        ready.record(side_stream)
+    return readouts, ready
+
+
+def _unique_delays(step_counts, continuous):
+    uniq, inverse = [], []
+    for c in step_counts:
+        u, inv = np.unique(np.asarray(c, dtype=np.float64 if continuous else np.int64), return_inverse=True)
+        uniq.append(u if continuous else u.astype(np.int32))
+        inverse.append(inv)
+    return uniq, inverse
+
+
+def response_function_set(program: StepProgram, mu, sequences, step_counts, engine=None, device_output: bool = False):
+    """Several diagrams ``sequences = [(side_seq, direction_seq), ...]`` of the same system on the same delay grid (the
+    contributions of one 2-D spectrum).  All distinct read-out propagations are enqueued first, each on its own side
+    stream, so the longest one (the two-exciton block of esa) runs while the shorter diagrams are evaluated; the delay
+    levels the diagrams have in common are computed once (``shared`` of ``response_function``).  -> list of signals."""
+    from .runtime import get_engine
+    eng = engine or get_engine()
+    continuous = bool(getattr(program, 'continuous', False))
+    uniq, _ = _unique_delays(step_counts, continuous)
+    rank, size = qdist.world()
+    shared = {}
+    pending = []
+    for side_seq, direction_seq in sequences:
+        plan = interaction_plan(side_seq, direction_seq)
+        if len(plan) != len(step_counts) + 1:
+            raise ValueError('side_seq must have one more entry than delay_time')
+        last_block, chains = _last_level(program, plan, uniq, rank, size)
+        key = ('readouts', last_block, uniq[-1].tobytes())
+        if key not in shared and key not in [k for k, _ in pending]:
+            pending.append((key, (last_block, chains)))
+    # longest first: the block size orders the propagation times
+    pending.sort(key=lambda item: -(item[1][0].size if item[1][0] is not None else 0))
+    for index, (key, (last_block, chains)) in enumerate(pending):
+        got = _propagate_readout(eng, program, mu, last_block, chains, uniq[-1], continuous, index)
+        if got is not None:
+            shared[key] = got
+    return [response_function(program, mu, side_seq, direction_seq, step_counts, engine=eng,
+                              device_output=device_output, shared=shared) for side_seq, direction_seq in sequences]
+
+
 def response_function(program: StepProgram, mu, side_seq: str, direction_seq: str, step_counts, engine=None,
-                      device_output: bool = False):
+                      device_output: bool = False, shared: dict | None = None):
     """Signal over the delay grid.  ``step_counts``: one integer list per delay (any order, duplicates allowed); for
     a continuous-time program (``engine.lindblad.LindbladProgram``, the comparison path clspectroscopy.py:18-132) the
     lists hold the delay times themselves.
     Returns a complex ndarray of shape [len(c) for c in step_counts], identical on every rank (``device_output``: a
-    complex128 CUDA tensor instead, e.g. for the device post-processing)."""
+    complex128 CUDA tensor instead, e.g. for the device post-processing).
+
+    ``shared``: a dict the caller passes to successive calls for diagrams of the SAME system, parameters and delay
+    grid (e.g. gsb, se and esa of one 2-D spectrum).  Levels whose interaction prefix and delays coincide (all three
+    rephasing diagrams share the t1 level, se and esa also the t2 level) and read-outs of the same final block are
+    then computed once and kept on the device in it.  A dict filled for another program raises ``ValueError``."""
     from .runtime import get_engine
     eng = engine or get_engine()
     n_sites = program.n_sites
@@ -86,12 +197,8 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
     if len(plan) != len(step_counts) + 1:
         raise ValueError('side_seq must have one more entry than delay_time')
     shape = [len(c) for c in step_counts]
-    uniq, inverse = [], []
     continuous = bool(getattr(program, 'continuous', False))
-    for c in step_counts:
-        u, inv = np.unique(np.asarray(c, dtype=np.float64 if continuous else np.int64), return_inverse=True)
-        uniq.append(u if continuous else u.astype(np.int32))
-        inverse.append(inv)
+    uniq, inverse = _unique_delays(step_counts, continuous)
 
     def upload(block):
         if continuous:
@@ -106,47 +213,29 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
     mu_dev = eng.to_device(np.asarray(mu, dtype=np.float64), torch.float64)
     rank, size = qdist.world()
 
+    if shared is not None:
+        mark = (_fingerprint(program), np.asarray(mu, dtype=float).tobytes(), rank, size)
+        if shared.setdefault('program', mark) != mark:
+            raise ValueError('the shared dict was filled for a different system, parameter set or process group')
+
+    def prefix_key(level):
+        return ('level', tuple(plan[:level + 1]), tuple(u.tobytes() for u in uniq[:level + 1]))
+
     # Last delay in the Heisenberg picture: <W, Phi^n sigma> = <(Phi^T)^n W, sigma>.  ONE propagation of the emission
     # read-out W with the transposed step replaces one propagation per chain; the signal is then the product
     # [chains x E] . [E x emissions] (qsx_readout_gemm).  The read-out does not depend on the chains, so it is
     # propagated on a side stream while the earlier delays run.
-    readouts = side_stream = None
+    readouts = ready = None                             # propagated read-outs and the CUDA event of their completion
     last_block, chains = _last_level(program, plan, uniq, rank, size)
-    if (last_block is not None and chains >= int(os.environ.get('QSX_HEISENBERG_MIN', '8'))
-            and not os.environ.get('QSX_DISABLE_HEISENBERG')):
-        small = False
-        if not continuous:                              # the register-resident small-block kernel is faster forwards
-            from . import rr as rr_mod
-            back = program.bind(last_block, fused=False)
-            small = not os.environ.get('QSX_DISABLE_RR') and rr_mod.build(program, back) is not None
-        if not small:
-            ptr, idx, w = last_block.emission_observable(np.asarray(mu, dtype=float))
-            readout = np.zeros(last_block.size, dtype=complex)
-            np.add.at(readout, np.asarray(idx[ptr[0]:ptr[1]]), np.asarray(w[ptr[0]:ptr[1]]))
-            emit = uniq[-1]
-            on_gpu = eng.device.type == 'cuda'           # (the CPU stand-in of the tests has no streams)
-            side_stream = eng.side_stream if on_gpu else None
-            if on_gpu:
-                side_stream.wait_stream(torch.cuda.current_stream(eng.device))
-            with (torch.cuda.stream(side_stream) if on_gpu else contextlib.nullcontext()):
-                start = eng.to_device(readout.reshape(1, -1))
-                if continuous:
-                    from .lindblad import segments_from_times
-                    dev_back = eng.upload_lindblad(program.bind(last_block, transposed=True))
-                    _, snap = eng.evolve_lindblad(dev_back, start, 1, segments_from_times(emit), snapshots=True)
-                    readouts = snap[0]
-                else:
-                    dev_back = eng.upload_program(back.transposed(), program)
-                    # One read-out walks the steps alone (latency-bound); the chains walk them side by side.  Without a
-                    # compile-time program the transposed step is a plain operation list, several times slower per
-                    # step than the fused forward passes: then it only pays once the chains outnumber the SMs.
-                    fast = (bool(os.environ.get('QSX_HEISENBERG_ALWAYS')) or
-                            getattr(eng, 'has_static_rrc', lambda p: True)(dev_back))
-                    if fast or chains >= 4 * getattr(eng, 'sm_count', 1):
-                        _, snap = eng.evolve(dev_back, start, 1, int(emit.max()), emit, snapshots=True)
-                        readouts = snap[0]
-            if readouts is None:
-                side_stream = None
+    readout_key = ('readouts', last_block, uniq[-1].tobytes())
+    if shared is not None and readout_key in shared:
+        readouts, ready = shared[readout_key]
+    else:
+        got = _propagate_readout(eng, program, mu, last_block, chains, uniq[-1], continuous, 0)
+        if got is not None:
+            readouts, ready = got
+            if shared is not None:
+                shared[readout_key] = got
 
     ka = kb = 0
     block = program.block(0, 0)
@@ -165,13 +254,17 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
         if not new_block.valid():
             zero = True
             break
+        last = level == len(plan) - 2
+        if shared is not None and not last and prefix_key(level) in shared:
+            sigma, n_global, sharded, shard_units, rows_per_unit = shared[prefix_key(level)]
+            block, ka, kb = new_block, nka, nkb
+            continue
         if not sharded and size > 1 and n_global >= size:
             lo, hi = qdist.shard_bounds(n_global, rank, size)
             sigma = sigma[lo:hi].contiguous()
             sharded, shard_units = True, n_global
         sigma = eng.apply_dipole(block, new_block, 0 if side == 'k' else 1, mu_dev, sigma)
         block, ka, kb = new_block, nka, nkb
-        last = level == len(plan) - 2
         dev = None if last and readouts is not None else upload(block)
         n_local = sigma.shape[0]
         emit = uniq[level]
@@ -179,9 +272,9 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
             _, snap = propagate(dev, sigma, n_local, emit, snapshots=True)
             sigma = snap.reshape(n_local * len(emit), block.size)
         elif readouts is not None:
-            if side_stream is not None:
+            if ready is not None:
                 main = torch.cuda.current_stream(eng.device)
-                main.wait_stream(side_stream)
+                main.wait_event(ready)
                 readouts.record_stream(main)
             out = eng.readout_gemm(sigma.reshape(n_local, block.size).contiguous(), readouts.contiguous())
         else:
@@ -191,6 +284,8 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
         n_global *= len(emit)
         if sharded and level < len(plan) - 2:
             rows_per_unit *= len(emit)
+        if shared is not None and not last:
+            shared[prefix_key(level)] = (sigma, n_global, sharded, shard_units, rows_per_unit)
 
     if zero:
         return torch.zeros(shape, dtype=torch.complex128, device=eng.device) if device_output else np.zeros(shape, dtype=complex)

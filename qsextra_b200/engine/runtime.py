@@ -58,9 +58,16 @@ class Engine:
     def side_stream(self):
         """One extra stream per engine for work that is independent of the main sequence (kept, so that the caching
         allocator reuses its blocks from call to call)."""
+        return self.side_stream_of(0)
+
+    def side_stream_of(self, index: int):
+        """Side stream number ``index`` (a small fixed set, created once)."""
         if self._side_stream is None:
-            self._side_stream = torch.cuda.Stream(device=self.device)
-        return self._side_stream
+            self._side_stream = []
+        index %= 4
+        while len(self._side_stream) <= index:
+            self._side_stream.append(torch.cuda.Stream(device=self.device))
+        return self._side_stream[index]
 
     def device_block(self, block: Block) -> DeviceBlock:
         db = self._blocks.get(block)

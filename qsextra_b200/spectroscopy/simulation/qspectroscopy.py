@@ -24,7 +24,7 @@ from ...system import ChromophoreSystem, ExcitonicSystem
 from ...tools.oracle import ending_sentence
 from ...tools.tools import create_checkpoint_folder, destroy_checkpoint_folder
 from ...engine.program import resolve_time_grid
-from ...engine.response import response_function
+from ...engine.response import response_function, response_function_set
 from ...qcomo.evolution.qevolve import _program_for, _validate_rates, _validate_system
 from ..spectroscopy import Spectroscopy
 
@@ -51,6 +51,7 @@ def qspectroscopy(system: ChromophoreSystem | ExcitonicSystem,
                   checkpoint: bool = False,
                   restart_from_checkpoint: str | None = None,
                   device_output: bool = False,
+                  shared: dict | None = None,
                   **qevolve_kwds,
                   ) -> np.ndarray:
     """Simulate ``spectroscopy`` (a ``FeynmanDiagram`` or a ``Spectroscopy`` with hand-set sequences) on ``system``.
@@ -59,13 +60,15 @@ def qspectroscopy(system: ChromophoreSystem | ExcitonicSystem,
     ``GPU``); the reserved keys system/time/shots/initialize_circuit/verbose are dropped like the reference does.
     Returns a complex array with one axis per delay list.  Under ``torch.distributed`` the delay-grid chains are
     sharded over the ranks and every rank returns the full array.  ``device_output`` (an addition to the reference
-    signature) returns the signal as a complex128 CUDA tensor, which ``postprocessing`` accepts as it is.
+    signature) returns the signal as a complex128 CUDA tensor, which ``postprocessing`` accepts as it is.  ``shared``
+    (another addition): pass one dict to the calls for several diagrams of the same system, parameters and delay grid;
+    the delay levels they have in common are then computed once (``engine.response.response_function``).
     """
     _validate_system(system)
     if type(system) is ChromophoreSystem and system.mode_dict is None:
         warnings.warn("Pseudomodes not specified. Executing the dynamics with system as an ExcitonicSystem.")
         return qspectroscopy(system.extract_ExcitonicSystem(), spectroscopy, shots, verbose, checkpoint,
-                             restart_from_checkpoint, device_output, **qevolve_kwds)
+                             restart_from_checkpoint, device_output, shared, **qevolve_kwds)
     for key in _RESERVED:
         qevolve_kwds.pop(key, None)
     if spectroscopy.side_seq == '' or spectroscopy.direction_seq == '':
@@ -90,7 +93,7 @@ def qspectroscopy(system: ChromophoreSystem | ExcitonicSystem,
         folder = create_checkpoint_folder()
         print(f'Checkpoint folder created ({folder})')
     signal = response_function(program, np.asarray(system.dipole_moments, dtype=float), spectroscopy.side_seq,
-                               spectroscopy.direction_seq, counts, device_output=device_output)
+                               spectroscopy.direction_seq, counts, device_output=device_output, shared=shared)
     if kept is not None and kept.shape == signal.shape and last >= 0:
         flat, old = signal.reshape(-1), kept.reshape(-1)
         if device_output:
@@ -101,3 +104,50 @@ def qspectroscopy(system: ChromophoreSystem | ExcitonicSystem,
         destroy_checkpoint_folder(folder)
     ending_sentence(verbose)
     return signal
+
+
+def qspectroscopy_set(system: ChromophoreSystem | ExcitonicSystem,
+                      spectroscopies,
+                      shots: int = 1000,
+                      verbose: bool = True,
+                      device_output: bool = False,
+                      **qevolve_kwds,
+                      ) -> list:
+    """Several diagrams of one spectrum at once (new API; the reference calls ``qspectroscopy`` per diagram).
+
+    ``spectroscopies``: ``FeynmanDiagram`` / ``Spectroscopy`` objects with the SAME ``delay_time``.  The delay levels
+    the diagrams have in common are computed once and the read-out propagations of all of them run concurrently with
+    the rest (``engine.response.response_function_set``).  Returns one signal per entry, each identical to what
+    ``qspectroscopy`` returns for it.
+    """
+    spectroscopies = list(spectroscopies)
+    if not spectroscopies:
+        return []
+    _validate_system(system)
+    if type(system) is ChromophoreSystem and system.mode_dict is None:
+        warnings.warn("Pseudomodes not specified. Executing the dynamics with system as an ExcitonicSystem.")
+        return qspectroscopy_set(system.extract_ExcitonicSystem(), spectroscopies, shots, verbose, device_output,
+                                 **qevolve_kwds)
+    for key in _RESERVED:
+        qevolve_kwds.pop(key, None)
+    delays = spectroscopies[0].delay_time
+    for sp in spectroscopies:
+        if sp.side_seq == '' or sp.direction_seq == '':
+            raise ValueError('Spectroscopy object is not correctly defined. Spectroscopy.side_seq or Spectroscopy.direction_seq are missing.')
+        if len(sp.delay_time) != len(delays) or any(not np.array_equal(np.asarray(a, dtype=float), np.asarray(b, dtype=float))
+                                                     for a, b in zip(sp.delay_time, delays)):
+            raise ValueError('qspectroscopy_set needs the same delay_time in every entry')
+    unknown = set(qevolve_kwds) - {'Trotter_number', 'Trotter_order', 'dt', 'coll_rates', 'GPU'}
+    if unknown:
+        raise TypeError("qevolve() got an unexpected keyword argument '{}'".format(sorted(unknown)[0]))
+    coll_rates = _validate_rates(system, qevolve_kwds.get('coll_rates'))
+    if qevolve_kwds.get('dt') is None:
+        raise ValueError('qspectroscopy needs an explicit dt (with dt=None the reference derives dt from each scalar '
+                         'delay and fails at zero delay).')
+    counts, (dt, dt_trotter, trotter_number, _) = delay_step_counts(delays, qevolve_kwds['dt'], qevolve_kwds.get('Trotter_number', 1))
+    program = _program_for(system, dt, dt_trotter, trotter_number, qevolve_kwds.get('Trotter_order', 1), coll_rates)
+    signals = response_function_set(program, np.asarray(system.dipole_moments, dtype=float),
+                                    [(sp.side_seq, sp.direction_seq) for sp in spectroscopies], counts,
+                                    device_output=device_output)
+    ending_sentence(verbose)
+    return signals

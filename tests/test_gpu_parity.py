@@ -181,3 +181,39 @@ def test_populations_of_a_chain_with_pseudomodes_use_the_cta_wide_kernel(engine)
         for b in range(3):
             ref = R.qevolve_exact(systems[b], time, dt=dt, coll_rates=rates[b])
             close(pops[b], ref['populations'])
+
+
+def test_diagrams_of_one_spectrum_share_their_common_levels(engine):
+    """``shared=``: gsb, se and esa of the same system and grid computed with one dict equal the independent calls
+    (bit for bit: the shared levels are the same launches) and need fewer launches; another system is refused."""
+    from qsextra_b200 import ChromophoreSystem
+    from qsextra_b200.spectroscopy import FeynmanDiagram
+    J = np.zeros((4, 4))
+    for i in range(3):
+        J[i, i + 1] = J[i + 1, i] = -0.01
+    s = ChromophoreSystem(energies=[1.55, 1.50, 1.46, 1.52], couplings=J, dipole_moments=[1., 0.8, -0.6, 1.1],
+                          frequencies_pseudomode=0.02, levels_pseudomode=2, couplings_ep=0.054)
+    dt = 0.15
+    delays = [(dt * 3 * np.arange(6)).tolist(), (dt * 5 * np.arange(3)).tolist(), (dt * 3 * np.arange(7)).tolist()]
+    kw = dict(shots=0, verbose=False, dt=dt, coll_rates=[0.2])
+    before = engine.launches
+    alone = {lab: qspectroscopy(s, FeynmanDiagram(lab, delays), **kw) for lab in ('gsb', 'se', 'esa')}
+    launches_alone = engine.launches - before
+    shared = {}
+    before = engine.launches
+    together = {lab: qspectroscopy(s, FeynmanDiagram(lab, delays), shared=shared, **kw) for lab in ('gsb', 'se', 'esa')}
+    launches_together = engine.launches - before
+    for lab in alone:
+        assert np.array_equal(alone[lab], together[lab]), lab
+    assert launches_together < launches_alone
+    other = ChromophoreSystem(energies=[1.55, 1.50, 1.46, 1.53], couplings=J, dipole_moments=[1., 0.8, -0.6, 1.1],
+                              frequencies_pseudomode=0.02, levels_pseudomode=2, couplings_ep=0.054)
+    with pytest.raises(ValueError, match='shared dict'):
+        qspectroscopy(other, FeynmanDiagram('gsb', delays), shared=shared, **kw)
+    # the set API: read-outs of all diagrams enqueued up front
+    from qsextra_b200.spectroscopy import qspectroscopy_set
+    as_set = qspectroscopy_set(s, [FeynmanDiagram(lab, delays) for lab in ('gsb', 'se', 'esa')], **kw)
+    for lab, got in zip(('gsb', 'se', 'esa'), as_set):
+        assert np.array_equal(alone[lab], got), lab
+    with pytest.raises(ValueError, match='same delay_time'):
+        qspectroscopy_set(s, [FeynmanDiagram('gsb', delays), FeynmanDiagram('se', [delays[0], delays[1], delays[2][:-1]])], **kw)
