@@ -117,3 +117,32 @@ def test_tree_sharded_over_a_gloo_group(tmp_path, size):
     for r in range(size):
         worst, transposed = np.load(os.path.join(str(tmp_path), 'r%d.npy' % r))
         assert worst < 1e-10                                  # every rank holds the full, correct signal
+
+
+def test_set_of_diagrams_shares_levels_and_read_outs(monkeypatch):
+    """response_function_set on the stand-in engine: identical signals, fewer propagations."""
+    from qsextra_b200.engine.response import response_function_set
+    from qsextra_b200.spectroscopy import FeynmanDiagram
+    monkeypatch.setenv('QSX_DISABLE_RR', '1')
+    monkeypatch.setenv('QSX_HEISENBERG_MIN', '1')
+    meta, _ = load_golden('qspectroscopy_esa_dimer_t2')
+    system = build_system(meta['system'])
+    kw = dict(meta['kwargs'])
+    diagrams = [FeynmanDiagram(lab, meta['delay_time']) for lab in ('gsb', 'se', 'esa')]
+    counts, (dt, dt_trotter, tn, _) = delay_step_counts(diagrams[0].delay_time, kw['dt'], kw.get('Trotter_number', 1))
+    program = _program_for(system, dt, dt_trotter, tn, kw.get('Trotter_order', 1), _validate_rates(system, kw.get('coll_rates')))
+    mu = np.asarray(system.dipole_moments, dtype=float)
+
+    class Counting(NumpyEngine):
+        evolves = 0
+
+        def evolve(self, *a, **k):
+            Counting.evolves += 1
+            return super().evolve(*a, **k)
+
+    alone = [response_function(program, mu, d.side_seq, d.direction_seq, counts, engine=Counting()) for d in diagrams]
+    separately, Counting.evolves = Counting.evolves, 0
+    together = response_function_set(program, mu, [(d.side_seq, d.direction_seq) for d in diagrams], counts, engine=Counting())
+    assert all(np.array_equal(a, b) for a, b in zip(alone, together))
+    assert Counting.evolves < separately                       # 5 instead of 9 propagations
+    assert Counting.evolves == 5 and separately == 9
