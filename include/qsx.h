@@ -8,6 +8,11 @@
  *   AerSimulator().run(qc_list, shots=shots).result()                 qsextra/qcomo/evolution/qevolve.py:556-562
  *   Estimator(run_options={'shots': shots}).run(circuits, obs)...     qsextra/spectroscopy/simulation/qspectroscopy.py:114, :180-181
  *
+ * and, for the rows next to the hot path:
+ *
+ *   qutip.mesolve / sesolve(H, state, time, c_ops, e_ops)             qsextra/qcomo/evolution/clevolve.py:27-46, :88-107
+ *   rotating frame, np.pad, fft / ifft, fftshift                      qsextra/spectroscopy/postprocessing.py:9-97
+ *
  * Model.  One "instance" is the ket x bra block sigma[a][b] (complex128, row-major, b fastest) of the density
  * operator (qevolve) or of the ket-bra coherence (qspectroscopy) restricted to exciton-number sectors:
  *   a = cfgA_index << n_bits | bits_a ,  b = cfgB_index << n_bits | bits_b
