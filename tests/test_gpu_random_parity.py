@@ -80,14 +80,22 @@ SPECTRO_CASES = [  # (n, modes, label or (side, direction), Trotter number, with
     (2, 0, 'a', 1, True), (3, 0, 'gsb', 1, True), (3, 0, 'se', 2, True), (3, 0, 'esa', 1, True), (4, 0, 'esa', 1, False),
     (2, 1, 'esa', 1, True), (2, 1, ('kbkk', 'iiio'), 1, True), (2, 2, 'se', 1, True), (3, 1, 'gsb', 1, True),
     (2, 0, ('kk', 'io'), 1, True), (2, 0, ('bkbkk', 'iioio'), 1, True), (3, 0, ('kkkk', 'iooi'), 1, True),
+    (2, [3], 'esa', 1, True), (2, [4], 'se', 1, True),          # multi-qubit pseudomode registers: Y rotations, resets
 ]
 
 
+@pytest.mark.parametrize('picture', ['planned', 'heisenberg'])
 @pytest.mark.parametrize('case', SPECTRO_CASES, ids=[str(i) for i in range(len(SPECTRO_CASES))])
-def test_qspectroscopy_random(engine, case):
+def test_qspectroscopy_random(engine, case, picture, monkeypatch):
+    if picture == 'heisenberg':                     # read-out propagated with the transposed step, whatever the size
+        monkeypatch.setenv('QSX_HEISENBERG_MIN', '1')
+        monkeypatch.setenv('QSX_HEISENBERG_ALWAYS', '1')
+        monkeypatch.setenv('QSX_DISABLE_RR', '1')
     n, modes, label, tn, with_rates = case
     rng = np.random.default_rng(zlib.crc32(repr(case).encode()))
-    system = random_system(rng, n, modes, ring=True)
+    levels = modes if isinstance(modes, list) else None
+    modes = len(levels) if levels else modes
+    system = random_system(rng, n, modes, levels, ring=True)
     dt = float(rng.uniform(0.2, 1.0))
     n_delays = (len(label[0]) - 1) if isinstance(label, tuple) else (1 if label == 'a' else 3)
     delays = [[int(s) * dt for s in rng.integers(0, 5, size=rng.integers(1, 4))] for _ in range(n_delays)]
