@@ -1,8 +1,10 @@
-"""Run the C2 kernel a few times in one configuration (for ncu): python tools/run_c2_once.py rr 4 | passes 8 1"""
+"""Run the C2 kernel a few times in one configuration (for ncu): python tools/run_c2_once.py rr 4 | passes 8 1
+(QSX_C2_SETS=65536 runs a batch other than BASELINE's 4096 parameter sets)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from bench import c2_parameters, DT, N_SETS, N_STEPS
+N_SETS = int(os.environ.get('QSX_C2_SETS', N_SETS))
 from qsextra_b200.engine.program import StepProgram, SystemBatch
 from qsextra_b200.engine.runtime import get_engine
 from qsextra_b200.engine.sectors import population_observables
