@@ -174,8 +174,14 @@ def response_function_set(program: StepProgram, mu, sequences, step_counts, engi
         got = _propagate_readout(eng, program, mu, last_block, chains, uniq[-1], continuous, index)
         if got is not None:
             shared[key] = got
-    return [response_function(program, mu, side_seq, direction_seq, step_counts, engine=eng,
-                              device_output=device_output, shared=shared) for side_seq, direction_seq in sequences]
+    # every diagram is enqueued before any result is read back: one synchronisation at the end instead of one per diagram
+    on_gpu = eng.device.type == 'cuda'
+    signals = [response_function(program, mu, side_seq, direction_seq, step_counts, engine=eng,
+                                 device_output=device_output or on_gpu, shared=shared)
+               for side_seq, direction_seq in sequences]
+    if device_output or not on_gpu:
+        return signals
+    return [eng.to_host(signal) for signal in signals]
 
 
 def response_function(program: StepProgram, mu, side_seq: str, direction_seq: str, step_counts, engine=None,
@@ -297,7 +303,7 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
             if len(inv) != table.shape[axis] or np.any(inv != np.arange(len(inv))):
                 table = table.index_select(axis, torch.as_tensor(inv, device=eng.device))
         return table.reshape(shape).contiguous()
-    table = out.cpu().numpy().reshape([len(u) for u in uniq])
+    table = (eng.to_host(out) if hasattr(eng, 'to_host') else out.cpu().numpy()).reshape([len(u) for u in uniq])
     if all(len(inv) == len(u) and np.array_equal(inv, np.arange(len(inv))) for inv, u in zip(inverse, uniq)):
         return table                                    # delays were ascending and distinct: nothing to reorder
     return table[np.ix_(*inverse)].reshape(shape)

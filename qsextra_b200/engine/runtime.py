@@ -45,6 +45,7 @@ class Engine:
         self._blocks: dict[Block, DeviceBlock] = {}
         self._recipes: dict = {}              # device copies of parameter recipes, by content
         self._side_stream = None
+        self._staging = None                  # pinned read-back buffer (to_host)
         self.aux_launches = 0                 # table-assembly kernels (qsx_bind_params, qsx_rr_tables)
         self.launches = 0                     # kernels enqueued through this engine (bench bookkeeping)
         self.h2d_bytes = 0                    # bytes copied host -> device through to_device()
@@ -74,6 +75,18 @@ class Engine:
         if db is None:
             db = self._blocks[block] = DeviceBlock(block, self.device)
         return db
+
+    def to_host(self, tensor: torch.Tensor) -> np.ndarray:
+        """Device tensor -> NumPy array through a pinned staging buffer kept by the engine (a pageable read-back of a
+        few MB costs milliseconds; the staged copy runs at PCIe speed and the final host copy at memory speed)."""
+        flat = tensor.contiguous().view(-1)
+        n_bytes = flat.numel() * flat.element_size()
+        if self._staging is None or self._staging.numel() < n_bytes:
+            self._staging = torch.empty(max(n_bytes, 1 << 20), dtype=torch.uint8).pin_memory()
+        stage = self._staging[:n_bytes].view(flat.dtype)
+        stage.copy_(flat, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return stage.numpy().reshape(tuple(tensor.shape)).copy()
 
     def to_device(self, array, dtype=None):
         t = torch.as_tensor(np.ascontiguousarray(array))

@@ -239,7 +239,7 @@ def run_populations(batch: SystemBatch, psi: np.ndarray, program: StepProgram, s
             if total is None:
                 total = torch.zeros((B, len(steps), width), dtype=torch.float64, device=eng.device)
             total[:, :, torch.as_tensor(cfgs, device=eng.device)] += out
-    return total if device_output else total.cpu().numpy()
+    return total if device_output else eng.to_host(total)
 
 
 def _program_for(system, dt, dt_trotter, Trotter_number, Trotter_order, coll_rates) -> StepProgram:
@@ -352,4 +352,7 @@ def qevolve_batch(systems, time, Trotter_number: int = 1, Trotter_order: int = 1
                           dt_trotter=dt_trotter)
     local = run_populations(sub, psi[lo:hi], program, steps, readout='populations', device_output=True)
     full = qdist.all_gather_rows(local, B) if size > 1 else local
-    return full if device_output else full.cpu().numpy()
+    if device_output:
+        return full
+    from ...engine.runtime import get_engine
+    return get_engine().to_host(full)
