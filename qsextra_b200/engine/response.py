@@ -245,8 +245,9 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
 
     ka = kb = 0
     block = program.block(0, 0)
-    sigma = torch.zeros((1, block.size), dtype=torch.complex128, device=eng.device)
-    sigma[0, 0] = 1.0                                   # |g><g|, pseudomodes and ancilla in |0>
+    ground = np.zeros((1, block.size), dtype=complex)
+    ground[0, 0] = 1.0                                  # |g><g|, pseudomodes and ancilla in |0>
+    sigma = eng.to_device(ground)
     n_global = 1                                        # instances across all ranks at the current level
     shard_units, rows_per_unit = 0, 1                   # units split over ranks, and rows each has grown into
     sharded = False
