@@ -218,22 +218,26 @@ def spectroscopy_extras(world, rank, barrier):
                         specs.append(extra)
                 for sp in specs:
                     qspectroscopy(system, sp, verbose=False, **kw)              # warm-up (module loads, caches)
-                barrier()
-                t0 = time.perf_counter()
-                sigs = [qspectroscopy(system, sp, verbose=False, **kw) for sp in specs]
-                barrier()
-                sec = time.perf_counter() - t0
+                def timed(run, repeats=3):
+                    """Median wall-clock of ``repeats`` evaluations (each between barriers) and the last result."""
+                    samples, result = [], None
+                    for _ in range(repeats):
+                        barrier()
+                        t_start = time.perf_counter()
+                        result = run()
+                        barrier()
+                        samples.append(time.perf_counter() - t_start)
+                    return sorted(samples)[len(samples) // 2], samples, result
+
+                sec, samples, sigs = timed(lambda: [qspectroscopy(system, sp, verbose=False, **kw) for sp in specs])
                 points = len(specs) * int(np.prod([len(d) for d in delays]))
                 out[name] = dict(grid_points=points, seconds=sec, grid_points_per_s=points / sec, warmup_runs=1,
-                                 checksum=float(sum(np.abs(s_).sum() for s_ in sigs)))
+                                 samples_s=samples, checksum=float(sum(np.abs(s_).sum() for s_ in sigs)))
                 # the same diagrams through qspectroscopy_set: common delay levels once, every read-out propagation
                 # enqueued up front (nothing of the runs above is reused: the sharing lives inside the call)
-                barrier()
-                t0 = time.perf_counter()
-                sigs = qspectroscopy_set(system, specs, verbose=False, **kw)
-                barrier()
-                sec = time.perf_counter() - t0
+                sec, samples, sigs = timed(lambda: qspectroscopy_set(system, specs, verbose=False, **kw))
                 out[name]['as_one_set'] = dict(seconds=sec, grid_points_per_s=points / sec, api='qspectroscopy_set',
+                                               samples_s=samples,
                                                checksum=float(sum(np.abs(s_).sum() for s_ in sigs)))
                 if name.startswith('C4'):
                     # the full 2-D spectra (every t2 slice, pad_extension 3) with the signal kept on the device from
