@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .program import Damp, Reset, _Diag, _Hop, _Prot
+from .program import Damp, _Diag, _Hop, _Prot
 from .sectors import Block, sector_rank
 
 PASS_CFG, PASS_MODE, PASS_OP = 0, 1, 2

@@ -141,7 +141,6 @@ def clevolve(system: ChromophoreSystem | ExcitonicSystem,
         if len(rates) != len(system.mode_dict['omega_mode']):
             raise ValueError('The number of dephasing rates is different from the number of pseudomodes per chromophore.')
 
-    import torch
     from ...engine.runtime import get_engine
     eng = get_engine()
     program = LindbladProgram.from_system(system, rates)

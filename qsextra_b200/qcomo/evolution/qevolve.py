@@ -28,7 +28,7 @@ from ...engine import dist as qdist
 from ...engine.cabi import RR_MAX_OBS
 from ...engine.program import StepProgram, SystemBatch, resolve_time_grid
 from ...engine.rr import eligible as rr_eligible
-from ...engine.sectors import population_observables, sector_configs, split_state_by_sector
+from ...engine.sectors import population_observables, sector_configs
 
 
 @dataclass

@@ -1,7 +1,6 @@
 """Pin the oracle: its restatement of the reference's circuit construction must reproduce, to rounding, the
 fixtures written by the UNMODIFIED reference running over oracle/refshim (tests/golden/make_golden.py), plus the
 notebook known-answers listed in SURVEY.md section 4."""
-import json
 
 import numpy as np
 import pytest
