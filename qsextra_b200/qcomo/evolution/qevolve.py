@@ -216,6 +216,8 @@ def run_populations(batch: SystemBatch, psi: np.ndarray, program: StepProgram, s
     same_state = B > 1 and not np.any(psi != psi[0])                   # one initial block shared by every instance
     inst_src = torch.zeros(B, dtype=torch.int32, device=eng.device) if same_state else None
     for k in sectors:
+        if readout == 'populations' and k == 0:
+            continue                                  # nothing is excited in the ground-state block: no population
         block = program.block(k, k)
         # the pass tables are only needed when the register-resident kernel cannot serve the block or the read-outs
         try_rr = rr_eligible(program, block) and width <= RR_MAX_OBS and not os.environ.get('QSX_DISABLE_RR')
@@ -239,6 +241,8 @@ def run_populations(batch: SystemBatch, psi: np.ndarray, program: StepProgram, s
             if total is None:
                 total = torch.zeros((B, len(steps), width), dtype=torch.float64, device=eng.device)
             total[:, :, torch.as_tensor(cfgs, device=eng.device)] += out
+    if total is None:                                 # only the ground state is populated
+        total = torch.zeros((B, len(steps), width), dtype=torch.float64, device=eng.device)
     return total if device_output else eng.to_host(total)
 
 

@@ -217,3 +217,31 @@ def test_diagrams_of_one_spectrum_share_their_common_levels(engine):
         assert np.array_equal(alone[lab], got), lab
     with pytest.raises(ValueError, match='same delay_time'):
         qspectroscopy_set(s, [FeynmanDiagram('gsb', delays), FeynmanDiagram('se', [delays[0], delays[1], delays[2][:-1]])], **kw)
+
+
+def test_batch_with_different_initial_states_equals_single_runs(engine):
+    """qevolve_batch over systems that differ in parameters AND in their (multi-sector) initial states."""
+    from qsextra_b200 import ExcitonicSystem
+    rng = np.random.default_rng(33)
+    systems = []
+    for b in range(5):
+        j01, j12 = rng.uniform(-.2, .2, 2)
+        s = ExcitonicSystem(energies=rng.uniform(1.3, 1.7, 3).tolist(),
+                            couplings=[[0, j01, 0], [j01, 0, j12], [0, j12, 0]], dipole_moments=[1., 1., 1.])
+        c = rng.normal(size=8) + 1j * rng.normal(size=8)
+        s.set_state('state', (c / np.linalg.norm(c)).tolist())
+        systems.append(s)
+    dt = 0.2
+    time = np.arange(0, 9, 2) * dt
+    rates = rng.uniform(0.05, 0.3, 5)
+    pops = qevolve_batch(systems, time, dt=dt, coll_rates=rates)
+    assert pops.shape == (5, 5, 3)
+    for b, s in enumerate(systems):
+        single = qevolve(s, time, shots=0, dt=dt, coll_rates=float(rates[b]), verbose=False)
+        close(pops[b], single.populations)
+        ref = R.qevolve_exact(s, time, dt=dt, coll_rates=float(rates[b]))
+        close(single.populations, ref['populations'])
+    # a batch that never leaves the ground state
+    for s in systems:
+        s.set_state('ground')
+    assert not np.any(qevolve_batch(systems, time, dt=dt, coll_rates=rates))
