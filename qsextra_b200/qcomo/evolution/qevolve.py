@@ -212,6 +212,9 @@ def run_populations(batch: SystemBatch, psi: np.ndarray, program: StepProgram, s
     total = None
     emit = eng.to_device(steps, torch.int32)
     inst_set = torch.arange(B, dtype=torch.int32, device=eng.device) if B > 1 else None
+    if B == 0:                                        # a rank without parameter sets (more ranks than sets)
+        empty = torch.zeros((0, len(steps), width), dtype=torch.float64, device=eng.device)
+        return empty if device_output else empty.cpu().numpy()
     sectors = [k for k in range(n + 1) if np.any(psi[:, np.array(sector_configs(n, k), dtype=np.int64)] != 0)]
     same_state = B > 1 and not np.any(psi != psi[0])                   # one initial block shared by every instance
     inst_src = torch.zeros(B, dtype=torch.int32, device=eng.device) if same_state else None

@@ -50,7 +50,7 @@ EVOLVE_CASES = [  # (n, modes, levels, state kind, Trotter number, Trotter order
     (2, 1, None, 'general', 1, 1, True), (2, 1, None, 'localized', 3, 1, True), (2, 2, None, 'general', 1, 1, True),
     (3, 1, None, 'general', 1, 1, True), (2, 1, [3], 'localized', 1, 1, True), (2, 1, [4], 'delocalized', 1, 2, True),
     (2, 2, [2, 3], 'localized', 1, 1, True), (3, 1, None, 'delocalized', 2, 2, False), (4, 1, None, 'localized', 1, 1, True),
-    (1, 1, [4], 'localized', 1, 1, True),
+    (1, 1, [4], 'localized', 1, 1, True), (8, 0, None, 'delocalized', 1, 1, True), (7, 0, None, 'general', 1, 1, True),
 ]
 
 
@@ -81,6 +81,7 @@ SPECTRO_CASES = [  # (n, modes, label or (side, direction), Trotter number, with
     (2, 1, 'esa', 1, True), (2, 1, ('kbkk', 'iiio'), 1, True), (2, 2, 'se', 1, True), (3, 1, 'gsb', 1, True),
     (2, 0, ('kk', 'io'), 1, True), (2, 0, ('bkbkk', 'iioio'), 1, True), (3, 0, ('kkkk', 'iooi'), 1, True),
     (2, [3], 'esa', 1, True), (2, [4], 'se', 1, True),          # multi-qubit pseudomode registers: Y rotations, resets
+    (6, 0, 'esa', 1, True), (5, 0, ('kbkk', 'iiio'), 1, True),  # larger aggregates: 15 x 6 and 10 x 5 configuration blocks
 ]
 
 
