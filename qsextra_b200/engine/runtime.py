@@ -417,7 +417,7 @@ class Engine:
         return out_obs, out_snap
 
     def rotating_frame(self, signal: torch.Tensor, t1: torch.Tensor, t3, t2_index: int, pad: int, rf_freq: float,
-                       damping: float):
+                       damping: float, out: torch.Tensor | None = None):
         """Rotating frame x damping x zero padding (postprocessing.py:9-37, :57, :77).  ``signal`` complex128 [n1]
         (linear, ``t3`` None) or [n1, n2, n3]; returns [n1*pad] or [n1*pad, n3*pad]."""
         assert signal.dtype == torch.complex128 and signal.is_contiguous() and signal.dim() in (1, 3)
@@ -430,7 +430,9 @@ class Engine:
         args.t1 = t1.data_ptr()
         args.t3 = None if linear else t3.data_ptr()
         shape = (args.n1 * pad,) if linear else (args.n1 * pad, args.n3 * pad)
-        out = torch.empty(shape, dtype=torch.complex128, device=self.device)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.complex128, device=self.device)
+        assert tuple(out.shape) == shape and out.dtype == torch.complex128 and out.is_contiguous()
         args.signal, args.out = signal.data_ptr(), out.data_ptr()
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -439,11 +441,13 @@ class Engine:
             self.launches += 1
         return out
 
-    def spectrum_shift(self, data: torch.Tensor, s1: int, s3: int, scale: float):
+    def spectrum_shift(self, data: torch.Tensor, s1: int, s3: int, scale: float, out: torch.Tensor | None = None):
         """out[i, j] = scale * data[(i + s1) % m1, (j + s3) % m3]  (fftshift / ifftshift + prefactor in one pass)."""
         assert data.dtype == torch.complex128 and data.is_contiguous() and data.dim() in (1, 2)
         m1, m3 = (data.shape[0], 1) if data.dim() == 1 else data.shape
-        out = torch.empty_like(data)
+        if out is None:
+            out = torch.empty_like(data)
+        assert out.shape == data.shape and out.dtype == data.dtype and out.is_contiguous() and out.data_ptr() != data.data_ptr()
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             cabi.check(self.lib.qsx_spectrum_shift(C.c_void_p(data.data_ptr()), C.c_void_p(out.data_ptr()), m1, m3,

@@ -105,3 +105,29 @@ def postprocessing(spectroscopy: Spectroscopy, signal, RF_freq: float = 0, dampi
     padded = _frame(dev, dev.signal, delay_time, RF_freq, damping_rate, T2_index, pad_extension)
     omega, spectrum = _transform(dev, padded, delay_time, RF_freq, pad_extension)
     return omega, dev.give(spectrum)
+
+
+def postprocessing_all_T2(spectroscopy: Spectroscopy, signal, RF_freq: float = 0, damping_rate: float = 0,
+                          pad_extension: int = 1):
+    """Every T2 slice of a third-order signal at once (an addition to the reference API, which takes one ``T2_index``
+    per call): (omega, spectra [n2, n1 * pad, n3 * pad]); ``spectra[k]`` equals ``postprocessing(..., T2_index=k)[1]``.
+    The frame/padding and shift passes run per slice into one buffer, the transforms are two batched cuFFT calls."""
+    delay_time = spectroscopy.delay_time
+    if len(delay_time) != 3:
+        raise ValueError('postprocessing_all_T2 needs a third-order signal (three delay lists)')
+    dev = _Device(signal)
+    t1, t2, t3 = delay_time
+    n1, n2, n3 = len(t1), len(t2), len(t3)
+    m1, m3 = n1 * pad_extension, n3 * pad_extension
+    torch = dev.torch
+    ax1, ax3 = dev.axis(t1), dev.axis(t3)
+    padded = torch.empty((n2, m1, m3), dtype=torch.complex128, device=dev.engine.device)
+    for k in range(n2):
+        dev.engine.rotating_frame(dev.signal, ax1, ax3, k, pad_extension, RF_freq, damping_rate, out=padded[k])
+    both = torch.fft.ifft(torch.fft.fft(padded, dim=1), dim=2).contiguous()
+    spectra = padded                                            # the padded buffer is free again: reuse it for the result
+    for k in range(n2):
+        dev.engine.spectrum_shift(both[k], m1 - m1 // 2, m3 - m3 // 2, m1 / n1 ** 2, out=spectra[k])
+    omega1 = _fft_axis(n1, pad_extension, t1[1] - t1[0], RF_freq)
+    omega3 = _fft_axis(n3, pad_extension, t3[1] - t3[0], RF_freq)
+    return list(np.meshgrid(omega1, omega3, indexing='ij')), dev.give(spectra)

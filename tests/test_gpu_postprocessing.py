@@ -99,3 +99,21 @@ def test_signal_stays_on_the_device_from_simulation_to_spectrum(engine):
     omega, spec = postprocessing(diagram, dev, RF_freq=1.5, damping_rate=0.03, pad_extension=2, T2_index=2)
     w_want, s_want = oracle_pp.postprocessing(diagram, host, RF_freq=1.5, damping_rate=0.03, pad_extension=2, T2_index=2)
     assert spec.is_cuda and close(spec.cpu().numpy(), s_want)
+
+
+def test_all_t2_slices_at_once(engine):
+    from qsextra_b200.spectroscopy.postprocessing import postprocessing_all_T2
+    rng = np.random.default_rng(4)
+    n1, n2, n3, pad = 12, 5, 9, 3
+    sig = rng.normal(size=(n1, n2, n3)) + 1j * rng.normal(size=(n1, n2, n3))
+    delays = [np.arange(n1) * 0.7, np.arange(n2) * 5.0, np.arange(n3) * 1.3]
+    spec = FeynmanDiagram('gsb', delays)
+    omega, spectra = postprocessing_all_T2(spec, sig, 1.4, 0.02, pad)
+    assert spectra.shape == (n2, n1 * pad, n3 * pad)
+    for k in range(n2):
+        w, one = postprocessing(spec, sig, 1.4, 0.02, pad, k)
+        assert np.array_equal(spectra[k], one) and all(np.array_equal(a, b) for a, b in zip(omega, w))
+    dev_spectra = postprocessing_all_T2(spec, torch.as_tensor(sig, device='cuda'), 1.4, 0.02, pad)[1]
+    assert dev_spectra.is_cuda and np.array_equal(dev_spectra.cpu().numpy(), spectra)
+    with pytest.raises(ValueError):
+        postprocessing_all_T2(FeynmanDiagram('a', delays[0]), sig[:, 0, 0])
