@@ -7,6 +7,9 @@ circuits.py        restatement of the reference's circuit construction (qevolve.
 densesim.py        dense density-matrix simulator (exact expectation values of those gate lists)
 reference_path.py  qevolve_exact, qspectroscopy_literal (circuit by circuit), qspectroscopy_operator (collective form)
 csrc/ + fast.py    the same literal gate application in plain C + OpenMP (CPU baseline / ``bench.py --impl reference``)
+postprocessing.py  NumPy/SciPy restatement of the reference's post-processing (spectroscopy/postprocessing.py:9-122)
+lindblad.py        dense full-space master equation with the reference's operators (clevolve.py, clspectroscopy.py),
+                   exact propagator exp(Lt) instead of QuTiP's ODE solver
 refshim/           stand-ins for qiskit / qiskit_aer / qutip, used ONLY by tests/golden/make_golden.py to run the
                    UNMODIFIED reference code and write tests/golden/*.npz
 
