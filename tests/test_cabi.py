@@ -29,15 +29,22 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header(tmp_path):
-    """Compile a tiny C program against include/qsx.h and compare sizeof() with the ctypes mirrors."""
+    """Compile a tiny C program against include/qsx.h and compare sizeof() and the offset of the last field of every
+    struct with the ctypes mirrors."""
+    pairs = [('qsx_op', cabi.QsxOp, 'flags'), ('qsx_pass', cabi.QsxPass, 'f'), ('qsx_block', cabi.QsxBlock, 'rankB'),
+             ('qsx_evolve_args', cabi.QsxEvolveArgs, 'hops'), ('qsx_rr_op', cabi.QsxRROp, 'aux1'),
+             ('qsx_rr_args', cabi.QsxRRArgs, 'out_snap'), ('qsx_rrc_args', cabi.QsxRRCArgs, 'out_snap'),
+             ('qsx_rr_tables_args', cabi.QsxRRTablesArgs, 'out'), ('qsx_lindblad_args', cabi.QsxLindbladArgs, 'workspace'),
+             ('qsx_frame_args', cabi.QsxFrameArgs, 'out')]
+    body = ''.join('printf("%zu %zu\\n", sizeof({0}), offsetof({0}, {1}));'.format(c_name, last) for c_name, _, last in pairs)
     src = tmp_path / 'sizes.c'
-    src.write_text('#include <stdio.h>\n#include "qsx.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(qsx_op), '
-                   'sizeof(qsx_pass), sizeof(qsx_block), sizeof(qsx_evolve_args)); return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "qsx.h"\nint main(){' + body + ' return 0;}\n')
     exe = tmp_path / 'sizes'
     subprocess.check_call(['gcc', '-I', os.path.join(REPO, 'include'), str(src), '-o', str(exe)])
-    sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
-    assert sizes == [ctypes.sizeof(cabi.QsxOp), ctypes.sizeof(cabi.QsxPass), ctypes.sizeof(cabi.QsxBlock),
-                     ctypes.sizeof(cabi.QsxEvolveArgs)]
+    rows = [[int(v) for v in line.split()] for line in subprocess.check_output([str(exe)]).decode().splitlines()]
+    for (c_name, mirror, last), (size, offset) in zip(pairs, rows):
+        assert ctypes.sizeof(mirror) == size, c_name
+        assert getattr(mirror, last).offset == offset, (c_name, last)
 
 
 def test_invalid_arguments_fail_loudly_without_a_device():
