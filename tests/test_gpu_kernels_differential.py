@@ -28,6 +28,16 @@ def chain(n, modes=True, levels=2, w=1, J=-0.3, g=0.7):
     return build_system(sd)
 
 
+def ring(n):
+    """All-to-all coupled aggregate with one 2-level pseudomode per site."""
+    coup = np.zeros((n, n))
+    for i in range(n):
+        for j in range(i + 1, n):
+            coup[i, j] = coup[j, i] = -0.2 / (1 + j - i)
+    return build_system(dict(energies=(1.5 + 0.07 * np.arange(n)).tolist(), couplings=coup.tolist(), dipole_moments=[1.] * n,
+                             frequencies_pseudomode=[0.3], levels_pseudomode=[2], couplings_ep=[0.7]))
+
+
 CASES = [
     ('dimer_modes', chain(2), dict(coll_rates=[0.5]), [(1, 1), (1, 0), (2, 1), (0, 0)]),
     ('dimer_markov', chain(2, modes=False), dict(coll_rates=0.2), [(1, 1), (1, 0), (2, 1)]),
@@ -37,6 +47,9 @@ CASES = [
     ('trimer_markov_trotter2', chain(3, modes=False), dict(coll_rates=0.2, Trotter_number=2), [(1, 1), (2, 1)]),
     ('chain4_modes', chain(4), dict(coll_rates=[0.5]), [(2, 1), (1, 1), (0, 1)]),
     ('chain4_suzuki2', chain(4, modes=False), dict(coll_rates=0.1, Trotter_order=2), [(1, 1), (2, 2)]),
+    # couplings outside the compile-time menus of the CTA-wide kernel: it must hand over to the pass program
+    ('trimer_ring_modes', ring(3), dict(coll_rates=[0.5]), [(1, 1), (2, 1)]),
+    ('tetramer_ring_modes', ring(4), dict(coll_rates=[0.5]), [(1, 1), (1, 0)]),
 ]
 
 
