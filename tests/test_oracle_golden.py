@@ -139,3 +139,49 @@ def test_collision_model_converges_to_lindblad_with_dt():
         pops = R.qevolve_exact(system, t, dt=dt, coll_rates=0.1)['populations']
         gaps.append(np.abs(pops - cl['populations']).max())
     assert 0.4 * gaps[0] < gaps[1] < 0.6 * gaps[0] and gaps[1] < 5e-3        # first order in dt
+
+
+def _golden_response_in_c(name, kraus):
+    """Signal of a qspectroscopy golden through the C restatement (oracle/csrc: qsxo_response_chains)."""
+    import itertools
+    meta, arrays = load_golden(name)
+    kw = dict(meta['kwargs'])
+    if kw.get('Trotter_order', 1) != 1 and kraus:
+        pytest.skip('Suzuki splitting of the collision gates has no two-gate pattern')
+    system = build_system(meta['system'])
+    spec = build_spectroscopy(meta['label'], meta['delay_time'])
+    shape = [len(d) for d in spec.delay_time]
+    rows = list(itertools.product(*[range(n) for n in shape[:-1]]))
+    dt = kw.pop('dt')
+    got, _ = fast.response_points(system, spec, rows, dt, kraus=kraus, **kw)
+    return got.reshape(shape), arrays['signal']
+
+
+@pytest.mark.parametrize('name', golden_names('qspectroscopy_'))
+def test_c_response_chains_match_reference_goldens(name):
+    """The C port used for far delay-grid points (bench.py cpu_baseline, tests/test_gpu_full_size.py) reproduces every
+    spectroscopy fixture written by the unmodified reference, with literal collision gates + ancilla reset."""
+    got, want = _golden_response_in_c(name, kraus=False)
+    assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize('name', golden_names('qspectroscopy_'))
+def test_c_response_chains_kraus_form_match_reference_goldens(name):
+    """... and with every collision replaced by the channel it induces once the ancilla is traced out (state without
+    the ancilla qubit: what makes the 5 000-step corners of BASELINE configs[3] affordable on the CPU)."""
+    got, want = _golden_response_in_c(name, kraus=True)
+    assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max())
+
+
+def test_kraus_form_rewrites_only_collision_patterns():
+    system = build_system(dict(energies=[1., 1.1], couplings=0.1, dipole_moments=[1., 1.], frequencies_pseudomode=[0.1],
+                               levels_pseudomode=[4], couplings_ep=[0.05]))
+    layout = C.Layout(system, True)
+    ops = C.step_ops(system, layout, 0.1, 0.1, 1, 1, [0.2])
+    assert fast.kraus_form(ops, layout) is None                 # d = 4 collisions are not the two-gate pattern
+    dimer = build_system(dict(energies=[1., 1.1], couplings=0.1, dipole_moments=[1., 1.]))
+    layout = C.Layout(dimer, True)
+    ops = fast.kraus_form(C.step_ops(dimer, layout, 0.1, 0.1, 1, 1, 0.3), layout)
+    assert [op[0] for op in ops[-2:]] == ['dephase', 'dephase']
+    assert all(len(op[1]) == layout.n_qubits - 1 for op in ops if op[0] == 'rot')
+    assert abs(ops[-1][2] - np.sqrt(0.3 * 0.1)) < 1e-15
