@@ -35,13 +35,14 @@
 extern "C" {
 #endif
 
-#define QSX_ABI_VERSION 16
+#define QSX_ABI_VERSION 17
 
 enum {
     QSX_OK = 0,
     QSX_ERR_INVALID = -1,   /* bad argument (message in qsx_last_error) */
     QSX_ERR_CUDA = -2,      /* CUDA runtime error */
-    QSX_ERR_TOO_LARGE = -3  /* block does not fit shared memory and no workspace was given */
+    QSX_ERR_TOO_LARGE = -3, /* block does not fit shared memory and no workspace was given */
+    QSX_ERR_NO_PROGRAM = -4 /* qsx_evolve_rrc: no compile-time program has this signature (use qsx_evolve) */
 };
 
 /* Operation codes (qsx_op.type).  Angles live in the per-parameter-set table `params` at slot `p`. */
@@ -125,7 +126,9 @@ typedef struct qsx_evolve_args {
     const double* sigma_in;     /* DEVICE [n_src][DA*DB] complex128 interleaved */
     int32_t n_steps;
     int32_t n_emit;
-    const int32_t* emit_steps;  /* DEVICE [n_emit] strictly increasing step counts in [0, n_steps] */
+    const int32_t* emit_steps;  /* DEVICE [n_emit] strictly increasing step counts in [0, n_steps]: a PRECONDITION the
+                                 * library cannot check without a device read-back (the Python binding asserts it on the
+                                 * host array); entries out of order leave their output slots untouched */
     int32_t n_obs;              /* read-outs: out_obs[inst][emit][o] = sum_k obs_w[k] * sigma[obs_idx[k]] */
     const int32_t* obs_ptr;     /* DEVICE [n_obs+1] CSR offsets */
     const int32_t* obs_idx;     /* DEVICE element indices a*DB+b */
@@ -216,7 +219,7 @@ int32_t qsx_evolve_rr(const qsx_rr_args* args, void* stream);
  * j < nB, of ONE pair of pseudomode states for the whole evolution; pseudomode rotations and damping exchange with the
  * thread whose pair differs in one bit (pair), by warp shuffle or through a shared-memory buffer.  Only programs whose
  * `signature` (engine/rrc.py: RRCProgram.signature) equals a compile-time entry of csrc/qsx_rrc_programs.inc can run;
- * the call returns QSX_ERR_INVALID with "no compile-time program" otherwise and the caller uses qsx_evolve.
+ * the call returns QSX_ERR_NO_PROGRAM otherwise and the caller uses qsx_evolve.
  * Parameter set: Wcfg (nA*nB complex) | gmA (2^n_bits complex) | gmB (2^n_bits complex) | op parameters. */
 typedef struct qsx_rrc_args {
     int32_t n_signature;
@@ -311,6 +314,12 @@ int32_t qsx_rr_tables(const qsx_rr_tables_args* args, void* stream);
 int64_t qsx_readout_gemm_workspace_bytes(int32_t n_inst, int32_t n_emit, int32_t n_elem);
 int32_t qsx_readout_gemm(int32_t n_inst, int32_t n_emit, int32_t n_elem, const double* sigma, const double* readout,
                          double* out, double* workspace, void* stream);
+/* The same for `n_batch` independent products in one launch -- the parameter sets of an ensemble (static-disorder
+ * realisations of one aggregate), each with its own propagated read-outs:
+ * sigma [n_batch][n_inst][E], readout [n_batch][n_emit][E], out [n_batch][n_inst][n_emit]. */
+int64_t qsx_readout_gemm_batched_workspace_bytes(int32_t n_batch, int32_t n_inst, int32_t n_emit, int32_t n_elem);
+int32_t qsx_readout_gemm_batched(int32_t n_batch, int32_t n_inst, int32_t n_emit, int32_t n_elem, const double* sigma,
+                                 const double* readout, double* out, double* workspace, void* stream);
 
 /* Lindblad limit of the collision model -- replaces the QuTiP solver calls of the comparison path
  * (qsextra/qcomo/evolution/clevolve.py:27-46 and :88-107: sesolve / mesolve(H, state, time, c_ops, e_ops)).

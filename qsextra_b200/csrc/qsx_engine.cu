@@ -840,16 +840,21 @@ constexpr int RG_TM = 32, RG_TN = 64, RG_TK = 16;
 // blockIdx.z selects a k-range of k_chunk elements (split-K: the output is small, 2048 x 128 for C4, so splitting the
 // 6144-long sums is what fills the GPU); partial sums go to C + z * M * N and reduce_splits_kernel adds them in a fixed
 // order (deterministic).
-static __global__ void __launch_bounds__(128) readout_gemm_kernel(int M, int N, int K, int k_chunk,
-                                                                  const double2* __restrict__ A,
+// blockIdx.y = batch * m_tiles + m-tile: `n_batch` independent products (one per parameter set of an ensemble) with
+// A [n_batch][M][K], B [n_batch][N][K], C [n_batch][M][N] (C of split z at offset z * n_batch * M * N).
+static __global__ void __launch_bounds__(128) readout_gemm_kernel(int M, int N, int K, int k_chunk, int m_tiles,
+                                                                  int n_batch, const double2* __restrict__ A,
                                                                   const double2* __restrict__ B, double2* __restrict__ C) {
     __shared__ double2 As[RG_TK][RG_TM + 1];
     __shared__ double2 Bs[RG_TK][RG_TN + 1];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * RG_TM, n0 = blockIdx.x * RG_TN;
+    const int batch = blockIdx.y / m_tiles;
+    const int m0 = (blockIdx.y % m_tiles) * RG_TM, n0 = blockIdx.x * RG_TN;
     const int k_begin = blockIdx.z * k_chunk;
     const int k_end = min(K, k_begin + k_chunk);
-    C += (size_t)blockIdx.z * M * N;
+    A += (size_t)batch * M * K;
+    B += (size_t)batch * N * K;
+    C += ((size_t)blockIdx.z * n_batch + batch) * M * N;
     double2 acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -1194,7 +1199,7 @@ int32_t qsx_evolve_rrc(const qsx_rrc_args* a, void* stream) {
     int32_t rc = device_limits(&sms, &smem_max);
     if (rc) return rc;
     int r = rrc::launch<0>(*a, sms, smem_max, (cudaStream_t)stream);
-    if (r == 1) return fail(QSX_ERR_INVALID, "no compile-time program matches this block%s");
+    if (r == 1) return fail(QSX_ERR_NO_PROGRAM, "no compile-time program matches this block%s");
     if (r < 0) return fail(QSX_ERR_CUDA, "CUDA error: %s", cudaGetErrorString((cudaError_t)(-r)));
     return QSX_OK;
 }
@@ -1206,34 +1211,44 @@ static int readout_splits(int n_inst, int n_emit, int n_elem, int sms) {
     return splits;
 }
 
-int64_t qsx_readout_gemm_workspace_bytes(int32_t n_inst, int32_t n_emit, int32_t n_elem) {
-    if (n_inst < 0 || n_emit < 0 || n_elem < 0) return fail(QSX_ERR_INVALID, "bad sizes%s");
+int64_t qsx_readout_gemm_batched_workspace_bytes(int32_t n_batch, int32_t n_inst, int32_t n_emit, int32_t n_elem) {
+    if (n_batch < 0 || n_inst < 0 || n_emit < 0 || n_elem < 0) return fail(QSX_ERR_INVALID, "bad sizes%s");
     int sms = 0, smem_max = 0;
     int32_t rc = device_limits(&sms, &smem_max);
     if (rc) return rc;
-    const int splits = readout_splits(n_inst, n_emit, n_elem, sms);
-    return splits > 1 ? (int64_t)splits * n_inst * n_emit * (int64_t)sizeof(double2) : 0;
+    const int splits = readout_splits(n_batch * n_inst, n_emit, n_elem, sms);
+    return splits > 1 ? (int64_t)splits * n_batch * n_inst * n_emit * (int64_t)sizeof(double2) : 0;
+}
+
+int64_t qsx_readout_gemm_workspace_bytes(int32_t n_inst, int32_t n_emit, int32_t n_elem) {
+    return qsx_readout_gemm_batched_workspace_bytes(1, n_inst, n_emit, n_elem);
 }
 
 int32_t qsx_readout_gemm(int32_t n_inst, int32_t n_emit, int32_t n_elem, const double* sigma, const double* readout,
                          double* out, double* workspace, void* stream) {
-    if (n_inst < 0 || n_emit < 0 || n_elem < 0) return fail(QSX_ERR_INVALID, "bad sizes%s");
-    if (n_inst == 0 || n_emit == 0) return QSX_OK;
+    return qsx_readout_gemm_batched(1, n_inst, n_emit, n_elem, sigma, readout, out, workspace, stream);
+}
+
+int32_t qsx_readout_gemm_batched(int32_t n_batch, int32_t n_inst, int32_t n_emit, int32_t n_elem, const double* sigma,
+                                 const double* readout, double* out, double* workspace, void* stream) {
+    if (n_batch < 0 || n_inst < 0 || n_emit < 0 || n_elem < 0) return fail(QSX_ERR_INVALID, "bad sizes%s");
+    if (n_batch == 0 || n_inst == 0 || n_emit == 0) return QSX_OK;
     if (!out || (n_elem > 0 && (!sigma || !readout))) return fail(QSX_ERR_INVALID, "null argument%s");
     int sms = 0, smem_max = 0;
     int32_t rc = device_limits(&sms, &smem_max);
     if (rc) return rc;
-    int splits = workspace ? readout_splits(n_inst, n_emit, n_elem, sms) : 1;     // without scratch: one pass, no split
-    dim3 grid((n_emit + RG_TN - 1) / RG_TN, (n_inst + RG_TM - 1) / RG_TM, splits);
-    if (grid.y > 65535u) return fail(QSX_ERR_INVALID, "more than 2097120 chains in one call%s");
+    int splits = workspace ? readout_splits(n_batch * n_inst, n_emit, n_elem, sms) : 1;   // without scratch: no split
+    const int m_tiles = (n_inst + RG_TM - 1) / RG_TM;
+    if ((long long)m_tiles * n_batch > 65535) return fail(QSX_ERR_INVALID, "more than 2097120 chains in one call%s");
+    dim3 grid((n_emit + RG_TN - 1) / RG_TN, m_tiles * n_batch, splits);
     int k_chunk = ((n_elem + splits - 1) / splits + RG_TK - 1) / RG_TK * RG_TK;
     if (k_chunk < RG_TK) k_chunk = RG_TK;
     double2* target = splits > 1 ? reinterpret_cast<double2*>(workspace) : reinterpret_cast<double2*>(out);
-    readout_gemm_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(n_inst, n_emit, n_elem, k_chunk,
+    readout_gemm_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(n_inst, n_emit, n_elem, k_chunk, m_tiles, n_batch,
                                                                  reinterpret_cast<const double2*>(sigma),
                                                                  reinterpret_cast<const double2*>(readout), target);
     if (splits > 1) {
-        const size_t n = (size_t)n_inst * n_emit;
+        const size_t n = (size_t)n_batch * n_inst * n_emit;
         size_t blocks = (n + 255) / 256;
         if (blocks > (size_t)sms * 8) blocks = (size_t)sms * 8;
         reduce_splits_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(n, splits, target, reinterpret_cast<double2*>(out));

@@ -43,6 +43,15 @@ struct Geo {
     static constexpr int NWB = 2 * NBITS > 5 ? 2 * NBITS - 5 : 0;       // warp bits
     static constexpr int NGROUP = NWB + 1;
     static constexpr int PAIRS = NWB > 0 ? 1 << (NWB - 1) : 1;
+    // The damping exchange synchronises the two warps that differ in the HIGHER thread bit of the (ket, bra) pair only:
+    // correct as long as the lower bit is a lane bit.  Named barriers 1 .. NWB * PAIRS must exist (16 per CTA).
+    static constexpr bool damping_pairs_ok() {
+        for (int q = 0; q < NBITS; ++q)
+            if ((BP::ket_pos[q] < BP::bra_pos[q] ? BP::ket_pos[q] : BP::bra_pos[q]) >= 5) return false;
+        return true;
+    }
+    static_assert(damping_pairs_ok(), "a pseudomode with both thread bits above the lanes needs a 4-warp barrier");
+    static_assert(1 + NWB * PAIRS <= 16, "named barrier ids exceed the 16 hardware barriers of a CTA");
     static constexpr size_t smem_bytes(int p_doubles) {
         return (size_t)2 * NGROUP * BUF * sizeof(double2) + (size_t)((p_doubles + 1) & ~1) * sizeof(double) +
                64 * sizeof(double2);

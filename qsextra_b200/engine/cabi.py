@@ -11,10 +11,12 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libqsx.so')
-ABI_VERSION = 16
+ABI_VERSION = 17
+ERR_NO_PROGRAM = -4
 
 EXPORTS = ('qsx_abi_version', 'qsx_last_error', 'qsx_device_info', 'qsx_evolve_workspace_bytes', 'qsx_evolve',
-           'qsx_evolve_rr', 'qsx_bind_params', 'qsx_rr_tables', 'qsx_evolve_rrc', 'qsx_rrc_find_program', 'qsx_apply_dipole', 'qsx_readout_gemm_workspace_bytes', 'qsx_readout_gemm', 'qsx_rotating_frame', 'qsx_spectrum_shift',
+           'qsx_evolve_rr', 'qsx_bind_params', 'qsx_rr_tables', 'qsx_evolve_rrc', 'qsx_rrc_find_program', 'qsx_apply_dipole', 'qsx_readout_gemm_workspace_bytes', 'qsx_readout_gemm',
+           'qsx_readout_gemm_batched_workspace_bytes', 'qsx_readout_gemm_batched', 'qsx_rotating_frame', 'qsx_spectrum_shift',
            'qsx_lindblad_workspace_bytes', 'qsx_lindblad_evolve',
            'qsx_fp64_peak')
 RR_MAX_OPS, RR_MAX_OBS, RR_MAX_ENTRIES = 24, 8, 4
@@ -139,6 +141,10 @@ def load():
     lib.qsx_readout_gemm_workspace_bytes.restype = C.c_int64
     lib.qsx_readout_gemm.argtypes = [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 5
     lib.qsx_readout_gemm.restype = C.c_int32
+    lib.qsx_readout_gemm_batched_workspace_bytes.argtypes = [C.c_int32] * 4
+    lib.qsx_readout_gemm_batched_workspace_bytes.restype = C.c_int64
+    lib.qsx_readout_gemm_batched.argtypes = [C.c_int32] * 4 + [C.c_void_p] * 5
+    lib.qsx_readout_gemm_batched.restype = C.c_int32
     lib.qsx_bind_params.argtypes = [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 7
     lib.qsx_bind_params.restype = C.c_int32
     lib.qsx_rr_tables.argtypes = [C.POINTER(QsxRRTablesArgs), C.c_void_p]

@@ -18,6 +18,12 @@ X/Y circuits, each re-evolved from t = 0.  Because everything is linear in sigma
 
 Independent chains are sharded over ranks at the first level that has enough of them; one all-gather assembles
 the signal.
+
+Ensembles.  A ``StepProgram`` bound to S > 1 parameter sets (static-disorder realisations of one aggregate: same
+structure, same dipole moments, different energies / couplings / bath parameters) is evaluated in ONE tree: level n
+holds S x (chains per set) instances, every instance carries the index of its parameter set (``inst_set``), each set
+propagates its own read-out and the last level is one batched product.  The sets are what is sharded over the ranks
+then (contiguous slices, one all-gather); the signal gets a leading axis of length S.
 """
 from __future__ import annotations
 
@@ -72,11 +78,17 @@ def _fingerprint(program) -> bytes:
     return b'S' + h.digest()
 
 
+def n_parameter_sets(program) -> int:
+    batch = getattr(program, 'batch', None)
+    return int(batch.batch) if batch is not None and hasattr(batch, 'batch') else 1
+
+
 def _last_level(program, plan, uniq, rank, size):
     """(block of the last delay or None if a sector is empty, chains this rank holds there) -- the bookkeeping of
     ``response_function`` without any propagation."""
     ka = kb = 0
-    n_global, local, sharded = 1, 1, False
+    n_sets = n_parameter_sets(program)
+    n_global, local, sharded = n_sets, n_sets, False
     block = None
     for level, (side, kind) in enumerate(plan[:-1]):
         delta = +1 if kind == 'X' or (kind == 'raise') == (side == 'k') else -1
@@ -84,7 +96,7 @@ def _last_level(program, plan, uniq, rank, size):
         block = Block(program.n_sites, program.n_bits, ka, kb)
         if not block.valid():
             return None, 0
-        if not sharded and size > 1 and n_global >= size:
+        if not sharded and size > 1 and (n_global >= size or n_sets > 1):
             lo, hi = qdist.shard_bounds(n_global, rank, size)
             local, sharded = hi - lo, True
         if level < len(plan) - 2:
@@ -96,7 +108,12 @@ def _last_level(program, plan, uniq, rank, size):
 def _propagate_readout(eng, program, mu, last_block, chains, emit, continuous, stream_index):
     """Enqueue the propagation of the emission read-out of ``last_block`` on a side stream, if the Heisenberg picture
     is planned for this level.  -> (read-outs [n_emit, E] on the device, completion event | None) or None."""
-    if (last_block is None or chains < int(os.environ.get('QSX_HEISENBERG_MIN', '8'))
+    n_sets = n_parameter_sets(program)
+    set_lo, set_hi = qdist.shard_bounds(n_sets, *qdist.world()) if n_sets > 1 else (0, 1)
+    local_sets = set_hi - set_lo
+    if local_sets == 0:
+        return None                                     # more ranks than parameter sets: nothing to do on this one
+    if (last_block is None or chains // local_sets < int(os.environ.get('QSX_HEISENBERG_MIN', '8'))
             or os.environ.get('QSX_DISABLE_HEISENBERG')):
         return None
     back = None
@@ -128,8 +145,13 @@ def _propagate_readout(eng, program, mu, last_block, chains, emit, continuous, s
             fast = (bool(os.environ.get('QSX_HEISENBERG_ALWAYS')) or
                     getattr(eng, 'has_static_rrc', lambda p: True)(dev_back))
             if fast or chains >= 4 * getattr(eng, 'sm_count', 1):
-                _, snap = eng.evolve(dev_back, start, 1, int(emit.max()), emit, snapshots=True)
-                readouts = snap[0]
+                if n_sets > 1:                          # one read-out per parameter set of this rank, same start
+                    sets = torch.arange(set_lo, set_hi, dtype=torch.int32, device=eng.device)
+                    _, readouts = eng.evolve(dev_back, start, local_sets, int(emit.max()), emit, snapshots=True,
+                                             inst_set=sets, inst_src=torch.zeros_like(sets))
+                else:
+                    _, snap = eng.evolve(dev_back, start, 1, int(emit.max()), emit, snapshots=True)
+                    readouts = snap[0]
     if readouts is None:
         return None
     ready = None
@@ -245,10 +267,14 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
 
     ka = kb = 0
     block = program.block(0, 0)
-    ground = np.zeros((1, block.size), dtype=complex)
-    ground[0, 0] = 1.0                                  # |g><g|, pseudomodes and ancilla in |0>
+    n_sets = n_parameter_sets(program)
+    if n_sets > 1 and continuous:
+        raise ValueError('ensembles are evaluated by the collision-model tree only')
+    ground = np.zeros((n_sets, block.size), dtype=complex)
+    ground[:, 0] = 1.0                                  # |g><g|, pseudomodes and ancilla in |0>
     sigma = eng.to_device(ground)
-    n_global = 1                                        # instances across all ranks at the current level
+    inst_set = torch.arange(n_sets, dtype=torch.int32, device=eng.device) if n_sets > 1 else None
+    n_global = n_sets                                   # instances across all ranks at the current level
     shard_units, rows_per_unit = 0, 1                   # units split over ranks, and rows each has grown into
     sharded = False
     zero = False
@@ -263,48 +289,72 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
             break
         last = level == len(plan) - 2
         if shared is not None and not last and prefix_key(level) in shared:
-            sigma, n_global, sharded, shard_units, rows_per_unit = shared[prefix_key(level)]
+            sigma, n_global, sharded, shard_units, rows_per_unit, inst_set = shared[prefix_key(level)]
             block, ka, kb = new_block, nka, nkb
             continue
-        if not sharded and size > 1 and n_global >= size:
+        if not sharded and size > 1 and (n_global >= size or n_sets > 1):
             lo, hi = qdist.shard_bounds(n_global, rank, size)
             sigma = sigma[lo:hi].contiguous()
+            if inst_set is not None:
+                inst_set = inst_set[lo:hi].contiguous()
             sharded, shard_units = True, n_global
+        n_local = sigma.shape[0]
+        emit = uniq[level]
+        if n_local == 0:                                # a rank without parameter sets (more ranks than sets)
+            block, ka, kb = new_block, nka, nkb
+            width = block.size if level < len(plan) - 2 else len(emit)
+            sigma = out = torch.zeros((0, width), dtype=torch.complex128, device=eng.device)
+            n_global *= len(emit)
+            if sharded and level < len(plan) - 2:
+                rows_per_unit *= len(emit)
+            continue
         sigma = eng.apply_dipole(block, new_block, 0 if side == 'k' else 1, mu_dev, sigma)
         block, ka, kb = new_block, nka, nkb
         dev = None if last and readouts is not None else upload(block)
-        n_local = sigma.shape[0]
-        emit = uniq[level]
+        sets_kw = {} if inst_set is None else dict(inst_set=inst_set)
         if level < len(plan) - 2:
-            _, snap = propagate(dev, sigma, n_local, emit, snapshots=True)
+            _, snap = propagate(dev, sigma, n_local, emit, snapshots=True, **sets_kw)
             sigma = snap.reshape(n_local * len(emit), block.size)
+            if inst_set is not None:
+                inst_set = inst_set.repeat_interleave(len(emit))
         elif readouts is not None:
             if ready is not None:
                 main = torch.cuda.current_stream(eng.device)
                 main.wait_event(ready)
                 readouts.record_stream(main)
-            out = eng.readout_gemm(sigma.reshape(n_local, block.size).contiguous(), readouts.contiguous())
+            if n_sets > 1:                              # whole sets per rank, equally many chains each: batched product
+                local_sets = readouts.shape[0]
+                out = eng.readout_gemm(sigma.reshape(local_sets, n_local // local_sets, block.size).contiguous(),
+                                       readouts.contiguous()).reshape(n_local, len(emit))
+            else:
+                out = eng.readout_gemm(sigma.reshape(n_local, block.size).contiguous(), readouts.contiguous())
         else:
             obs = eng.upload_observables(*block.emission_observable(np.asarray(mu, dtype=float)), kind='emission', mu=mu)
-            out, _ = propagate(dev, sigma, n_local, emit, obs=obs)
+            out, _ = propagate(dev, sigma, n_local, emit, obs=obs, **sets_kw)
             out = out.reshape(n_local, len(emit))
         n_global *= len(emit)
         if sharded and level < len(plan) - 2:
             rows_per_unit *= len(emit)
         if shared is not None and not last:
-            shared[prefix_key(level)] = (sigma, n_global, sharded, shard_units, rows_per_unit)
+            shared[prefix_key(level)] = (sigma, n_global, sharded, shard_units, rows_per_unit, inst_set)
 
+    lead = [n_sets] if n_sets > 1 else []               # ensembles: one signal per parameter set
     if zero:
-        return torch.zeros(shape, dtype=torch.complex128, device=eng.device) if device_output else np.zeros(shape, dtype=complex)
+        if device_output:
+            return torch.zeros(lead + shape, dtype=torch.complex128, device=eng.device)
+        return np.zeros(lead + shape, dtype=complex)
     if sharded:
         out = qdist.all_gather_rows(out, shard_units, rows_per_unit)
+    skip = len(lead)
     if device_output:
-        table = out.reshape([len(u) for u in uniq])
+        table = out.reshape(lead + [len(u) for u in uniq])
         for axis, inv in enumerate(inverse):            # back to the caller's order/duplicates, axis by axis
-            if len(inv) != table.shape[axis] or np.any(inv != np.arange(len(inv))):
-                table = table.index_select(axis, torch.as_tensor(inv, device=eng.device))
-        return table.reshape(shape).contiguous()
-    table = (eng.to_host(out) if hasattr(eng, 'to_host') else out.cpu().numpy()).reshape([len(u) for u in uniq])
+            if len(inv) != table.shape[skip + axis] or np.any(inv != np.arange(len(inv))):
+                table = table.index_select(skip + axis, torch.as_tensor(inv, device=eng.device))
+        return table.reshape(lead + shape).contiguous()
+    table = (eng.to_host(out) if hasattr(eng, 'to_host') else out.cpu().numpy()).reshape(lead + [len(u) for u in uniq])
     if all(len(inv) == len(u) and np.array_equal(inv, np.arange(len(inv))) for inv, u in zip(inverse, uniq)):
         return table                                    # delays were ascending and distinct: nothing to reorder
+    if lead:
+        return table[np.ix_(np.arange(n_sets), *inverse)].reshape(lead + shape)
     return table[np.ix_(*inverse)].reshape(shape)

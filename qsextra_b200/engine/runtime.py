@@ -178,7 +178,7 @@ class Engine:
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             rc = self.lib.qsx_evolve_rrc(C.byref(args), C.c_void_p(stream))
-        if rc < 0 and b'no compile-time program' in self.lib.qsx_last_error():
+        if rc == cabi.ERR_NO_PROGRAM:
             return None
         cabi.check(rc)
         if n_inst > 0 and n_emit > 0:
@@ -253,7 +253,13 @@ class Engine:
         out_obs [n_inst, n_emit, n_obs] (float64 if obs_real else complex128), out_snap [n_inst, n_emit, E] complex128."""
         blk: DeviceBlock = prog['block']
         E = blk.block.size
-        emit = emit_steps if isinstance(emit_steps, torch.Tensor) else self.to_device(np.asarray(emit_steps), torch.int32)
+        if isinstance(emit_steps, torch.Tensor):         # (a device tensor is the caller's promise of the precondition)
+            emit = emit_steps
+        else:
+            host_emit = np.asarray(emit_steps, dtype=np.int64).reshape(-1)
+            if host_emit.size and (np.any(np.diff(host_emit) <= 0) or host_emit[0] < 0 or host_emit[-1] > n_steps):
+                raise cabi.QsxError('emit_steps must be strictly increasing step counts in [0, n_steps] (include/qsx.h)')
+            emit = self.to_device(host_emit, torch.int32)
         n_emit = int(emit.numel())
         assert sigma_in.dtype == torch.complex128 and sigma_in.is_contiguous() and sigma_in.numel() % E == 0
         if 'rr' in prog and (obs is None or obs['n'] <= cabi.RR_MAX_OBS):
@@ -457,22 +463,27 @@ class Engine:
         return out
 
     def readout_gemm(self, sigma: torch.Tensor, readouts: torch.Tensor) -> torch.Tensor:
-        """out[i, k] = sum_e sigma[i, e] readouts[k, e] (complex128, no conjugation; ``qsx_readout_gemm``)."""
+        """out[i, k] = sum_e sigma[i, e] readouts[k, e] (complex128, no conjugation; ``qsx_readout_gemm``).  With a
+        leading batch axis on both operands (``sigma`` [S, n, E], ``readouts`` [S, m, E]: the parameter sets of an
+        ensemble, each with its own propagated read-outs) the S products run in one launch -> [S, n, m]."""
         assert sigma.dtype == readouts.dtype == torch.complex128 and sigma.is_contiguous() and readouts.is_contiguous()
-        n_inst, E = sigma.shape
-        n_emit = readouts.shape[0]
-        assert readouts.shape[1] == E
-        out = torch.empty((n_inst, n_emit), dtype=torch.complex128, device=self.device)
+        batched = sigma.dim() == 3
+        assert readouts.dim() == sigma.dim() and (not batched or readouts.shape[0] == sigma.shape[0])
+        n_batch = sigma.shape[0] if batched else 1
+        n_inst, E = sigma.shape[-2:]
+        n_emit = readouts.shape[-2]
+        assert readouts.shape[-1] == E
+        out = torch.empty(((n_batch,) if batched else ()) + (n_inst, n_emit), dtype=torch.complex128, device=self.device)
         with torch.cuda.device(self.device):
-            ws_bytes = self.lib.qsx_readout_gemm_workspace_bytes(n_inst, n_emit, E)
+            ws_bytes = self.lib.qsx_readout_gemm_batched_workspace_bytes(n_batch, n_inst, n_emit, E)
             cabi.check(ws_bytes)
             workspace = torch.empty(ws_bytes // 8, dtype=torch.float64, device=self.device) if ws_bytes else None
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            cabi.check(self.lib.qsx_readout_gemm(n_inst, n_emit, E, C.c_void_p(sigma.data_ptr()),
-                                                 C.c_void_p(readouts.data_ptr()), C.c_void_p(out.data_ptr()),
-                                                 C.c_void_p(workspace.data_ptr() if workspace is not None else None),
-                                                 C.c_void_p(stream)))
-        if n_inst > 0 and n_emit > 0:
+            cabi.check(self.lib.qsx_readout_gemm_batched(n_batch, n_inst, n_emit, E, C.c_void_p(sigma.data_ptr()),
+                                                         C.c_void_p(readouts.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                         C.c_void_p(workspace.data_ptr() if workspace is not None else None),
+                                                         C.c_void_p(stream)))
+        if n_batch > 0 and n_inst > 0 and n_emit > 0:
             self.launches += 1
         return out
 

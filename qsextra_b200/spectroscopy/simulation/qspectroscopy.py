@@ -151,3 +151,75 @@ def qspectroscopy_set(system: ChromophoreSystem | ExcitonicSystem,
                                     device_output=device_output)
     ending_sentence(verbose)
     return signals
+
+
+def qspectroscopy_ensemble(systems,
+                           spectroscopies,
+                           shots: int = 1000,
+                           verbose: bool = True,
+                           device_output: bool = False,
+                           average: bool = False,
+                           **qevolve_kwds,
+                           ) -> list:
+    """The diagrams ``spectroscopies`` for an ENSEMBLE of systems in one batched evaluation (new API: the reference
+    loops ``qspectroscopy`` over realisations by hand, e.g. for static disorder).
+
+    ``systems``: ExcitonicSystem / ChromophoreSystem objects with the same structure (sites, pseudomode levels, which
+    couplings are non-zero) and the same dipole moments; energies, couplings and bath parameters may differ.
+    ``coll_rates``: one value (list) for all members, or one row per member.  The members are the parameter sets of
+    one step program: every level of the response tree holds all of them, each propagates its own read-out, the last
+    level is one batched product (``engine.response``).  Under ``torch.distributed`` the MEMBERS are sharded over the
+    ranks (contiguous slices) and one all-gather assembles the result on every rank.
+    Returns one array per diagram with a leading ensemble axis, ``[len(systems), *grid]`` (``average=True``: the
+    ensemble mean, ``[*grid]``)."""
+    from ...engine.program import StepProgram, SystemBatch
+    systems, spectroscopies = list(systems), list(spectroscopies)
+    if not systems or not spectroscopies:
+        return []
+    for s_ in systems:
+        _validate_system(s_)
+        if type(s_) is not type(systems[0]):
+            raise TypeError('all members of an ensemble must be of the same class')
+    if type(systems[0]) is ChromophoreSystem and systems[0].mode_dict is None:
+        warnings.warn("Pseudomodes not specified. Executing the dynamics with system as an ExcitonicSystem.")
+        return qspectroscopy_ensemble([s_.extract_ExcitonicSystem() for s_ in systems], spectroscopies, shots, verbose,
+                                      device_output, average, **qevolve_kwds)
+    for key in _RESERVED:
+        qevolve_kwds.pop(key, None)
+    unknown = set(qevolve_kwds) - {'Trotter_number', 'Trotter_order', 'dt', 'coll_rates', 'GPU'}
+    if unknown:
+        raise TypeError("qevolve() got an unexpected keyword argument '{}'".format(sorted(unknown)[0]))
+    delays = spectroscopies[0].delay_time
+    for sp in spectroscopies:
+        if sp.side_seq == '' or sp.direction_seq == '':
+            raise ValueError('Spectroscopy object is not correctly defined. Spectroscopy.side_seq or Spectroscopy.direction_seq are missing.')
+        if len(sp.delay_time) != len(delays) or any(not np.array_equal(np.asarray(a, dtype=float), np.asarray(b, dtype=float))
+                                                     for a, b in zip(sp.delay_time, delays)):
+            raise ValueError('qspectroscopy_ensemble needs the same delay_time in every entry')
+    mu = np.asarray(systems[0].dipole_moments, dtype=float)
+    if any(not np.array_equal(np.asarray(s_.dipole_moments, dtype=float), mu) for s_ in systems):
+        raise ValueError('the members of an ensemble must have the same dipole moments')
+    if qevolve_kwds.get('dt') is None:
+        raise ValueError('qspectroscopy needs an explicit dt')
+    B = len(systems)
+    rates_in = qevolve_kwds.get('coll_rates')
+    rates = None
+    if rates_in is not None:
+        arr = np.asarray(rates_in, dtype=float)
+        per_member = arr.ndim == 2 or (arr.ndim == 1 and type(systems[0]) is ExcitonicSystem and arr.size == B and B > 1)
+        rows = [_validate_rates(s_, (arr[b].tolist() if arr.ndim == 2 else float(arr[b])) if per_member else rates_in)
+                for b, s_ in enumerate(systems)]
+        rates = np.array([np.atleast_1d(np.asarray(r, dtype=float)) for r in rows])
+        if type(systems[0]) is ExcitonicSystem:
+            rates = rates.reshape(B)
+    counts, (dt, dt_trotter, trotter_number, _) = delay_step_counts(delays, qevolve_kwds['dt'], qevolve_kwds.get('Trotter_number', 1))
+    program = StepProgram(SystemBatch.from_systems(systems), dt, trotter_number, qevolve_kwds.get('Trotter_order', 1), rates,
+                          dt_trotter=dt_trotter)
+    signals = response_function_set(program, mu, [(sp.side_seq, sp.direction_seq) for sp in spectroscopies], counts,
+                                    device_output=device_output)
+    if B == 1:                                          # a one-member ensemble still carries the ensemble axis
+        signals = [sig[None] for sig in signals]
+    if average:
+        signals = [sig.mean(0) for sig in signals]
+    ending_sentence(verbose)
+    return signals

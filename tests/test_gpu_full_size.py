@@ -169,3 +169,70 @@ def test_c5_collision_model_against_master_equation(engine):
         q = qevolve(s, t, shots=0, dt=DT / sub, coll_rates=[0.2], verbose=False).populations
         gaps.append(np.abs(q - cl).max())
     assert gaps[0] < 2e-3 and 1.7 < gaps[0] / gaps[1] < 2.3, gaps
+
+
+# ---- far corners of the full grids against the C oracle (literal gates; collisions as channels, tests/test_oracle_golden.py) --
+def _c4_system():
+    J = np.zeros((4, 4))
+    for i in range(3):
+        J[i, i + 1] = J[i + 1, i] = -0.01
+    return ChromophoreSystem(energies=[1.55, 1.50, 1.46, 1.52], couplings=J, dipole_moments=[1., 1., 1., 1.],
+                             frequencies_pseudomode=0.02, levels_pseudomode=2, couplings_ep=float(np.sqrt(GAMMA * 0.1 / 2)))
+
+
+def test_c4_full_grid_far_corners_against_the_oracle(engine):
+    """BASELINE configs[3] at FULL size (128 x 16 x 128, gsb + se + esa, one qspectroscopy_set call) compared with the
+    oracle where the delays are longest: the whole t3 rows of the chains (t1, t2) = (127, 15) and (64, 7) -- 1905 + 1500
+    + 1905 collision steps at the far corner (127, 15, 127) -- 2 x 128 points per diagram."""
+    from qsextra_b200.spectroscopy import qspectroscopy_set
+    s = _c4_system()
+    t1 = (15 * DT * np.arange(128)).tolist()
+    t2 = (100 * DT * np.arange(16)).tolist()
+    specs = [FeynmanDiagram(lab, [t1, t2, t1]) for lab in ('gsb', 'se', 'esa')]
+    sigs = qspectroscopy_set(s, specs, verbose=False, dt=DT, coll_rates=[0.2])
+    rows = [(127, 15), (64, 7)]
+    for spec, sig in zip(specs, sigs):
+        assert sig.shape == (128, 16, 128)
+        ref, _ = fast.response_points(s, spec, rows, DT, coll_rates=[0.2], kraus=True)
+        got = np.array([sig[i, j] for i, j in rows])
+        scale = np.abs(sig).max()
+        assert np.abs(got - ref).max() < 1e-10 * scale, (spec.side_seq, np.abs(got - ref).max() / scale)
+        # and relative to the local magnitude of the (decayed) far row itself
+        assert np.abs(got - ref).max() < 1e-8 * np.abs(ref).max()
+
+
+def test_c3_all_six_pathways_far_rows_against_the_oracle(engine):
+    """BASELINE configs[2] at full size, the three rephasing and the three non-rephasing pathways, compared with the
+    oracle on the t3 rows of t1 = 63 (1890 steps) and t1 = 31."""
+    from qsextra_b200.spectroscopy import Spectroscopy
+    s = ExcitonicSystem(energies=[1.55, 1.46], couplings=-0.01, dipole_moments=[1., 0.8])
+    grid = (30 * DT * np.arange(64)).tolist()
+    kw = dict(dt=DT, coll_rates=GAMMA / 4)
+    specs = [FeynmanDiagram(lab, [grid, [0.], grid]) for lab in ('gsb', 'se', 'esa')]
+    for sides, directions in (('kkkk', 'ioio'), ('kbbk', 'iioo'), ('kbkk', 'iiio')):
+        extra = Spectroscopy([grid, [0.], grid])
+        extra.side_seq, extra.direction_seq = sides, directions
+        specs.append(extra)
+    rows = [(63, 0), (31, 0)]
+    for spec in specs:
+        sig = qspectroscopy(s, spec, verbose=False, **kw)
+        ref, _ = fast.response_points(s, spec, rows, DT, coll_rates=GAMMA / 4, kraus=True)
+        got = np.array([sig[i, j] for i, j in rows])
+        assert np.abs(got - ref).max() < 1e-10 * np.abs(sig).max(), spec.side_seq
+
+
+def test_c5_eight_sites_50_steps_against_the_sector_oracle(engine):
+    """BASELINE configs[4] geometry (8 sites, one 2-level pseudomode each, 2048 x 2048 single-exciton block, streaming
+    path) against the oracle's literal gate list restricted to the single-exciton sector (oracle/sector.py)."""
+    from oracle import sector
+    n = 8
+    J = np.zeros((n, n))
+    for i in range(n - 1):
+        J[i, i + 1] = J[i + 1, i] = -0.01
+    s = ChromophoreSystem(energies=[1.55, 1.50, 1.46, 1.52, 1.49, 1.53, 1.47, 1.51], couplings=J, dipole_moments=[1.] * n,
+                          frequencies_pseudomode=0.02, levels_pseudomode=2, couplings_ep=float(np.sqrt(GAMMA * 0.1 / 2)))
+    s.set_state('localized excitation', 0)
+    steps = [0, 1, 10, 25, 50]
+    got = qevolve(s, np.array(steps) * DT, shots=0, dt=DT, coll_rates=[0.2], verbose=False).populations
+    ref = sector.populations(s, steps, DT, coll_rates=[0.2])
+    assert np.abs(got - ref).max() < 1e-10, np.abs(got - ref).max()

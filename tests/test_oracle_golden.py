@@ -185,3 +185,21 @@ def test_kraus_form_rewrites_only_collision_patterns():
     assert [op[0] for op in ops[-2:]] == ['dephase', 'dephase']
     assert all(len(op[1]) == layout.n_qubits - 1 for op in ops if op[0] == 'rot')
     assert abs(ops[-1][2] - np.sqrt(0.3 * 0.1)) < 1e-15
+
+
+def test_sector_oracle_equals_full_space_simulation():
+    """oracle/sector.py (the literal gate list kept inside one exciton-number sector; used for the 8-site BASELINE
+    configs[4], whose full space no CPU can hold) against the full-space dense simulator on 3 sites."""
+    from oracle import sector
+    J = np.array([[0, -0.01, 0.005], [-0.01, 0, 0.02], [0.005, 0.02, 0]])
+    chrom = build_system(dict(energies=[1.55, 1.50, 1.46], couplings=J.tolist(), dipole_moments=[1., 1., 1.],
+                              frequencies_pseudomode=[0.02], levels_pseudomode=[2], couplings_ep=[0.054],
+                              state=['delocalized excitation', [0.6, [0.0, 0.8], 0.0]]))
+    steps = [0, 1, 2, 7, 20]
+    dt = 0.15
+    ref = R.qevolve_exact(chrom, np.array(steps) * dt, dt=dt, coll_rates=[0.2])['populations']
+    assert np.abs(sector.populations(chrom, steps, dt, coll_rates=[0.2]) - ref).max() < 1e-12
+    exc = build_system(dict(energies=[1.55, 1.50, 1.46], couplings=J.tolist(), dipole_moments=[1., 1., 1.],
+                            state=['localized excitation', 1]))
+    ref = R.qevolve_exact(exc, np.array(steps) * dt, dt=dt, coll_rates=0.05, Trotter_number=2)['populations']
+    assert np.abs(sector.populations(exc, steps, dt, coll_rates=0.05, Trotter_number=2) - ref).max() < 1e-12

@@ -42,7 +42,8 @@ class NumpyEngine:
     def upload_observables(self, ptr, idx, w, kind=None, mu=None):
         return dict(host=(np.asarray(ptr), np.asarray(idx), np.asarray(w)))
 
-    def evolve(self, prog, sigma_in, n_inst, n_steps, emit_steps, obs=None, snapshots=False, **_):
+    def evolve(self, prog, sigma_in, n_inst, n_steps, emit_steps, obs=None, snapshots=False, inst_set=None,
+               inst_src=None, **_):
         bound = prog['bound']
         self.transposed_runs += int(bound.is_transposed)
         blk = bound.block
@@ -50,10 +51,11 @@ class NumpyEngine:
         rows = sigma_in.numpy().reshape(-1, blk.dim_a, blk.dim_b)
         snaps = np.zeros((n_inst, len(emit), blk.size), dtype=complex)
         for i in range(n_inst):
-            sigma = rows[i]
+            sigma = rows[i if inst_src is None else int(inst_src[i])]
+            member = 0 if inst_set is None else int(inst_set[i])
             for step in range(n_steps + 1):
                 if step:
-                    sigma = emulator.apply_step(sigma, bound)
+                    sigma = emulator.apply_step(sigma, bound, member)
                 for k, e in enumerate(emit):
                     if e == step:
                         snaps[i, k] = sigma.reshape(-1)
@@ -64,7 +66,7 @@ class NumpyEngine:
         return out_obs, (torch.as_tensor(snaps) if snapshots else None)
 
     def readout_gemm(self, sigma, readouts):
-        return sigma @ readouts.transpose(0, 1)
+        return sigma @ readouts.transpose(-1, -2)
 
 
 def signal_of(name, engine):
@@ -146,3 +148,76 @@ def test_set_of_diagrams_shares_levels_and_read_outs(monkeypatch):
     assert all(np.array_equal(a, b) for a, b in zip(alone, together))
     assert Counting.evolves < separately                       # 5 instead of 9 propagations
     assert Counting.evolves == 5 and separately == 9
+
+
+# ---- ensembles: the parameter sets of one step program through one tree -----------------------------------------
+def _ensemble(n_members):
+    import warnings
+    from qsextra_b200 import ChromophoreSystem
+    rng = np.random.default_rng(5)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        return [ChromophoreSystem(energies=(np.array([1.55, 1.46]) + 0.02 * rng.standard_normal(2)).tolist(),
+                                  couplings=-0.01 + 0.002 * rng.standard_normal(), dipole_moments=[1., 0.8],
+                                  frequencies_pseudomode=0.02, levels_pseudomode=2, couplings_ep=0.054)
+                for _ in range(n_members)]
+
+
+def _ensemble_signals(systems, labels, delays, engine):
+    from qsextra_b200.engine.program import StepProgram, SystemBatch
+    from qsextra_b200.engine.response import response_function_set
+    from qsextra_b200.spectroscopy import FeynmanDiagram
+    dt = 0.15
+    diagrams = [FeynmanDiagram(lab, delays) for lab in labels]
+    counts, (dt_, dt_trotter, tn, _) = delay_step_counts(diagrams[0].delay_time, dt, 1)
+    rates = np.array([[0.2 + 0.01 * b] for b in range(len(systems))])
+    program = StepProgram(SystemBatch.from_systems(systems), dt_, tn, 1, rates, dt_trotter=dt_trotter)
+    mu = np.asarray(systems[0].dipole_moments, dtype=float)
+    return response_function_set(program, mu, [(d.side_seq, d.direction_seq) for d in diagrams], counts, engine=engine)
+
+
+_ENSEMBLE_DELAYS = [[0., 0.3, 0.15], [0.15, 0.45], [0., 0.15, 0.6]]
+
+
+@pytest.mark.parametrize('heisenberg', [False, True])
+def test_ensemble_equals_member_by_member(heisenberg, monkeypatch):
+    monkeypatch.setenv('QSX_DISABLE_RR', '1')
+    monkeypatch.setenv('QSX_HEISENBERG_MIN', '1' if heisenberg else '1000000')
+    systems = _ensemble(3)
+    engine = NumpyEngine()
+    together = _ensemble_signals(systems, ('gsb', 'esa'), _ENSEMBLE_DELAYS, engine)
+    assert (engine.transposed_runs > 0) == heisenberg
+    for d, sig in enumerate(together):
+        assert sig.shape == (3, 3, 2, 3)
+        for b, system in enumerate(systems):
+            # a member alone, with ITS rate: a one-set program
+            from qsextra_b200.engine.program import StepProgram, SystemBatch
+            from qsextra_b200.spectroscopy import FeynmanDiagram
+            diagram = FeynmanDiagram(('gsb', 'esa')[d], _ENSEMBLE_DELAYS)
+            counts, (dt_, dt_trotter, tn, _) = delay_step_counts(diagram.delay_time, 0.15, 1)
+            program = StepProgram(SystemBatch.from_systems([system]), dt_, tn, 1, np.array([[0.2 + 0.01 * b]]), dt_trotter=dt_trotter)
+            alone = response_function(program, np.asarray(system.dipole_moments, dtype=float), diagram.side_seq,
+                                      diagram.direction_seq, counts, engine=NumpyEngine())
+            assert np.abs(sig[b] - alone).max() < 1e-12
+
+
+def _ensemble_worker(rank, size, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), QSX_DISABLE_RR='1', QSX_HEISENBERG_MIN='2')
+    dist.init_process_group('gloo', rank=rank, world_size=size)
+    try:
+        sigs = _ensemble_signals(_ensemble(3), ('se', 'esa'), _ENSEMBLE_DELAYS, NumpyEngine())
+        np.save(os.path.join(out_dir, 'e%d.npy' % rank), np.array(sigs))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('size', [2, 4])
+def test_ensemble_members_sharded_over_a_gloo_group(tmp_path, size, monkeypatch):
+    """Members over ranks (4 ranks for 3 members: one rank holds nothing), one gather, every rank the whole result."""
+    monkeypatch.setenv('QSX_DISABLE_RR', '1')
+    monkeypatch.setenv('QSX_HEISENBERG_MIN', '2')
+    want = np.array(_ensemble_signals(_ensemble(3), ('se', 'esa'), _ENSEMBLE_DELAYS, NumpyEngine()))
+    mp.spawn(_ensemble_worker, args=(size, _free_port(), str(tmp_path)), nprocs=size, join=True)
+    for r in range(size):
+        got = np.load(os.path.join(str(tmp_path), 'e%d.npy' % r))
+        assert got.shape == want.shape and np.abs(got - want).max() < 1e-12

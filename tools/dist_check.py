@@ -43,6 +43,20 @@ worst = max(worst, float(np.abs(sh - al).max()))
 one = SystemBatch(batch.energies[:1], batch.couplings[:1], batch.dipole_moments[:1], batch.omega[:1], batch.coupl_ep[:1], (2,))
 sh1 = qevolve_batch(one, t, dt=DT, coll_rates=rates[:1])
 worst = max(worst, float(np.abs(sh1 - al[:1]).max()))
+# an ensemble (parameter sets of one program): members over the ranks, one gather; 3 members also leave ranks empty at N = 4, 8
+from qsextra_b200.spectroscopy import qspectroscopy_ensemble
+members = [ChromophoreSystem(energies=(np.array([1.55, 1.50, 1.46, 1.52]) + 0.01 * k).tolist(), couplings=J,
+                             dipole_moments=[1., 0.9, 1.1, 1.], frequencies_pseudomode=0.02, levels_pseudomode=2,
+                             couplings_ep=0.054) for k in range(3)]
+specs = [FeynmanDiagram(lab, delays) for lab in ('gsb', 'esa')]
+together = qspectroscopy_ensemble(members, specs, verbose=False, **kw)
+w = qdist.world
+qdist.world = lambda: (0, 1)
+for k, member in enumerate(members):
+    for d, spec in enumerate(specs):
+        alone = qspectroscopy(member, spec, verbose=False, **kw)
+        worst = max(worst, float(np.abs(together[d][k] - alone).max()))
+qdist.world = w
 flag = torch.tensor([worst], device='cuda')
 dist.all_reduce(flag, op=dist.ReduceOp.MAX)
 if rank == 0:
