@@ -217,7 +217,7 @@ def spectroscopy_extras(world, rank, barrier):
                         extra.side_seq, extra.direction_seq = sides, directions
                         specs.append(extra)
                 for sp in specs:
-                    qspectroscopy(system, sp, verbose=False, **kw)              # warm-up (module loads, caches)
+                    qspectroscopy(system, sp, shots=0, verbose=False, **kw)              # warm-up (module loads, caches)
                 def timed(run, repeats=3):
                     """Median wall-clock of ``repeats`` evaluations (each between barriers) and the last result."""
                     samples, result = [], None
@@ -229,7 +229,7 @@ def spectroscopy_extras(world, rank, barrier):
                         samples.append(time.perf_counter() - t_start)
                     return sorted(samples)[len(samples) // 2], samples, result
 
-                sec, samples, sigs = timed(lambda: [qspectroscopy(system, sp, verbose=False, **kw) for sp in specs])
+                sec, samples, sigs = timed(lambda: [qspectroscopy(system, sp, shots=0, verbose=False, **kw) for sp in specs])
                 points = len(specs) * int(np.prod([len(d) for d in delays]))
                 out[name] = dict(grid_points=points, seconds=sec, grid_points_per_s=points / sec, warmup_runs=1,
                                  samples_s=samples, checksum=float(sum(np.abs(s_).sum() for s_ in sigs)))
@@ -244,13 +244,13 @@ def spectroscopy_extras(world, rank, barrier):
                     # the simulation to the transformed spectrum; only the spectra's checksum comes back to the host
                     from qsextra_b200.spectroscopy.postprocessing import postprocessing
                     import torch as _torch
-                    warm = qspectroscopy(system, specs[0], verbose=False, device_output=True, **kw)
+                    warm = qspectroscopy(system, specs[0], shots=0, verbose=False, device_output=True, **kw)
                     float(postprocessing(specs[0], warm, pad_extension=3)[1].abs().sum())   # cuFFT plans, lazy module loads
                     barrier()
                     t0 = time.perf_counter()
                     total = _torch.zeros((), dtype=_torch.float64, device='cuda')
                     for sp in specs:
-                        sig = qspectroscopy(system, sp, verbose=False, device_output=True, **kw)
+                        sig = qspectroscopy(system, sp, shots=0, verbose=False, device_output=True, **kw)
                         for idx in range(len(delays[1])):
                             _, spectrum = postprocessing(sp, sig, RF_freq=1.5, damping_rate=0.005, pad_extension=3, T2_index=idx)
                             total += spectrum.abs().sum()

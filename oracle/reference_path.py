@@ -164,13 +164,16 @@ def qspectroscopy_operator(system, spectroscopy, **qevolve_kwds):
     layout = C.Layout(system, qevolve_kwds.get('coll_rates') is not None, offset=0)
     inter = interaction_operators(system, layout, spectroscopy.side_seq, spectroscopy.direction_seq)
     step = None
-    counts = []
+    counts, evolutions = [], []
+    shared_step = qevolve_kwds.get('dt') is not None    # dt=None: every delay is its own step size (qevolve.py:373-379)
     for k in range(len(delays)):
-        row = []
+        row, ops_row = [], []
         for t in delays[k]:
-            _, step, c = _evolution_ops(system, layout, t, qevolve_kwds)
+            ops, step, c = _evolution_ops(system, layout, t, qevolve_kwds)
             row.append(c)
+            ops_row.append(ops)
         counts.append(row)
+        evolutions.append(ops_row)
     signal = np.zeros([len(t) for t in delays], dtype=complex)
 
     def apply(dm, side, op):
@@ -183,6 +186,12 @@ def qspectroscopy_operator(system, spectroscopy, **qevolve_kwds):
         apply(work, side, op)
         if level == len(delays):                       # emission: trace after the last operator
             signal[idx] += np.trace(work.rho)
+            return
+        if not shared_step:                            # no common prefix: evolve every delay from the interaction
+            for j in range(len(counts[level])):
+                branch = work.copy()
+                run_ops(branch, evolutions[level][j])
+                descend(branch, level + 1, idx + (j,))
             return
         order = np.argsort(counts[level], kind='stable')
         done = 0

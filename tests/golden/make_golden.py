@@ -148,6 +148,9 @@ def spectroscopy_cases():
         'custom_kkkk_dimer': (DIMER, ('kkkk', 'ioio'), [t2s, [0.], t2s], mk),
         'custom_kbbk_dimer': (DIMER, ('kbbk', 'iioo'), [t2s, [0.], t2s], mk),
         'custom_kbkk_dimer': (DIMER, ('kbkk', 'iiio'), [t2s, [0.], t2s], mk),
+        # dt not given: every scalar delay becomes its own step size (delay / Trotter_number), qevolve.py:373-379
+        'abs_dimer_no_dt': (DIMER, 'a', [0.7, 1.9, 0.4], dict(Trotter_number=3, coll_rates=GAMMA / 4)),
+        'esa_dimer_modes_no_dt': (dimer_modes, 'esa', [[0.5, 1.1], [0.8], [0.3, 0.9]], dict(Trotter_number=2, coll_rates=[0.2])),
     }
     only = [a for a in sys.argv[1:] if a.startswith('only=')]
     for name, (sysdef, label, delays, kw) in cases.items():
@@ -214,8 +217,22 @@ def structure_cases():
          omega1=w2[0], omega3=w2[1], spec_2d=s2)
 
 
+def heom_benchmark():
+    """The only numeric artefact the reference ships for the master-equation path: the HEOM curve rho_11(t) of
+    ``Examples/qcomo - Examples/Benchmark Example 3/data.mat`` (401 points, t = 0 ... 20), which the notebook
+    'Example 3 - More is better' overlays on ``clevolve`` with 1 x 16-, 2 x 4- and 4 x 2-level pseudomodes per site
+    (cells 8-26: N = 2, eps = 0, J = 1, Gamma = 20, Omega = 0.1, g = sqrt(Gamma Omega / (2 W)), rates 2 Omega)."""
+    from scipy.io import loadmat
+    m = loadmat('/root/reference/Examples/qcomo - Examples/Benchmark Example 3/data.mat')
+    save('heom_example3', dict(source='Examples/qcomo - Examples/Benchmark Example 3/data.mat', N=2, energies=[0., 0.],
+                               coupling=1.0, Gamma=20.0, Omega=0.1),
+         t=m['x'][0], rho11=m['y'][0])
+
+
 if __name__ == '__main__':
-    which = [a for a in sys.argv[1:] if not a.startswith('only=')] or ['structure', 'qevolve', 'classical', 'spectroscopy']
+    which = [a for a in sys.argv[1:] if not a.startswith('only=')] or ['structure', 'qevolve', 'classical', 'spectroscopy', 'heom']
+    if 'heom' in which:
+        heom_benchmark()
     if 'structure' in which:
         structure_cases()
     if 'qevolve' in which:

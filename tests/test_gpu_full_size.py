@@ -74,17 +74,17 @@ def test_c3_dimer_2des_full_grid(engine):
     s = ExcitonicSystem(energies=[1.55, 1.46], couplings=-0.01, dipole_moments=[1., 0.8])
     grid = (30 * DT * np.arange(64)).tolist()
     kw = dict(dt=DT, coll_rates=GAMMA / 4)
-    sig = {lab: qspectroscopy(s, FeynmanDiagram(lab, [grid, [0.], grid]), verbose=False, **kw) for lab in ('gsb', 'se', 'esa')}
+    sig = {lab: qspectroscopy(s, FeynmanDiagram(lab, [grid, [0.], grid]), shots=0, verbose=False, **kw) for lab in ('gsb', 'se', 'esa')}
     mu2 = 1. + 0.8 ** 2
     assert abs(sig['gsb'][0, 0, 0] - mu2 ** 2) < 1e-12 and sig['gsb'].shape == (64, 1, 64)
     assert np.abs(sig['gsb'] - sig['se']).max() < 1e-11           # identical at t2 = 0 for this model
     # linearity: doubling every dipole multiplies a third-order response by 16
     s2 = ExcitonicSystem(energies=[1.55, 1.46], couplings=-0.01, dipole_moments=[2., 1.6])
-    twice = qspectroscopy(s2, FeynmanDiagram('esa', [grid, [0.], grid]), verbose=False, **kw)
+    twice = qspectroscopy(s2, FeynmanDiagram('esa', [grid, [0.], grid]), shots=0, verbose=False, **kw)
     assert np.abs(twice - 16 * sig['esa']).max() < 1e-10 * np.abs(twice).max()
     # sub-grid consistency (prefix sharing) and unsorted / repeated delays
     pick1, pick3 = [5, 0, 63, 5], [7, 62, 1]
-    sub = qspectroscopy(s, FeynmanDiagram('esa', [[grid[i] for i in pick1], [0.], [grid[i] for i in pick3]]), verbose=False, **kw)
+    sub = qspectroscopy(s, FeynmanDiagram('esa', [[grid[i] for i in pick1], [0.], [grid[i] for i in pick3]]), shots=0, verbose=False, **kw)
     assert np.abs(sub - sig['esa'][np.ix_(pick1, [0], pick3)]).max() < 1e-12
     # oracle on a corner
     corner = [grid[i] for i in (0, 1, 2)]
@@ -104,13 +104,13 @@ def test_c4_chain_with_pseudomodes_reduced_grid(engine):
     kw = dict(dt=DT, coll_rates=[0.2])
     t1 = (15 * DT * np.arange(6)).tolist()
     t2 = (100 * DT * np.arange(2)).tolist()
-    sig = {lab: qspectroscopy(s, FeynmanDiagram(lab, [t1, t2, t1]), verbose=False, **kw) for lab in ('gsb', 'se', 'esa')}
+    sig = {lab: qspectroscopy(s, FeynmanDiagram(lab, [t1, t2, t1]), shots=0, verbose=False, **kw) for lab in ('gsb', 'se', 'esa')}
     mu2 = float(np.sum(np.array([1., 0.9, 1.1, 1.]) ** 2))
     assert abs(sig['gsb'][0, 0, 0] - mu2 ** 2) < 1e-11
     assert np.abs(sig['gsb'][:, 0, :] - sig['se'][:, 0, :]).max() < 1e-10
     small = [0., 2 * DT]
     for lab in ('gsb', 'se', 'esa'):
-        got = qspectroscopy(s, FeynmanDiagram(lab, [small, [0., 3 * DT], small]), verbose=False, **kw)
+        got = qspectroscopy(s, FeynmanDiagram(lab, [small, [0., 3 * DT], small]), shots=0, verbose=False, **kw)
         ref = R.qspectroscopy_operator(s, FeynmanDiagram(lab, [small, [0., 3 * DT], small]), **kw)
         assert np.abs(got - ref).max() < 1e-10 * np.abs(ref).max()
 
@@ -215,7 +215,7 @@ def test_c3_all_six_pathways_far_rows_against_the_oracle(engine):
         specs.append(extra)
     rows = [(63, 0), (31, 0)]
     for spec in specs:
-        sig = qspectroscopy(s, spec, verbose=False, **kw)
+        sig = qspectroscopy(s, spec, shots=0, verbose=False, **kw)
         ref, _ = fast.response_points(s, spec, rows, DT, coll_rates=GAMMA / 4, kraus=True)
         got = np.array([sig[i, j] for i, j in rows])
         assert np.abs(got - ref).max() < 1e-10 * np.abs(sig).max(), spec.side_seq

@@ -105,17 +105,17 @@ def test_restart_from_reference_checkpoint(engine, tmp_path, monkeypatch):
     dt = 0.1 / 0.658212
     spec = FeynmanDiagram('gsb', [[0., 10 * dt], [0.], [0., 5 * dt, 10 * dt]])
     kw = dict(dt=dt, coll_rates=59.08e-3 / 4)
-    full = qspectroscopy(s, spec, verbose=False, **kw)
+    full = qspectroscopy(s, spec, shots=0, verbose=False, **kw)
     os.mkdir('ckpt')
     partial = np.zeros_like(full)
     partial.reshape(-1)[:4] = 77.0 + 1j                      # what the "interrupted run" had stored for points 0..3
     np.save('ckpt/signal.npy', partial)
     np.save('ckpt/last_time_indices_number.npy', 3)
-    resumed = qspectroscopy(s, spec, verbose=False, restart_from_checkpoint='ckpt', **kw)
+    resumed = qspectroscopy(s, spec, shots=0, verbose=False, restart_from_checkpoint='ckpt', **kw)
     assert np.all(resumed.reshape(-1)[:4] == 77.0 + 1j)
     close(resumed.reshape(-1)[4:], full.reshape(-1)[4:])
     assert not os.path.exists('ckpt')
-    again = qspectroscopy(s, spec, verbose=False, checkpoint=True, **kw)
+    again = qspectroscopy(s, spec, shots=0, verbose=False, checkpoint=True, **kw)
     close(again, full)
     assert [d for d in os.listdir('.') if os.path.isdir(d)] == []
 
@@ -197,11 +197,11 @@ def test_diagrams_of_one_spectrum_share_their_common_levels(engine):
     delays = [(dt * 3 * np.arange(6)).tolist(), (dt * 5 * np.arange(3)).tolist(), (dt * 3 * np.arange(7)).tolist()]
     kw = dict(shots=0, verbose=False, dt=dt, coll_rates=[0.2])
     before = engine.launches
-    alone = {lab: qspectroscopy(s, FeynmanDiagram(lab, delays), **kw) for lab in ('gsb', 'se', 'esa')}
+    alone = {lab: qspectroscopy(s, FeynmanDiagram(lab, delays), shots=0, **kw) for lab in ('gsb', 'se', 'esa')}
     launches_alone = engine.launches - before
     shared = {}
     before = engine.launches
-    together = {lab: qspectroscopy(s, FeynmanDiagram(lab, delays), shared=shared, **kw) for lab in ('gsb', 'se', 'esa')}
+    together = {lab: qspectroscopy(s, FeynmanDiagram(lab, delays), shots=0, shared=shared, **kw) for lab in ('gsb', 'se', 'esa')}
     launches_together = engine.launches - before
     for lab in alone:
         assert np.array_equal(alone[lab], together[lab]), lab
@@ -209,7 +209,7 @@ def test_diagrams_of_one_spectrum_share_their_common_levels(engine):
     other = ChromophoreSystem(energies=[1.55, 1.50, 1.46, 1.53], couplings=J, dipole_moments=[1., 0.8, -0.6, 1.1],
                               frequencies_pseudomode=0.02, levels_pseudomode=2, couplings_ep=0.054)
     with pytest.raises(ValueError, match='shared dict'):
-        qspectroscopy(other, FeynmanDiagram('gsb', delays), shared=shared, **kw)
+        qspectroscopy(other, FeynmanDiagram('gsb', delays), shots=0, shared=shared, **kw)
     # the set API: read-outs of all diagrams enqueued up front
     from qsextra_b200.spectroscopy import qspectroscopy_set
     as_set = qspectroscopy_set(s, [FeynmanDiagram(lab, delays) for lab in ('gsb', 'se', 'esa')], **kw)
@@ -245,3 +245,30 @@ def test_batch_with_different_initial_states_equals_single_runs(engine):
     for s in systems:
         s.set_state('ground')
     assert not np.any(qevolve_batch(systems, time, dt=dt, coll_rates=rates))
+
+
+def test_shots_add_the_estimator_sampling_error(engine):
+    """F2 (qspectroscopy.py:114, :180-181): shots > 0 returns exact signal + sampling error of the stated sigma,
+    reproducible with a seed, on the host and on the device; shots = 0 / None stay exact."""
+    from qsextra_b200 import ExcitonicSystem
+    from qsextra_b200.spectroscopy import FeynmanDiagram, qspectroscopy_set
+    from qsextra_b200.spectroscopy.simulation.qspectroscopy import estimator_noise_sigma
+    s = ExcitonicSystem(energies=[1.55, 1.46], couplings=-0.01, dipole_moments=[1., 0.8])
+    dt = 0.1 / 0.658212
+    grid = (dt * np.arange(40)).tolist()
+    spec = FeynmanDiagram('gsb', [grid, [0.], grid])
+    kw = dict(verbose=False, dt=dt, coll_rates=59.08e-3 / 4)
+    exact = qspectroscopy(s, spec, shots=0, **kw)
+    assert np.array_equal(exact, qspectroscopy(s, spec, shots=None, **kw))
+    noisy = qspectroscopy(s, spec, shots=4000, seed=3, **kw)
+    sigma = estimator_noise_sigma(spec.side_seq, spec.direction_seq, [1., 0.8], 4000)
+    dev = noisy - exact
+    assert abs(dev.real.std() / sigma - 1) < 0.1 and abs(dev.imag.std() / sigma - 1) < 0.1
+    assert np.array_equal(noisy, qspectroscopy(s, spec, shots=4000, seed=3, **kw))
+    on_device = qspectroscopy(s, spec, shots=4000, seed=3, device_output=True, **kw)
+    dev2 = on_device.cpu().numpy() - exact
+    assert abs(dev2.real.std() / sigma - 1) < 0.1
+    default = qspectroscopy(s, spec, **kw)                    # the reference's default: shots = 1000
+    assert abs((default - exact).real.std() / (sigma * 2) - 1) < 0.1
+    both = qspectroscopy_set(s, [spec], **kw)                 # the set API defaults to exact
+    assert np.array_equal(both[0], exact)

@@ -110,3 +110,33 @@ def test_ket_generator_and_segments():
     assert np.array_equal(segments_from_times([0., 0.5, 2.0]), [0., 0.5, 1.5])
     with pytest.raises(ValueError):
         LindbladProgram([1.] * 2, np.zeros((2, 2)), None, [0.1] * 2, [0.1] * 2, (64, 128))
+
+
+def test_generator_reproduces_the_heom_curve_of_example_3():
+    """K-HEOM on the host: the sparse generator ``engine/lindblad.py`` builds for the 4 x 2-level pseudomode model of
+    the notebook 'Example 3 - More is better', propagated with SciPy, against the HEOM curve the reference ships
+    (tests/golden/heom_example3.npz <- Benchmark Example 3/data.mat): 1e-6 while t <= 0.15, 1.225e-2 at t = 10.65
+    (the survey's figures).  The GPU propagator is checked on the whole curve in tests/test_gpu_lindblad.py."""
+    import warnings
+    import scipy.sparse.linalg as spl
+    from helpers import load_golden
+    from qsextra_b200 import ChromophoreSystem
+    meta, g = load_golden('heom_example3')
+    W = 4
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        s = ChromophoreSystem(energies=meta['energies'], couplings=meta['coupling'], dipole_moments=[1., 1.],
+                              frequencies_pseudomode=[0.] * W, levels_pseudomode=[2] * W,
+                              couplings_ep=[float(np.sqrt(meta['Gamma'] / W * meta['Omega'] / 2))] * W)
+    prog = LindbladProgram.from_system(s, rates=[2 * meta['Omega']] * W)
+    blk = prog.block(1, 1)
+    gen = prog.generator(blk)
+    rho = np.zeros(blk.size, complex)
+    rho[0] = 1.0                                        # site 0 excited, pseudomodes empty
+    early = spl.expm_multiply(gen, rho, start=0.0, stop=0.15, num=4, endpoint=True)
+    pop0 = [np.real(np.diag(v.reshape(blk.dim_a, blk.dim_b))).reshape(blk.n_a, -1).sum(1)[0] for v in early]
+    assert np.abs(np.array(pop0) - g['rho11'][:4]).max() < 1e-6
+    late = spl.expm_multiply(gen, early[-1], start=0.0, stop=10.5, num=2, endpoint=True)[-1]
+    pop = np.real(np.diag(late.reshape(blk.dim_a, blk.dim_b))).reshape(blk.n_a, -1).sum(1)[0]
+    k = int(np.argmin(np.abs(g['t'] - 10.65)))
+    assert abs(abs(pop - g['rho11'][k]) - 1.225e-2) < 2e-4

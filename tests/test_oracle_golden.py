@@ -146,6 +146,8 @@ def _golden_response_in_c(name, kraus):
     import itertools
     meta, arrays = load_golden(name)
     kw = dict(meta['kwargs'])
+    if 'dt' not in kw:
+        pytest.skip('the C port evolves with one step size (dt given)')
     if kw.get('Trotter_order', 1) != 1 and kraus:
         pytest.skip('Suzuki splitting of the collision gates has no two-gate pattern')
     system = build_system(meta['system'])

@@ -34,7 +34,7 @@ for label in ('gsb', 'se', 'esa'):
     for rep in range(2):
         rows.clear()
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        qspectroscopy(system, spec, verbose=False, **kw)
+        qspectroscopy(system, spec, shots=0, verbose=False, **kw)
         torch.cuda.synchronize(); total = (time.perf_counter() - t0) * 1e3
     print('== %s total %.2f ms (second run), in engine calls %.2f ms' % (label, total, sum(r[1] for r in rows)))
     for name, ms, what in rows:

@@ -23,11 +23,11 @@ kw = dict(dt=DT, coll_rates=[0.2])
 delays = [(15 * DT * np.arange(5)).tolist(), (100 * DT * np.arange(3)).tolist(), (15 * DT * np.arange(7)).tolist()]
 worst = 0.0
 for lab in ('gsb', 'se', 'esa'):
-    sharded = qspectroscopy(s, FeynmanDiagram(lab, delays), verbose=False, **kw)
+    sharded = qspectroscopy(s, FeynmanDiagram(lab, delays), shots=0, verbose=False, **kw)
     # single-rank reference: temporarily pretend there is no process group
     w = qdist.world
     qdist.world = lambda: (0, 1)
-    alone = qspectroscopy(s, FeynmanDiagram(lab, delays), verbose=False, **kw)
+    alone = qspectroscopy(s, FeynmanDiagram(lab, delays), shots=0, verbose=False, **kw)
     qdist.world = w
     worst = max(worst, float(np.abs(sharded - alone).max()))
 rng = np.random.default_rng(0)
@@ -54,7 +54,7 @@ w = qdist.world
 qdist.world = lambda: (0, 1)
 for k, member in enumerate(members):
     for d, spec in enumerate(specs):
-        alone = qspectroscopy(member, spec, verbose=False, **kw)
+        alone = qspectroscopy(member, spec, shots=0, verbose=False, **kw)
         worst = max(worst, float(np.abs(together[d][k] - alone).max()))
 qdist.world = w
 flag = torch.tensor([worst], device='cuda')

@@ -11,5 +11,5 @@ if len(sys.argv) > 2:
     delays = [delays[0][:n1], delays[1][:n2], delays[2]]
 spec = FeynmanDiagram(sys.argv[3] if len(sys.argv) > 3 else 'esa', [np.asarray(d).tolist() for d in delays])
 torch.cuda.synchronize(); t0 = time.perf_counter()
-sig = qspectroscopy(system, spec, verbose=False, **kw)
+sig = qspectroscopy(system, spec, shots=0, verbose=False, **kw)
 torch.cuda.synchronize(); print('ms', (time.perf_counter() - t0) * 1e3, float(np.abs(sig).sum()))

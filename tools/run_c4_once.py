@@ -10,6 +10,6 @@ delays = [np.asarray(d).tolist() for d in delays]
 specs = [FeynmanDiagram(l, delays) for l in ('gsb', 'se', 'esa')]
 for rep in range(2):
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    sigs = [qspectroscopy(system, sp, verbose=False, **kw) for sp in specs]
+    sigs = [qspectroscopy(system, sp, shots=0, verbose=False, **kw) for sp in specs]
     torch.cuda.synchronize()
     print('run %d: %.1f ms, checksum %.9f' % (rep, (time.perf_counter() - t0) * 1e3, sum(float(np.abs(s).sum()) for s in sigs)))

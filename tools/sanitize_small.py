@@ -26,7 +26,7 @@ for system, kw in ((chain(2), dict(coll_rates=[0.2])),            # RR static
                    (chain(3, modes=False), dict(coll_rates=0.1)),  # pass program / op list
                    (chain(2, d=3), dict(coll_rates=[0.2]))):      # op list with ancilla + reset
     for lab in ('gsb', 'esa'):
-        sig = qspectroscopy(system, FeynmanDiagram(lab, [t, [0., DT], t]), verbose=False, dt=DT, **kw)
+        sig = qspectroscopy(system, FeynmanDiagram(lab, [t, [0., DT], t]), shots=0, verbose=False, dt=DT, **kw)
         out.append(float(np.abs(sig).sum()))
     system.set_state('localized excitation', 0)
     out.append(float(qevolve(system, t, shots=0, dt=DT, verbose=False, **kw).populations.sum()))

@@ -11,7 +11,7 @@ delays = [np.asarray(d).tolist() for d in delays]
 specs = [FeynmanDiagram(l, delays) for l in ('gsb', 'se', 'esa')]
 for rep in range(5):
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    sigs = [qspectroscopy(system, sp, verbose=False, device_output=True, **kw) for sp in specs]
+    sigs = [qspectroscopy(system, sp, shots=0, verbose=False, device_output=True, **kw) for sp in specs]
     torch.cuda.synchronize(); t1 = time.perf_counter()
     total = torch.zeros((), dtype=torch.float64, device='cuda')
     for sp, sig in zip(specs, sigs):
@@ -36,7 +36,7 @@ for rep in range(4):
     marks = []
     for sp in specs:
         ta = time.perf_counter()
-        sig = qspectroscopy(system, sp, verbose=False, device_output=True, **kw)
+        sig = qspectroscopy(system, sp, shots=0, verbose=False, device_output=True, **kw)
         tb = time.perf_counter()
         for idx in range(len(delays[1])):
             _, spectrum = postprocessing(sp, sig, RF_freq=1.5, damping_rate=0.005, pad_extension=3, T2_index=idx)

@@ -11,7 +11,7 @@ def run(device_output, sync_each):
     torch.cuda.synchronize(); t0 = time.perf_counter(); per = []
     for sp in specs:
         t1 = time.perf_counter()
-        s = qspectroscopy(system, sp, verbose=False, device_output=device_output, **kw)
+        s = qspectroscopy(system, sp, shots=0, verbose=False, device_output=device_output, **kw)
         if sync_each: torch.cuda.synchronize()
         per.append((time.perf_counter() - t1) * 1e3)
     torch.cuda.synchronize()
