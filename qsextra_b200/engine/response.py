@@ -170,13 +170,84 @@ def _unique_delays(step_counts, continuous):
     return uniq, inverse
 
 
+class ResponsePlan:
+    """The device work of ``response_function_set`` for ONE (program, dipoles, diagrams, delay grid), captured in a
+    CUDA graph: every propagation, dipole application and read-out product of the tree, on the main and the side
+    streams, becomes one ``cudaGraphLaunch`` (a C4 evaluation is ~30 launches on 4 streams; enqueueing them from Python
+    costs more than their critical path).  The graph ends with the rank-local signal rows; the gather over ranks and
+    the reshaping to the caller's grid stay outside it.  Tables the tree uploads are kept resident by the plan."""
+
+    def __init__(self, graph, local, infos, uploads, launches):
+        self.graph, self.local, self.infos, self.uploads, self.launches = graph, local, infos, uploads, launches
+
+    @classmethod
+    def build(cls, eng, program, mu, sequences, step_counts):
+        """Warm pass (fills the upload memo, loads modules, sizes the allocator), then the captured pass."""
+        eng._memo = {}
+        try:
+            _set_local(eng, program, mu, sequences, step_counts)
+            torch.cuda.synchronize(eng.device)
+            before = eng.launches
+            graph = torch.cuda.CUDAGraph()
+            eng._capturing = True
+            with torch.cuda.graph(graph):
+                local, infos = _set_local(eng, program, mu, sequences, step_counts)
+            return cls(graph, local, infos, eng._memo, eng.launches - before)
+        finally:
+            eng._memo, eng._capturing = None, False
+
+    def run(self, eng, device_output: bool):
+        """Replay -> list of signals (fresh tensors / arrays: the graph's own output buffers are reused by the next
+        replay)."""
+        self.graph.replay()
+        eng.launches += self.launches
+        return [_finish(eng, out.clone() if device_output and not info['sharded'] else out, info, device_output)
+                for out, info in zip(self.local, self.infos)]
+
+
+def plan_key(program, mu, sequences, step_counts):
+    rank, size = qdist.world()
+    return (_fingerprint(program), np.asarray(mu, dtype=float).tobytes(), tuple((a, b) for a, b in sequences),
+            tuple(np.asarray(c).tobytes() for c in step_counts), rank, size)
+
+
 def response_function_set(program: StepProgram, mu, sequences, step_counts, engine=None, device_output: bool = False):
     """Several diagrams ``sequences = [(side_seq, direction_seq), ...]`` of the same system on the same delay grid (the
     contributions of one 2-D spectrum).  All distinct read-out propagations are enqueued first, each on its own side
     stream, so the longest one (the two-exciton block of esa) runs while the shorter diagrams are evaluated; the delay
-    levels the diagrams have in common are computed once (``shared`` of ``response_function``).  -> list of signals."""
+    levels the diagrams have in common are computed once (``shared`` of ``response_function``).  -> list of signals.
+
+    The second evaluation of the same content on a GPU builds a ``ResponsePlan`` (CUDA graph); later ones replay it
+    (``QSX_DISABLE_GRAPH`` switches this off)."""
     from .runtime import get_engine
     eng = engine or get_engine()
+    continuous = bool(getattr(program, 'continuous', False))
+    on_gpu = eng.device.type == 'cuda'
+    if on_gpu and not continuous and not os.environ.get('QSX_DISABLE_GRAPH') and hasattr(eng, 'plans'):
+        key = plan_key(program, mu, sequences, step_counts)
+        plan = eng.plans.get(key)
+        if plan is None and key not in eng.plans:
+            seen = eng.plan_seen[key] = eng.plan_seen.get(key, 0) + 1
+            if len(eng.plan_seen) > 64:
+                eng.plan_seen.clear()
+            if seen >= 2:
+                try:
+                    plan = ResponsePlan.build(eng, program, mu, sequences, step_counts)
+                except Exception as exc:                  # not capturable (e.g. the streaming path synchronises): stay eager
+                    import warnings
+                    warnings.warn('response tree not captured in a CUDA graph: {!r}'.format(exc))
+                    plan = None
+                if len(eng.plans) >= 8:
+                    eng.plans.pop(next(iter(eng.plans)))
+                eng.plans[key] = plan
+        if plan is not None:
+            return plan.run(eng, device_output)
+    local, infos = _set_local(eng, program, mu, sequences, step_counts)
+    return [_finish(eng, out, info, device_output) for out, info in zip(local, infos)]
+
+
+def _set_local(eng, program, mu, sequences, step_counts):
+    """Enqueue the whole tree of a set of diagrams; -> (rank-local signal rows per diagram, bookkeeping per diagram)."""
     continuous = bool(getattr(program, 'continuous', False))
     uniq, _ = _unique_delays(step_counts, continuous)
     rank, size = qdist.world()
@@ -197,13 +268,9 @@ def response_function_set(program: StepProgram, mu, sequences, step_counts, engi
         if got is not None:
             shared[key] = got
     # every diagram is enqueued before any result is read back: one synchronisation at the end instead of one per diagram
-    on_gpu = eng.device.type == 'cuda'
-    signals = [response_function(program, mu, side_seq, direction_seq, step_counts, engine=eng,
-                                 device_output=device_output or on_gpu, shared=shared)
-               for side_seq, direction_seq in sequences]
-    if device_output or not on_gpu:
-        return signals
-    return [eng.to_host(signal) for signal in signals]
+    pairs = [_response_local(program, mu, side_seq, direction_seq, step_counts, eng, shared)
+             for side_seq, direction_seq in sequences]
+    return [p[0] for p in pairs], [p[1] for p in pairs]
 
 
 def response_function(program: StepProgram, mu, side_seq: str, direction_seq: str, step_counts, engine=None,
@@ -217,9 +284,18 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
     ``shared``: a dict the caller passes to successive calls for diagrams of the SAME system, parameters and delay
     grid (e.g. gsb, se and esa of one 2-D spectrum).  Levels whose interaction prefix and delays coincide (all three
     rephasing diagrams share the t1 level, se and esa also the t2 level) and read-outs of the same final block are
-    then computed once and kept on the device in it.  A dict filled for another program raises ``ValueError``."""
+    then computed once and kept on the device in it.  A dict filled for another program raises ``ValueError``.
+"""
     from .runtime import get_engine
     eng = engine or get_engine()
+    out, info = _response_local(program, mu, side_seq, direction_seq, step_counts, eng, shared)
+    return _finish(eng, out, info, device_output)
+
+
+def _response_local(program: StepProgram, mu, side_seq: str, direction_seq: str, step_counts, eng,
+                    shared: dict | None = None):
+    """Enqueue the tree of one diagram; -> (rank-local signal rows, bookkeeping for ``_finish``: gather over the
+    ranks, caller's delay order, host copy).  Arguments as ``response_function``."""
     n_sites = program.n_sites
     plan = interaction_plan(side_seq, direction_seq)
     if len(plan) != len(step_counts) + 1:
@@ -339,22 +415,30 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
             shared[prefix_key(level)] = (sigma, n_global, sharded, shard_units, rows_per_unit, inst_set)
 
     lead = [n_sets] if n_sets > 1 else []               # ensembles: one signal per parameter set
+    info = dict(lead=lead, shape=shape, uniq_len=[len(u) for u in uniq], inverse=inverse, zero=zero, sharded=sharded,
+                shard_units=shard_units, rows_per_unit=rows_per_unit)
     if zero:
-        if device_output:
-            return torch.zeros(lead + shape, dtype=torch.complex128, device=eng.device)
-        return np.zeros(lead + shape, dtype=complex)
-    if sharded:
-        out = qdist.all_gather_rows(out, shard_units, rows_per_unit)
+        out = torch.zeros(lead + shape, dtype=torch.complex128, device=eng.device)
+    return out, info
+
+
+def _finish(eng, out, info, device_output: bool):
+    """Rank-local rows -> the signal on the caller's delay grid (one all-gather when the tree was sharded)."""
+    lead, shape, inverse, uniq_len = info['lead'], info['shape'], info['inverse'], info['uniq_len']
+    if info['zero']:
+        return out if device_output else out.cpu().numpy()
+    if info['sharded']:
+        out = qdist.all_gather_rows(out, info['shard_units'], info['rows_per_unit'])
     skip = len(lead)
     if device_output:
-        table = out.reshape(lead + [len(u) for u in uniq])
+        table = out.reshape(lead + uniq_len)
         for axis, inv in enumerate(inverse):            # back to the caller's order/duplicates, axis by axis
             if len(inv) != table.shape[skip + axis] or np.any(inv != np.arange(len(inv))):
                 table = table.index_select(skip + axis, torch.as_tensor(inv, device=eng.device))
         return table.reshape(lead + shape).contiguous()
-    table = (eng.to_host(out) if hasattr(eng, 'to_host') else out.cpu().numpy()).reshape(lead + [len(u) for u in uniq])
-    if all(len(inv) == len(u) and np.array_equal(inv, np.arange(len(inv))) for inv, u in zip(inverse, uniq)):
+    table = (eng.to_host(out) if hasattr(eng, 'to_host') else out.cpu().numpy()).reshape(lead + uniq_len)
+    if all(len(inv) == n and np.array_equal(inv, np.arange(len(inv))) for inv, n in zip(inverse, uniq_len)):
         return table                                    # delays were ascending and distinct: nothing to reorder
     if lead:
-        return table[np.ix_(np.arange(n_sets), *inverse)].reshape(lead + shape)
+        return table[np.ix_(np.arange(lead[0]), *inverse)].reshape(lead + shape)
     return table[np.ix_(*inverse)].reshape(shape)

@@ -36,6 +36,29 @@ class RRCProgram:
     def threads(self):
         return 1 << (2 * self.n_bits)
 
+    def executed_flops_per_step(self):
+        """(FP64 flops, FP64 instructions) one instance executes per step in ``rrc::evolve_rrc_kernel``, counted from the
+        operation list as the kernel applies it: DIAG = complex multiply per element (2 DMUL + 2 DFMA); HOP on a pair of
+        configurations = (cos, sin) rotation of both elements (4 DMUL + 4 DFMA per pair and partner index); ROT on a
+        participating element = 2 DFMA (tangent form); damping = DMUL + DFMA per component on the quarter of the
+        elements that receives, 2 DMUL on the others."""
+        nt = self.threads
+        flops = instr = 0
+        for kind, a, b, mask, slot in self.ops:
+            if kind == OP_DIAG:
+                n = self.n_a * self.n_b * nt
+                flops, instr = flops + 6 * n, instr + 4 * n
+            elif kind in (OP_HOPK, OP_HOPB):
+                pairs = (self.n_b if kind == OP_HOPK else self.n_a) * nt
+                flops, instr = flops + 12 * pairs, instr + 8 * pairs
+            elif kind in (OP_ROTK, OP_ROTB):
+                n = bin(mask).count('1') * (self.n_b if kind == OP_ROTK else self.n_a) * nt
+                flops, instr = flops + 4 * n, instr + 2 * n
+            else:
+                n = self.n_a * self.n_b * nt
+                flops, instr = flops + (6 * n) // 4 + (2 * n * 3) // 4, instr + (4 * n) // 4 + (2 * n * 3) // 4
+        return flops, instr
+
     def signature(self) -> np.ndarray:
         """Everything the compile-time copy must agree on, as one int32 vector."""
         sig = [self.n_a, self.n_b, self.n_bits] + list(self.ket_pos) + list(self.bra_pos) + [len(self.ops)]

@@ -5,6 +5,7 @@
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 
@@ -46,6 +47,11 @@ class Engine:
         self._recipes: dict = {}              # device copies of parameter recipes, by content
         self._side_stream = None
         self._staging = None                  # pinned read-back buffer (to_host)
+        self.trace = None                     # list of (name, meta, start, stop) while bench.py profiles launches
+        self._memo = None                     # while a response plan is built: uploads by content (see to_device)
+        self._capturing = False
+        self.plans = {}                       # response plans (CUDA graphs) by content key (engine/response.py)
+        self.plan_seen = {}
         self.aux_launches = 0                 # table-assembly kernels (qsx_bind_params, qsx_rr_tables)
         self.launches = 0                     # kernels enqueued through this engine (bench bookkeeping)
         self.h2d_bytes = 0                    # bytes copied host -> device through to_device()
@@ -55,6 +61,20 @@ class Engine:
         self.sm_count, self.smem_optin, self.cc = sm.value, smem.value, cc.value
 
     # ---- helpers --------------------------------------------------------------------------
+    @contextlib.contextmanager
+    def span(self, name: str, **meta):
+        """When ``self.trace`` is a list: CUDA events around one launch on the stream it is enqueued on (bench.py's
+        per-kernel device times; never active inside a captured graph)."""
+        if self.trace is None:
+            yield
+            return
+        stream = torch.cuda.current_stream(self.device)
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(stream)
+        yield
+        stop.record(stream)
+        self.trace.append((name, meta, start, stop))
+
     @property
     def side_stream(self):
         """One extra stream per engine for work that is independent of the main sequence (kept, so that the caching
@@ -89,11 +109,27 @@ class Engine:
         return stage.numpy().reshape(tuple(tensor.shape)).copy()
 
     def to_device(self, array, dtype=None):
-        t = torch.as_tensor(np.ascontiguousarray(array))
+        """Host array -> device tensor.  While a response plan is being built (``_memo`` is a dict) uploads are kept by
+        content: the capture pass of the CUDA graph then finds every table of the warm pass already resident -- a
+        host-to-device copy cannot be captured -- and the plan keeps them alive."""
+        host = np.ascontiguousarray(array)
+        key = None
+        if self._memo is not None:
+            import hashlib
+            key = (host.dtype.str, host.shape, str(dtype), hashlib.blake2b(host.tobytes(), digest_size=16).digest())
+            hit = self._memo.get(key)
+            if hit is not None:
+                return hit
+            if self._capturing:
+                raise cabi.QsxError('an upload the warm pass did not make was requested during graph capture')
+        t = torch.as_tensor(host)
         if dtype is not None:
             t = t.to(dtype)
         self.h2d_bytes += t.numel() * t.element_size()
-        return t.to(self.device, non_blocking=True)
+        out = t.to(self.device, non_blocking=True)
+        if key is not None:
+            self._memo[key] = out
+        return out
 
     def upload_program(self, bound: BoundProgram, program=None, use_rr: bool = True, reg_bits=None):
         """-> dict of device tensors for a bound program (ops + parameter sets).  With ``program`` (the StepProgram
@@ -175,7 +211,12 @@ class Engine:
         if snapshots:
             out_snap = torch.empty((n_inst, n_emit, E), dtype=torch.complex128, device=self.device)
             args.out_snap = out_snap.data_ptr()
-        with torch.cuda.device(self.device):
+        ex_flops, ex_instr = big.executed_flops_per_step()
+        with torch.cuda.device(self.device), self.span(
+                'evolve_rrc ({},{}) {}x{}{}'.format(big.block.ka, big.block.kb, big.block.dim_a, big.block.dim_b,
+                                                   ' transposed' if any(op[0] == 6 for op in big.ops) else ''),
+                instances=n_inst, steps=int(n_steps), elements=E, executed_flops_per_step=ex_flops,
+                fp64_instructions_per_step=ex_instr, threads=big.threads):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             rc = self.lib.qsx_evolve_rrc(C.byref(args), C.c_void_p(stream))
         if rc == cabi.ERR_NO_PROGRAM:
@@ -239,7 +280,11 @@ class Engine:
         if snapshots:
             out_snap = torch.empty((n_inst, n_emit, E), dtype=torch.complex128, device=self.device)
             args.out_snap = out_snap.data_ptr()
-        with torch.cuda.device(self.device):
+        ex_flops, ex_instr = rrp.executed_flops_per_step()
+        with torch.cuda.device(self.device), self.span(
+                'evolve_rr ({},{}) {}x{}'.format(rrp.block.ka, rrp.block.kb, rrp.block.dim_a, rrp.block.dim_b),
+                instances=n_inst, steps=int(n_steps), elements=E, executed_flops_per_step=ex_flops,
+                fp64_instructions_per_step=ex_instr, threads=rrp.team):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             cabi.check(self.lib.qsx_evolve_rr(C.byref(args), C.c_void_p(stream)))
         if n_inst > 0 and n_emit > 0:
@@ -308,7 +353,9 @@ class Engine:
                 workspace = torch.empty(ws_bytes // 8, dtype=torch.float64, device=self.device)
                 args.workspace = workspace.data_ptr()
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            cabi.check(self.lib.qsx_evolve(C.byref(args), C.c_void_p(stream)))
+            with self.span('evolve ({},{}) {}x{}'.format(blk_.ka, blk_.kb, blk_.dim_a, blk_.dim_b), instances=n_inst,
+                           steps=int(n_steps), elements=E):
+                cabi.check(self.lib.qsx_evolve(C.byref(args), C.c_void_p(stream)))
         if n_inst > 0 and n_emit > 0:
             self.launches += 1
         return out_obs, out_snap
@@ -318,7 +365,7 @@ class Engine:
         n_inst = sigma_in.numel() // in_block.size
         out = torch.empty((n_inst, out_block.size), dtype=torch.complex128, device=self.device)
         bi, bo = self.device_block(in_block), self.device_block(out_block)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), self.span('apply_dipole', instances=n_inst, elements=out_block.size):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             cabi.check(self.lib.qsx_apply_dipole(C.byref(bi.c), C.byref(bo.c), side, C.c_void_p(mu.data_ptr()), n_inst,
                                                  C.c_void_p(sigma_in.data_ptr()), C.c_void_p(out.data_ptr()),
@@ -479,10 +526,12 @@ class Engine:
             cabi.check(ws_bytes)
             workspace = torch.empty(ws_bytes // 8, dtype=torch.float64, device=self.device) if ws_bytes else None
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            cabi.check(self.lib.qsx_readout_gemm_batched(n_batch, n_inst, n_emit, E, C.c_void_p(sigma.data_ptr()),
-                                                         C.c_void_p(readouts.data_ptr()), C.c_void_p(out.data_ptr()),
-                                                         C.c_void_p(workspace.data_ptr() if workspace is not None else None),
-                                                         C.c_void_p(stream)))
+            with self.span('readout_gemm {}x{}x{}'.format(n_batch * n_inst, n_emit, E),
+                           flops=8.0 * n_batch * n_inst * n_emit * E):
+                cabi.check(self.lib.qsx_readout_gemm_batched(
+                    n_batch, n_inst, n_emit, E, C.c_void_p(sigma.data_ptr()), C.c_void_p(readouts.data_ptr()),
+                    C.c_void_p(out.data_ptr()), C.c_void_p(workspace.data_ptr() if workspace is not None else None),
+                    C.c_void_p(stream)))
         if n_batch > 0 and n_inst > 0 and n_emit > 0:
             self.launches += 1
         return out

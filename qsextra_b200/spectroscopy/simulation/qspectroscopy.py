@@ -163,8 +163,12 @@ def qspectroscopy(system: ChromophoreSystem | ExcitonicSystem,
     else:
         counts, (dt, dt_trotter, trotter_number, _) = delay_step_counts(spectroscopy.delay_time, dt_in, trotter_in)
         program = _program_for(system, dt, dt_trotter, trotter_number, qevolve_kwds.get('Trotter_order', 1), coll_rates)
-        signal = response_function(program, mu, spectroscopy.side_seq, spectroscopy.direction_seq, counts,
-                                   device_output=device_output, shared=shared)
+        if shared is None:                              # (a one-diagram set: repeated evaluations replay a CUDA graph)
+            signal = response_function_set(program, mu, [(spectroscopy.side_seq, spectroscopy.direction_seq)], counts,
+                                           device_output=device_output)[0]
+        else:
+            signal = response_function(program, mu, spectroscopy.side_seq, spectroscopy.direction_seq, counts,
+                                       device_output=device_output, shared=shared)
         signal = add_estimator_noise(signal, spectroscopy.side_seq, spectroscopy.direction_seq, mu, shots, seed)
     if kept is not None and last >= 0 and last + 1 < kept.size:
         flat, old = signal.reshape(-1), kept.reshape(-1)
@@ -289,37 +293,15 @@ def qspectroscopy_set(system: ChromophoreSystem | ExcitonicSystem,
     return signals
 
 
-def qspectroscopy_ensemble(systems,
-                           spectroscopies,
-                           shots: int = 0,
-                           verbose: bool = True,
-                           device_output: bool = False,
-                           average: bool = False,
-                           **qevolve_kwds,
-                           ) -> list:
-    """The diagrams ``spectroscopies`` for an ENSEMBLE of systems in one batched evaluation (new API: the reference
-    loops ``qspectroscopy`` over realisations by hand, e.g. for static disorder).
-
-    ``systems``: ExcitonicSystem / ChromophoreSystem objects with the same structure (sites, pseudomode levels, which
-    couplings are non-zero) and the same dipole moments; energies, couplings and bath parameters may differ.
-    ``coll_rates``: one value (list) for all members, or one row per member.  The members are the parameter sets of
-    one step program: every level of the response tree holds all of them, each propagates its own read-out, the last
-    level is one batched product (``engine.response``).  Under ``torch.distributed`` the MEMBERS are sharded over the
-    ranks (contiguous slices) and one all-gather assembles the result on every rank.
-    Returns one array per diagram with a leading ensemble axis, ``[len(systems), *grid]`` (``average=True``: the
-    ensemble mean, ``[*grid]``)."""
+def ensemble_program(systems, spectroscopies, **qevolve_kwds):
+    """Checks of ``qspectroscopy_ensemble`` and the objects its evaluation is made of:
+    -> (StepProgram over all members, dipole moments, [(side_seq, direction_seq)], step counts per delay)."""
     from ...engine.program import StepProgram, SystemBatch
     systems, spectroscopies = list(systems), list(spectroscopies)
-    if not systems or not spectroscopies:
-        return []
     for s_ in systems:
         _validate_system(s_)
         if type(s_) is not type(systems[0]):
             raise TypeError('all members of an ensemble must be of the same class')
-    if type(systems[0]) is ChromophoreSystem and systems[0].mode_dict is None:
-        warnings.warn("Pseudomodes not specified. Executing the dynamics with system as an ExcitonicSystem.")
-        return qspectroscopy_ensemble([s_.extract_ExcitonicSystem() for s_ in systems], spectroscopies, shots, verbose,
-                                      device_output, average, **qevolve_kwds)
     for key in _RESERVED:
         qevolve_kwds.pop(key, None)
     unknown = set(qevolve_kwds) - {'Trotter_number', 'Trotter_order', 'dt', 'coll_rates', 'GPU'}
@@ -351,10 +333,46 @@ def qspectroscopy_ensemble(systems,
     counts, (dt, dt_trotter, trotter_number, _) = delay_step_counts(delays, qevolve_kwds['dt'], qevolve_kwds.get('Trotter_number', 1))
     program = StepProgram(SystemBatch.from_systems(systems), dt, trotter_number, qevolve_kwds.get('Trotter_order', 1), rates,
                           dt_trotter=dt_trotter)
-    signals = response_function_set(program, mu, [(sp.side_seq, sp.direction_seq) for sp in spectroscopies], counts,
-                                    device_output=device_output)
+    return program, mu, [(sp.side_seq, sp.direction_seq) for sp in spectroscopies], counts
+
+
+def qspectroscopy_ensemble(systems,
+                           spectroscopies,
+                           shots: int = 0,
+                           verbose: bool = True,
+                           device_output: bool = False,
+                           average: bool = False,
+                           seed: int | None = None,
+                           **qevolve_kwds,
+                           ) -> list:
+    """The diagrams ``spectroscopies`` for an ENSEMBLE of systems in one batched evaluation (new API: the reference
+    loops ``qspectroscopy`` over realisations by hand, e.g. for static disorder).
+
+    ``systems``: ExcitonicSystem / ChromophoreSystem objects with the same structure (sites, pseudomode levels, which
+    couplings are non-zero) and the same dipole moments; energies, couplings and bath parameters may differ.
+    ``coll_rates``: one value (list) for all members, or one row per member.  The members are the parameter sets of
+    one step program: every level of the response tree holds all of them, each propagates its own read-out, the last
+    level is one batched product (``engine.response``).  Under ``torch.distributed`` the MEMBERS are sharded over the
+    ranks (contiguous slices) and one all-gather assembles the result on every rank.
+    Returns one array per diagram with a leading ensemble axis, ``[len(systems), *grid]`` (``average=True``: the
+    ensemble mean, ``[*grid]``)."""
+    systems, spectroscopies = list(systems), list(spectroscopies)
+    if not systems or not spectroscopies:
+        return []
+    if type(systems[0]) is ChromophoreSystem and systems[0].mode_dict is None:
+        for s_ in systems:
+            _validate_system(s_)
+        warnings.warn("Pseudomodes not specified. Executing the dynamics with system as an ExcitonicSystem.")
+        return qspectroscopy_ensemble([s_.extract_ExcitonicSystem() for s_ in systems], spectroscopies, shots, verbose,
+                                      device_output, average, seed, **qevolve_kwds)
+    program, mu, sequences, counts = ensemble_program(systems, spectroscopies, **qevolve_kwds)
+    B = len(systems)
+    signals = response_function_set(program, mu, sequences, counts, device_output=device_output)
     if B == 1:                                          # a one-member ensemble still carries the ensemble axis
         signals = [sig[None] for sig in signals]
+    if shots:                                           # every member is its own set of estimator runs
+        signals = [add_estimator_noise(sig, a, b, mu, shots, None if seed is None else seed + k)
+                   for k, ((a, b), sig) in enumerate(zip(sequences, signals))]
     if average:
         signals = [sig.mean(0) for sig in signals]
     ending_sentence(verbose)
