@@ -91,7 +91,7 @@ def test_trimer_two_excitons_vs_oracle(engine):
     dt = 0.5
     spec = FeynmanDiagram('esa', [[0., 2., 1.], [1., 0.], [0., 3., 3.]])
     kw = dict(dt=dt, coll_rates=[0.2])
-    close(qspectroscopy(s, spec, verbose=False, **kw), R.qspectroscopy_operator(s, spec, **kw))
+    close(qspectroscopy(s, spec, shots=0, verbose=False, **kw), R.qspectroscopy_operator(s, spec, **kw))
 
 
 def test_restart_from_reference_checkpoint(engine, tmp_path, monkeypatch):
@@ -197,11 +197,11 @@ def test_diagrams_of_one_spectrum_share_their_common_levels(engine):
     delays = [(dt * 3 * np.arange(6)).tolist(), (dt * 5 * np.arange(3)).tolist(), (dt * 3 * np.arange(7)).tolist()]
     kw = dict(shots=0, verbose=False, dt=dt, coll_rates=[0.2])
     before = engine.launches
-    alone = {lab: qspectroscopy(s, FeynmanDiagram(lab, delays), shots=0, **kw) for lab in ('gsb', 'se', 'esa')}
+    alone = {lab: qspectroscopy(s, FeynmanDiagram(lab, delays), **kw) for lab in ('gsb', 'se', 'esa')}
     launches_alone = engine.launches - before
     shared = {}
     before = engine.launches
-    together = {lab: qspectroscopy(s, FeynmanDiagram(lab, delays), shots=0, shared=shared, **kw) for lab in ('gsb', 'se', 'esa')}
+    together = {lab: qspectroscopy(s, FeynmanDiagram(lab, delays), shared=shared, **kw) for lab in ('gsb', 'se', 'esa')}
     launches_together = engine.launches - before
     for lab in alone:
         assert np.array_equal(alone[lab], together[lab]), lab
@@ -209,7 +209,7 @@ def test_diagrams_of_one_spectrum_share_their_common_levels(engine):
     other = ChromophoreSystem(energies=[1.55, 1.50, 1.46, 1.53], couplings=J, dipole_moments=[1., 0.8, -0.6, 1.1],
                               frequencies_pseudomode=0.02, levels_pseudomode=2, couplings_ep=0.054)
     with pytest.raises(ValueError, match='shared dict'):
-        qspectroscopy(other, FeynmanDiagram('gsb', delays), shots=0, shared=shared, **kw)
+        qspectroscopy(other, FeynmanDiagram('gsb', delays), shared=shared, **kw)
     # the set API: read-outs of all diagrams enqueued up front
     from qsextra_b200.spectroscopy import qspectroscopy_set
     as_set = qspectroscopy_set(s, [FeynmanDiagram(lab, delays) for lab in ('gsb', 'se', 'esa')], **kw)
