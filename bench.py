@@ -1,16 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- headline measurement of the hot path on B200 (contract: see DESIGN.md "Measurement").
+"""bench.py -- headline measurement of the hot path on B200 (contract: DESIGN.md "Measurement").
 
-Workload (BASELINE.json configs[1], "C2"): non-Markovian dimers, one 2-level pseudomode per site, 1000 collision
-steps, a batch of 4096 parameter sets PER GPU (weak scaling), populations written after every step
-([4096, 1001, 2] float64).  One bench "step" = one pass of the hot path over that batch.
+Workload (BASELINE.json configs[3], "C4", the north-star target): the 2-D electronic spectrum of the 4-chromophore
+chain with one 2-level pseudomode per site on the 128 x 16 x 128 (t1, t2, t3) delay grid, the three rephasing diagrams
+gsb + se + esa, for MEMBERS static-disorder realisations of the aggregate PER GPU (member 0 is the unperturbed BASELINE
+system; 2-D spectra are always averaged over such realisations).  One bench "step" = one evaluation of all members'
+signals: 3 x 128 x 16 x 128 grid points per member.  Members are sharded over the ranks (weak scaling) and ONE all-gather
+over NCCL assembles every member's signal on every rank -- inside the timed region.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--members M]
 
-metric = collision steps per second (whole job).  `value` is timed with CUDA events around the K launches with
-all inputs resident in HBM (L2 flushed between launches, outside the event pairs); `e2e` goes through the public
-API `qevolve_batch` from host arrays to a pinned host result.  `--impl reference` times the CPU oracle port
-(oracle/csrc/qsx_oracle.c, all host cores) on a bounded sample of the same workload.
+metric = 2DES grid points per second (whole job).  `value`: CUDA events around the K evaluations (the response tree as
+a CUDA graph + the gather), step program and parameter tables resident in HBM, L2 flushed between evaluations outside
+the event pairs.  `e2e`: the public API `qspectroscopy_ensemble` from host objects (new realisations every step, so every
+table is lowered and uploaded again) to the signals in pinned host memory.  `--impl reference`: the CPU oracle port
+(oracle/csrc/qsx_oracle.c, all host cores) on a bounded sample of the same grid with the grid-average cost per point.
+Other BASELINE configurations are reported as extras of the same line: `collision_steps` (configs[1], C2, with its own
+roofline), `spectroscopy` (configs[2] C3; C4 as ONE system = the latency of a single spectrum; strong scaling of it).
 """
 import argparse
 import json
@@ -27,106 +33,129 @@ sys.path.insert(0, REPO)
 
 HBAR = 0.658212
 DT = 0.1 / HBAR
+GAMMA = 59.08e-3
+METRIC = 'grid_points_per_sec'
+UNIT = 'grid points/s'
+N_T1, N_T2, N_T3 = 128, 16, 128
+DIAGRAMS = ('gsb', 'se', 'esa')
+POINTS_PER_MEMBER = len(DIAGRAMS) * N_T1 * N_T2 * N_T3
+DISORDER_EV = 0.01
+# C2 (extra block)
 N_SETS = 4096
 N_STEPS = 1000
-METRIC = 'collision_steps_per_sec'
-UNIT = 'steps/s'
-
-
-def c2_parameters(n_sets, seed=0):
-    """SURVEY.md 8(d) C2: eps~U(1.4,1.6), J~U(-.05,.05), omega~U(.01,.2), Gamma~U(.02,.1), Omega~U(.05,.2),
-    g = sqrt(Gamma Omega / 2), rate = 2 Omega."""
-    rng = np.random.default_rng(seed)
-    eps = rng.uniform(1.4, 1.6, (n_sets, 2))
-    J = rng.uniform(-0.05, 0.05, n_sets)
-    omega = rng.uniform(0.01, 0.2, n_sets)
-    Gamma = rng.uniform(0.02, 0.1, n_sets)
-    Omega = rng.uniform(0.05, 0.2, n_sets)
-    coup = np.zeros((n_sets, 2, 2))
-    coup[:, 0, 1] = coup[:, 1, 0] = J
-    return dict(energies=eps, couplings=coup, dipole_moments=np.ones((n_sets, 2)), omega=omega[:, None],
-                coupl_ep=np.sqrt(Gamma * Omega / 2)[:, None], rates=(2 * Omega)[:, None])
-
-
-def algorithmic_flops_per_step(n_sites=2, n_modes=1, stored_elements=64):
-    """F_step = E (6 n_Z + 12 n_R + 2.5 n_AD) for the d=2 pseudomode step, E = stored elements of
-    the block (1-exciton sector of the dimer: 8 x 8)."""
-    n_z = n_sites + n_sites * n_modes
-    n_r = 2 * (n_sites * (n_sites - 1) // 2) + 2 * n_sites * n_modes
-    n_ad = n_sites * n_modes
-    return stored_elements * (6 * n_z + 12 * n_r + 2.5 * n_ad)
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU reference arm (oracle port)
+# workloads
 # ------------------------------------------------------------------------------------------------
-def cpu_systems(params, lo, hi):
+def c4_delays(n3=N_T3):
+    return [(15 * DT * np.arange(N_T1)).tolist(), (100 * DT * np.arange(N_T2)).tolist(), (15 * DT * np.arange(n3)).tolist()]
+
+
+def c4_member(delta=None):
+    """4-site chain, eps = [1.55, 1.50, 1.46, 1.52], J = -0.01 between neighbours, mu = 1, one 2-level
+    pseudomode per site (omega 0.02, Gamma 59.08e-3, Omega 0.1, g = sqrt(Gamma Omega / 2), rate 0.2); ``delta``: site-energy
+    shifts of a disorder realisation."""
     import warnings
     from qsextra_b200 import ChromophoreSystem
-    out, rates = [], []
+    J = np.zeros((4, 4))
+    for i in range(3):
+        J[i, i + 1] = J[i + 1, i] = -0.01
+    eps = np.array([1.55, 1.50, 1.46, 1.52]) + (0.0 if delta is None else np.asarray(delta))
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
-        for b in range(lo, hi):
-            s = ChromophoreSystem(energies=params['energies'][b].tolist(), couplings=float(params['couplings'][b, 0, 1]),
-                                  dipole_moments=[1., 1.], frequencies_pseudomode=float(params['omega'][b, 0]),
-                                  levels_pseudomode=2, couplings_ep=float(params['coupl_ep'][b, 0]))
-            s.set_state('localized excitation', 0)
-            out.append(s)
-            rates.append([float(params['rates'][b, 0])])
-    return out, np.array(rates)
+        return ChromophoreSystem(energies=eps.tolist(), couplings=J, dipole_moments=[1., 1., 1., 1.],
+                                 frequencies_pseudomode=0.02, levels_pseudomode=2, couplings_ep=float(np.sqrt(GAMMA * 0.1 / 2)))
 
 
-def cpu_sample(params, n_sample, n_steps=N_STEPS, keep=None):
-    """Time the C oracle on the first n_sample parameter sets; -> (steps/s, threads, seconds).  ``keep`` (a list)
-    receives the populations it computed, so that the GPU result of the same sets can be compared with them."""
+def c4_members(n_total, seed=0):
+    """Global ensemble: member 0 (with seed 0) is the unperturbed system, the others carry Gaussian site-energy disorder."""
+    rng = np.random.default_rng(seed)
+    deltas = rng.normal(0.0, DISORDER_EV, (n_total, 4))
+    if seed == 0:
+        deltas[0] = 0.0
+    return [c4_member(d) for d in deltas]
+
+
+def c4_specs(n3=N_T3):
+    from qsextra_b200.spectroscopy import FeynmanDiagram
+    return [FeynmanDiagram(lab, c4_delays(n3)) for lab in DIAGRAMS]
+
+
+def workload_config(n_gpus, members):
+    return dict(workload='C4: 2DES of the 4-chromophore chain with one 2-level pseudomode per site, {} x {} x {} (t1, t2, t3) '
+                         'grid, gsb + se + esa, {} static-disorder realisation(s) of the aggregate per GPU (member 0 = the '
+                         'BASELINE system)'.format(N_T1, N_T2, N_T3, members),
+                grid=[N_T1, N_T2, N_T3], diagrams=list(DIAGRAMS), members_per_gpu=members, global_members=members * n_gpus,
+                grid_points_per_member=POINTS_PER_MEMBER, disorder_sigma_eV=DISORDER_EV,
+                sharding='members over ranks (contiguous), one all_gather_into_tensor of the signals inside the timed region',
+                cache='L2 flushed (256 MiB write) between timed evaluations, outside the event pairs',
+                reference_arm_sample='rows of the same grid with the grid-average cost per point, one row per host thread '
+                                     'and bench step (see cpu_baseline.sample)')
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (oracle port): a bounded sample with the grid-average cost per point
+# ------------------------------------------------------------------------------------------------
+CPU_ROW = (16, 2)           # n1 = 240, n2 = 200 steps
+CPU_T3 = 32                 # first 32 t3 values: 465 more steps -> 905 steps per 32 points = 28.3 steps per point;
+                            # the oracle's algorithm over the full grid: (952 + 750 + 1905) / 128 = 28.2 steps per point
+
+
+def cpu_rows(n_threads):
+    return [(CPU_ROW[0] + (k % 5) - 2, CPU_ROW[1]) for k in range(n_threads)]
+
+
+def cpu_sample(diagrams=DIAGRAMS, n_threads=None):
+    """Time the C oracle (full-space literal gates, one (t1, t2) row per thread, shared prefix along t3) on
+    ``n_threads`` rows per diagram.  -> (grid points/s, threads, seconds, description)."""
     from oracle import fast
-    systems, rates = cpu_systems(params, 0, n_sample)
-    time_grid = np.arange(n_steps + 1) * DT
-    fast.populations_batch(systems[:2], time_grid[:3], dt=DT, coll_rates=rates[:2])      # load + warm
+    from qsextra_b200.spectroscopy import FeynmanDiagram
+    n_threads = n_threads or os.cpu_count() or 1
+    system = c4_member()
+    rows = cpu_rows(n_threads)
+    points, used = 0, 1
     t0 = time.perf_counter()
-    pops, threads = fast.populations_batch(systems, time_grid, dt=DT, coll_rates=rates, n_threads=os.cpu_count() or 1)
+    for lab in diagrams:
+        sig, used = fast.response_points(system, FeynmanDiagram(lab, c4_delays(CPU_T3)), rows, DT, coll_rates=[0.2],
+                                         kraus=True, n_threads=n_threads)
+        points += sig.size
     sec = time.perf_counter() - t0
-    if keep is not None:
-        keep.append(pops)
-    return n_sample * n_steps / sec, threads, sec
+    what = ('{} rows (t1 index {}..{}, t2 index {}) x first {} t3 values x {} of the C4 grid: {} points, ~905 collision '
+            'steps per 32 points = the grid-average 28 steps per point of the oracle algorithm (one chain per (t1, t2), '
+            'prefix shared along t3); C oracle port, full-space literal gate list with the collisions as channels, one '
+            'row per thread, {:.1f} s'.format(len(rows), CPU_ROW[0] - 2, CPU_ROW[0] + 2, CPU_ROW[1], CPU_T3,
+                                            '+'.join(diagrams), points, sec))
+    return points / sec, used, sec, what
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    params = c2_parameters(N_SETS)
-    n_sample = 128
-    cpu_sample(params, 8, 50)
-    for _ in range(args.warmup):
-        cpu_sample(params, 16, 100)
+    n_threads = os.cpu_count() or 1
+    cpu_sample(('gsb',), min(2, n_threads))                    # load the library, touch the code paths
+    for w in range(args.warmup):
+        cpu_sample((DIAGRAMS[w % 3],), n_threads)
     t0 = time.perf_counter()
-    threads = 1
-    for _ in range(args.steps):
-        _, threads, _ = cpu_sample(params, n_sample)
+    points = 0.0
+    used, what = 1, ''
+    for k in range(args.steps):
+        rate, used, sec, what = cpu_sample((DIAGRAMS[k % 3],), n_threads)
+        points += rate * sec
     sec = time.perf_counter() - t0
-    value = args.steps * n_sample * N_STEPS / sec
-    sample = '{} of {} parameter sets x {} steps per bench step (C oracle port, full-space literal gates, OpenMP)'.format(
-        n_sample, N_SETS, N_STEPS)
+    value = points / sec
     line = dict(impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=1e3 * sec / args.steps, higher_is_better=True, scaling='weak',
-                vs_baseline=None, dtype='f64', data='synthetic',
-                config=workload_config(args.gpus),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind='port', sample=sample),
+                warmup=args.warmup, ms_per_step=1e3 * sec / max(args.steps, 1), higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='f64', data='synthetic', config=workload_config(args.gpus, args.members),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=used, kind='port',
+                                  sample='per bench step (diagram rotating gsb, se, esa): ' + what),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
-
-
-def workload_config(n_gpus):
-    return dict(workload='C2: qcomo qevolve, non-Markovian dimer, 1 two-level pseudomode/site, {} collision steps, '
-                         '{} parameter sets per GPU, populations after every step'.format(N_STEPS, N_SETS),
-                parameter_sets_per_gpu=N_SETS, collision_steps=N_STEPS, global_parameter_sets=N_SETS * n_gpus,
-                sharding='parameter sets over ranks, no data-path collective',
-                cache='L2 flushed (256 MiB write) between timed launches, outside the event pairs')
+    print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
-# GPU arm
+# GPU arm helpers
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi sampling (every 20 ms) started BEFORE the warm-up; `stop(t0, t1)` keeps the samples whose timestamps
@@ -183,100 +212,303 @@ class ClockSampler:
                     samples=len(inside), window=where, reasons=reasons)
 
 
-def spectroscopy_extras(world, rank, barrier):
-    """BASELINE metric part 1, '2DES grid points/sec': full C3 (dimer, 64 x 64, t2 = 0, the three rephasing and the
-    three non-rephasing pathways) and full C4 (4-site chain with
-    pseudomodes, 128 x 128 x 16) grids, three rephasing diagrams each, through the public qspectroscopy API (delay-grid
-    chains sharded over the ranks, one all-gather).  Wall-clock with synchronisation on both sides, max over ranks by the
-    barrier.  Reported next to the headline line; not part of the timed K steps."""
-    import warnings
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
+    except (OSError, ValueError):
+        return {}
+
+
+def ncu_traffic(kernel_key):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture of this workload (profiles/), or
+    None when the capture of the current round does not hold it."""
+    try:
+        table = json.load(open(os.path.join(REPO, 'profiles', 'ncu_traffic.json')))
+    except (OSError, ValueError):
+        return None, None
+    hit = table.get(kernel_key)
+    return (hit.get('dram_bytes_per_launch'), hit.get('source')) if hit else (None, None)
+
+
+def survey_flops_per_step(n_sites, n_modes, stored_elements, n_bonds):
+    """F_step = E (6 n_Z + 12 n_R + 2.5 n_AD) for the d = 2 pseudomode step (un-fused gate list)."""
+    n_z = n_sites + n_sites * n_modes
+    n_r = 2 * n_bonds + 2 * n_sites * n_modes
+    n_ad = n_sites * n_modes
+    return stored_elements * (6 * n_z + 12 * n_r + 2.5 * n_ad)
+
+
+def trace_table(trace, t_ref):
+    """[(name, meta, start, stop)] -> per-launch rows and per-kernel sums (device times from the CUDA events)."""
+    rows = []
+    for name, meta, start, stop in trace:
+        ms = start.elapsed_time(stop)
+        flops = meta.get('flops')
+        if flops is None and 'executed_flops_per_step' in meta:
+            flops = float(meta['executed_flops_per_step']) * meta['instances'] * meta['steps']
+        rows.append(dict(kernel=name, start_ms=t_ref.elapsed_time(start), ms=ms, executed_flops=flops,
+                         **{k: v for k, v in meta.items() if k in ('instances', 'steps', 'elements', 'threads',
+                                                                    'fp64_instructions_per_step', 'executed_flops_per_step')}))
+    sums = {}
+    for r in rows:
+        s = sums.setdefault(r['kernel'], dict(launches=0, ms=0.0, executed_flops=0.0, fp64_instructions=0.0))
+        s['launches'] += 1
+        s['ms'] += r['ms']
+        s['executed_flops'] += r['executed_flops'] or 0.0
+        if 'fp64_instructions_per_step' in r:
+            s['fp64_instructions'] += float(r['fp64_instructions_per_step']) * r['instances'] * r['steps']
+    return rows, sums
+
+
+# ------------------------------------------------------------------------------------------------
+# extras: BASELINE configs[1] (C2, collision steps/s) with its own roofline
+# ------------------------------------------------------------------------------------------------
+def c2_parameters(n_sets, seed=0):
+    """SURVEY.md 8(d) C2: eps~U(1.4,1.6), J~U(-.05,.05), omega~U(.01,.2), Gamma~U(.02,.1), Omega~U(.05,.2),
+    g = sqrt(Gamma Omega / 2), rate = 2 Omega."""
+    rng = np.random.default_rng(seed)
+    eps = rng.uniform(1.4, 1.6, (n_sets, 2))
+    J = rng.uniform(-0.05, 0.05, n_sets)
+    omega = rng.uniform(0.01, 0.2, n_sets)
+    Gamma = rng.uniform(0.02, 0.1, n_sets)
+    Omega = rng.uniform(0.05, 0.2, n_sets)
+    coup = np.zeros((n_sets, 2, 2))
+    coup[:, 0, 1] = coup[:, 1, 0] = J
+    return dict(energies=eps, couplings=coup, dipole_moments=np.ones((n_sets, 2)), omega=omega[:, None],
+                coupl_ep=np.sqrt(Gamma * Omega / 2)[:, None], rates=(2 * Omega)[:, None])
+
+
+def collision_steps_block(eng, world, rank, barrier, fp64_peak, sm_clock_hz, repeats=20):
+    """configs[1]: 4096 parameter sets per GPU x 1000 collision steps of the non-Markovian dimer, populations after
+    every step.  Device-timed rate, end-to-end rate through ``qevolve_batch`` and the roofline of its kernel."""
     import torch
-    from qsextra_b200 import ChromophoreSystem, ExcitonicSystem
-    from qsextra_b200.spectroscopy import FeynmanDiagram, Spectroscopy, qspectroscopy, qspectroscopy_set
-    gamma = 59.08e-3
-    out = {}
+    import torch.distributed as dist
+    from qsextra_b200.engine.program import StepProgram, SystemBatch
+    from qsextra_b200.engine.sectors import population_observables
+    from qsextra_b200.qcomo import qevolve_batch
+    params = c2_parameters(N_SETS * world)
+    lo, hi = rank * N_SETS, (rank + 1) * N_SETS
+    batch = SystemBatch(params['energies'][lo:hi], params['couplings'][lo:hi], params['dipole_moments'][lo:hi],
+                        params['omega'][lo:hi], params['coupl_ep'][lo:hi], (2,))
+    program = StepProgram(batch, DT, 1, 1, params['rates'][lo:hi])
+    block = program.block(1, 1)
+    bound = program.bind(block)
+    dev = eng.upload_program(bound, program)
+    sigma0 = torch.zeros((1, block.size), dtype=torch.complex128, device=eng.device)
+    sigma0[0, 0] = 1.0                                          # |site 0 excited, modes 0>
+    inst_set = torch.arange(N_SETS, dtype=torch.int32, device=eng.device)
+    inst_src = torch.zeros(N_SETS, dtype=torch.int32, device=eng.device)
+    emit = eng.to_device(np.arange(N_STEPS + 1), torch.int32)
+    obs = eng.upload_observables(*population_observables(block), kind='populations')
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
+
+    def hot_path():
+        return eng.evolve(dev, sigma0, N_SETS, N_STEPS, emit, obs=obs, obs_real=True, inst_set=inst_set, inst_src=inst_src)[0]
+
+    for _ in range(5):
+        flush.fill_(1)
+        hot_path()
+    barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(repeats)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(repeats)]
+    for i in range(repeats):
+        flush.fill_(i & 0xff)
+        starts[i].record()
+        hot_path()
+        stops[i].record()
+    barrier()
+    kernel_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
+    t_dev = torch.tensor([sum(kernel_ms)], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    value = repeats * N_SETS * N_STEPS * world / (float(t_dev.item()) * 1e-3)
+    # end to end: host arrays in, pinned host populations out, in chunks so that read-back overlaps the next kernel
+    pinned = torch.empty((N_SETS, N_STEPS + 1, 2), dtype=torch.float64).pin_memory()
+    host_batch = SystemBatch(np.array(batch.energies), np.array(batch.couplings), np.array(batch.dipole_moments),
+                             np.array(batch.omega), np.array(batch.coupl_ep), (2,))
+    time_grid = np.arange(N_STEPS + 1) * DT
+
+    def e2e_once():
+        res = qevolve_batch(host_batch, time_grid, dt=DT, coll_rates=params['rates'][lo:hi], device_output=True, shard=False)
+        pinned.copy_(res, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_once()
+    e2e_once()
+    h2d0 = eng.h2d_bytes
+    barrier()
+    t0 = time.perf_counter()
+    iters = 5
+    for _ in range(iters):
+        e2e_once()
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = iters * N_SETS * N_STEPS * world / float(t_e2e.item())
+    out = dict(metric='collision_steps_per_sec', value=value, unit='steps/s', kernel_ms_per_launch=float(np.mean(kernel_ms)),
+               workload='C2: non-Markovian dimer, 1 two-level pseudomode/site, {} steps, {} parameter sets per GPU, populations '
+                        'after every step'.format(N_STEPS, N_SETS),
+               e2e=dict(value=e2e_value, unit='steps/s', h2d_bytes_per_step=int((eng.h2d_bytes - h2d0) // iters),
+                        d2h_bytes_per_step=int(pinned.numel() * 8),
+                        api='qevolve_batch(SystemBatch of host arrays) -> pinned host tensor'))
+    if rank == 0 and 'rr' in dev:
+        ex_flops, ex_instr = dev['rr'].executed_flops_per_step()
+        per_ms = float(np.mean(kernel_ms))
+        ex_tf = ex_flops * N_SETS * N_STEPS / (per_ms * 1e-3) / 1e12
+        f_step = survey_flops_per_step(2, 1, block.size, 1)
+        traffic, source = ncu_traffic('rr::evolve_rr_static_kernel<0,1>')
+        out['roofline'] = dict(bound='fp64', kernel='rr::evolve_rr_static_kernel<0, 1>', achieved=ex_tf, peak=fp64_peak,
+                               unit='TFLOP/s', frac=ex_tf / fp64_peak if fp64_peak else None,
+                               note='executed flops (operation list of the register-resident kernel, read-outs excluded)',
+                               fp64_pipe_utilisation_estimate=ex_instr * N_SETS * N_STEPS / (per_ms * 1e-3) / (64 * eng.sm_count * sm_clock_hz),
+                               survey_formula=dict(flops_per_collision_step=f_step,
+                                                   achieved=f_step * N_SETS * N_STEPS / (per_ms * 1e-3) / 1e12,
+                                                   note='un-fused gate list of SURVEY 8(d); the kernel executes fewer flops'),
+                               traffic=traffic, traffic_source=source)
+    return out, (params, lo, hi, hot_path)
+
+
+def c2_parity(params, hot_path, n_check=256):
+    """The kernel's populations of the first ``n_check`` parameter sets against the C oracle."""
+    import warnings
+    from oracle import fast
+    from qsextra_b200 import ChromophoreSystem
+    systems, rates = [], []
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
-        dimer = ExcitonicSystem(energies=[1.55, 1.46], couplings=-0.01, dipole_moments=[1., 1.])
-        J = np.zeros((4, 4))
-        for i in range(3):
-            J[i, i + 1] = J[i + 1, i] = -0.01
-        chain = ChromophoreSystem(energies=[1.55, 1.50, 1.46, 1.52], couplings=J, dipole_moments=[1., 1., 1., 1.],
-                                  frequencies_pseudomode=0.02, levels_pseudomode=2, couplings_ep=float(np.sqrt(gamma * 0.1 / 2)))
-        configs = {'C3_dimer_64x1x64_6pathways': (dimer, dict(dt=DT, coll_rates=gamma / 4),
-                                        [(30 * DT * np.arange(64)).tolist(), [0.], (30 * DT * np.arange(64)).tolist()]),
-                   'C4_chain4_pseudomodes_128x16x128': (chain, dict(dt=DT, coll_rates=[0.2]),
-                                                        [(15 * DT * np.arange(128)).tolist(), (100 * DT * np.arange(16)).tolist(),
-                                                         (15 * DT * np.arange(128)).tolist()])}
-        for name, (system, kw, delays) in configs.items():
-            try:
-                specs = [FeynmanDiagram(lab, delays) for lab in ('gsb', 'se', 'esa')]
-                if name.startswith('C3'):                       # config 2 asks for the non-rephasing pathways as well
-                    for sides, directions in (('kkkk', 'ioio'), ('kbbk', 'iioo'), ('kbkk', 'iiio')):
-                        extra = Spectroscopy(delays)
-                        extra.side_seq, extra.direction_seq = sides, directions
-                        specs.append(extra)
-                for sp in specs:
-                    qspectroscopy(system, sp, shots=0, verbose=False, **kw)              # warm-up (module loads, caches)
-                def timed(run, repeats=3):
-                    """Median wall-clock of ``repeats`` evaluations (each between barriers) and the last result."""
-                    samples, result = [], None
-                    for _ in range(repeats):
-                        barrier()
-                        t_start = time.perf_counter()
-                        result = run()
-                        barrier()
-                        samples.append(time.perf_counter() - t_start)
-                    return sorted(samples)[len(samples) // 2], samples, result
+        for b in range(n_check):
+            s = ChromophoreSystem(energies=params['energies'][b].tolist(), couplings=float(params['couplings'][b, 0, 1]),
+                                  dipole_moments=[1., 1.], frequencies_pseudomode=float(params['omega'][b, 0]),
+                                  levels_pseudomode=2, couplings_ep=float(params['coupl_ep'][b, 0]))
+            s.set_state('localized excitation', 0)
+            systems.append(s)
+            rates.append([float(params['rates'][b, 0])])
+    pops, _ = fast.populations_batch(systems, np.arange(N_STEPS + 1) * DT, dt=DT, coll_rates=np.array(rates),
+                                     n_threads=os.cpu_count() or 1)
+    got = hot_path()[:n_check].cpu().numpy()
+    return float(np.abs(got - pops).max())
 
-                sec, samples, sigs = timed(lambda: [qspectroscopy(system, sp, shots=0, verbose=False, **kw) for sp in specs])
-                points = len(specs) * int(np.prod([len(d) for d in delays]))
-                out[name] = dict(grid_points=points, seconds=sec, grid_points_per_s=points / sec, warmup_runs=1,
-                                 samples_s=samples, checksum=float(sum(np.abs(s_).sum() for s_ in sigs)))
-                # the same diagrams through qspectroscopy_set: common delay levels once, every read-out propagation
-                # enqueued up front (nothing of the runs above is reused: the sharing lives inside the call)
-                sec, samples, sigs = timed(lambda: qspectroscopy_set(system, specs, verbose=False, **kw))
-                out[name]['as_one_set'] = dict(seconds=sec, grid_points_per_s=points / sec, api='qspectroscopy_set',
-                                               samples_s=samples,
-                                               checksum=float(sum(np.abs(s_).sum() for s_ in sigs)))
-                if name.startswith('C4'):
-                    # the full 2-D spectra (every t2 slice, pad_extension 3) with the signal kept on the device from
-                    # the simulation to the transformed spectrum; only the spectra's checksum comes back to the host
-                    from qsextra_b200.spectroscopy.postprocessing import postprocessing
-                    import torch as _torch
-                    warm = qspectroscopy(system, specs[0], shots=0, verbose=False, device_output=True, **kw)
-                    float(postprocessing(specs[0], warm, pad_extension=3)[1].abs().sum())   # cuFFT plans, lazy module loads
-                    barrier()
-                    t0 = time.perf_counter()
-                    total = _torch.zeros((), dtype=_torch.float64, device='cuda')
-                    for sp in specs:
-                        sig = qspectroscopy(system, sp, shots=0, verbose=False, device_output=True, **kw)
-                        for idx in range(len(delays[1])):
-                            _, spectrum = postprocessing(sp, sig, RF_freq=1.5, damping_rate=0.005, pad_extension=3, T2_index=idx)
-                            total += spectrum.abs().sum()
-                    total = float(total)                                     # one device-to-host read at the end
-                    barrier()
-                    sec = time.perf_counter() - t0
-                    out[name]['with_spectra'] = dict(seconds=sec, spectra=3 * len(delays[1]), shape=list(spectrum.shape),
-                                                     grid_points_per_s=points / sec, checksum=float(total))
-                    # the whole pipeline with the batched entry points: one set call, then all t2 slices per diagram
-                    from qsextra_b200.spectroscopy.postprocessing import postprocessing_all_T2
 
-                    def pipeline():
-                        signals = qspectroscopy_set(system, specs, verbose=False, device_output=True, **kw)
-                        acc = _torch.zeros((), dtype=_torch.float64, device='cuda')
-                        for sp, sig in zip(specs, signals):
-                            acc += postprocessing_all_T2(sp, sig, RF_freq=1.5, damping_rate=0.005, pad_extension=3)[1].abs().sum()
-                        return float(acc)
+# ------------------------------------------------------------------------------------------------
+# extras: the other spectroscopy configurations, C4 as ONE system (latency), strong scaling of it
+# ------------------------------------------------------------------------------------------------
+def spectroscopy_extras(world, rank, barrier):
+    import warnings
+    import torch
+    from qsextra_b200 import ExcitonicSystem
+    from qsextra_b200.spectroscopy import FeynmanDiagram, Spectroscopy, qspectroscopy, qspectroscopy_set
+    from qsextra_b200.spectroscopy.postprocessing import postprocessing_all_T2
+    out = {}
 
-                    pipeline()
-                    sec, samples, total = timed(pipeline)
-                    out[name]['set_with_spectra'] = dict(seconds=sec, samples_s=samples, spectra=3 * len(delays[1]),
-                                                         grid_points_per_s=points / sec, checksum=total,
-                                                         api='qspectroscopy_set + postprocessing_all_T2')
-            except Exception as exc:                                              # keep the headline line alive
-                out[name] = dict(error=repr(exc))
+    def timed(run, repeats=5):
+        """Median wall-clock of ``repeats`` evaluations (each between barriers) and the last result."""
+        samples, result = [], None
+        for _ in range(repeats):
+            barrier()
+            t_start = time.perf_counter()
+            result = run()
+            barrier()
+            samples.append(time.perf_counter() - t_start)
+        return sorted(samples)[len(samples) // 2], samples, result
+
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        try:
+            dimer = ExcitonicSystem(energies=[1.55, 1.46], couplings=-0.01, dipole_moments=[1., 1.])
+            grid = (30 * DT * np.arange(64)).tolist()
+            delays = [grid, [0.], grid]
+            specs = [FeynmanDiagram(lab, delays) for lab in DIAGRAMS]
+            for sides, directions in (('kkkk', 'ioio'), ('kbbk', 'iioo'), ('kbkk', 'iiio')):
+                extra = Spectroscopy(delays)
+                extra.side_seq, extra.direction_seq = sides, directions
+                specs.append(extra)
+            kw = dict(dt=DT, coll_rates=GAMMA / 4)
+            for _ in range(3):
+                qspectroscopy_set(dimer, specs, verbose=False, **kw)
+            sec, samples, sigs = timed(lambda: qspectroscopy_set(dimer, specs, verbose=False, **kw))
+            points = len(specs) * 64 * 64
+            out['C3_dimer_64x1x64_6pathways'] = dict(grid_points=points, seconds=sec, grid_points_per_s=points / sec,
+                                                     api='qspectroscopy_set', samples_s=samples,
+                                                     checksum=float(sum(np.abs(s_).sum() for s_ in sigs)))
+        except Exception as exc:                                              # keep the headline line alive
+            out['C3_dimer_64x1x64_6pathways'] = dict(error=repr(exc))
+        try:
+            chain = c4_member()
+            specs = c4_specs()
+            kw = dict(dt=DT, coll_rates=[0.2])
+            t_first = time.perf_counter()
+            qspectroscopy_set(chain, specs, verbose=False, **kw)
+            first = time.perf_counter() - t_first
+            for _ in range(2):
+                qspectroscopy_set(chain, specs, verbose=False, **kw)
+            sec, samples, sigs = timed(lambda: qspectroscopy_set(chain, specs, verbose=False, **kw))
+            entry = dict(grid_points=POINTS_PER_MEMBER, seconds=sec, grid_points_per_s=POINTS_PER_MEMBER / sec,
+                         api='qspectroscopy_set (host objects -> NumPy signals; chains of the ONE system sharded over the '
+                             'ranks, one all-gather: strong scaling)', samples_s=samples, first_call_s=first,
+                         checksum=float(sum(np.abs(s_).sum() for s_ in sigs)))
+
+            def pipeline():
+                signals = qspectroscopy_set(chain, specs, verbose=False, device_output=True, **kw)
+                acc = torch.zeros((), dtype=torch.float64, device='cuda')
+                for sp, sig in zip(specs, signals):
+                    acc += postprocessing_all_T2(sp, sig, RF_freq=1.5, damping_rate=0.005, pad_extension=3)[1].abs().sum()
+                return float(acc)
+
+            pipeline()
+            sec, samples, total = timed(pipeline)
+            entry['with_all_48_spectra'] = dict(seconds=sec, samples_s=samples, spectra=3 * N_T2, checksum=total,
+                                                grid_points_per_s=POINTS_PER_MEMBER / sec,
+                                                api='qspectroscopy_set(device_output=True) + postprocessing_all_T2 '
+                                                    '(zero-padded 384 x 384 2-D spectra, cuFFT)')
+            out['C4_one_system_128x16x128'] = entry
+        except Exception as exc:
+            out['C4_one_system_128x16x128'] = dict(error=repr(exc))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def c4_parity(signals_dev, members):
+    """The timed evaluation's signals against the C oracle on whole t3 rows: member 0 (the BASELINE system) on the far
+    corners and random interior rows, member 1 (a disordered realisation) on two rows.  Runs the six oracle calls
+    concurrently (the library releases the GIL).  -> dict."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import fast
+    rng = np.random.default_rng(7)
+    rows0 = [(127, 15), (127, 0), (0, 15), (0, 0)] + [(int(a), int(b)) for a, b in zip(rng.integers(1, 127, 4), rng.integers(1, 15, 4))]
+    rows1 = [(127, 15), (int(rng.integers(1, 127)), int(rng.integers(1, 15)))]
+    specs = c4_specs()
+    jobs = []
+    for d, spec in enumerate(specs):
+        jobs.append((d, 0, rows0))
+        if len(members) > 1:
+            jobs.append((d, 1, rows1))
+
+    def run(job):
+        d, m, rows = job
+        ref, _ = fast.response_points(members[m], specs[d], rows, DT, coll_rates=[0.2], kraus=True, n_threads=len(rows))
+        return ref
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(len(jobs)) as pool:
+        refs = list(pool.map(run, jobs))
+    sec = time.perf_counter() - t0
+    worst_rel, worst_abs, n_points, worst_local = 0.0, 0.0, 0, 0.0
+    for (d, m, rows), ref in zip(jobs, refs):
+        sig = signals_dev[d][m] if signals_dev[d].dim() == 4 else signals_dev[d]
+        scale = float(sig.abs().max())
+        got = np.array([sig[i, j].cpu().numpy() for i, j in rows])
+        err = np.abs(got - ref)
+        worst_abs = max(worst_abs, float(err.max()))
+        worst_rel = max(worst_rel, float(err.max()) / scale)
+        worst_local = max(worst_local, float((err.max(axis=1) / np.abs(ref).max(axis=1)).max()))
+        n_points += ref.size
+    return dict(max_rel_err=worst_rel, max_abs_err=worst_abs, max_err_relative_to_each_row=worst_local, points=n_points,
+                rows_member0=rows0, rows_member1=rows1 if len(members) > 1 else [],
+                includes=['(127,15,127)', '(127,0,0)', '(0,15,127)', '(0,0,0)'], oracle_seconds=sec,
+                note='whole t3 rows (128 points each) per diagram; relative = max |gpu - oracle| / max |signal of the diagram|')
 
 
 def run_ours(args):
@@ -287,34 +519,23 @@ def run_ours(args):
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    from qsextra_b200.engine.program import StepProgram, SystemBatch
+    from qsextra_b200.engine import response as R
     from qsextra_b200.engine.runtime import get_engine
-    from qsextra_b200.engine.sectors import population_observables
-    from qsextra_b200.qcomo import qevolve_batch
+    from qsextra_b200.spectroscopy import qspectroscopy_ensemble
+    from qsextra_b200.spectroscopy.simulation.qspectroscopy import ensemble_program
 
     eng = get_engine()
-    params = c2_parameters(N_SETS * world)                      # global batch; this rank owns a contiguous slice
-    lo, hi = rank * N_SETS, (rank + 1) * N_SETS
-    batch = SystemBatch(params['energies'][lo:hi], params['couplings'][lo:hi], params['dipole_moments'][lo:hi],
-                        params['omega'][lo:hi], params['coupl_ep'][lo:hi], (2,))
-    program = StepProgram(batch, DT, 1, 1, params['rates'][lo:hi])
-    block = program.block(1, 1)
-    bound = program.bind(block)
-    dev = eng.upload_program(bound, program)
-    sigma0 = torch.zeros((1, block.size), dtype=torch.complex128, device=eng.device)
-    site0 = (0 << block.n_bits) * block.dim_b + (0 << block.n_bits)    # |cfg 0 (site 0 excited), modes 0>
-    sigma0[0, site0] = 1.0
-    inst_set = torch.arange(N_SETS, dtype=torch.int32, device=eng.device)
-    inst_src = torch.zeros(N_SETS, dtype=torch.int32, device=eng.device)
-    emit = eng.to_device(np.arange(N_STEPS + 1), torch.int32)
-    obs = eng.upload_observables(*population_observables(block), kind='populations')
+    M = args.members
+    members = c4_members(M * world)                             # global ensemble; ranks own contiguous slices of it
+    specs = c4_specs()
+    kw = dict(dt=DT, coll_rates=[0.2])
+    program, mu, sequences, counts = ensemble_program(members, specs, **kw)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
 
     def hot_path():
-        return eng.evolve(dev, sigma0, N_SETS, N_STEPS, emit, obs=obs, obs_real=True, inst_set=inst_set,
-                          inst_src=inst_src)[0]
+        """All members' signals on the device: the response tree (CUDA graph from the third call on) + the gather."""
+        return R.response_function_set(program, mu, sequences, counts, engine=eng, device_output=True)
 
     def barrier():
         torch.cuda.synchronize()
@@ -322,17 +543,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    out = None
     sampler = ClockSampler(local_rank)
     sampler.wait_for_first_sample()
-    warm_until = time.time() + 0.5                  # at least W steps and half a second under load before timing
+    warm_until = time.time() + 0.5                  # at least W (>= 3) steps and half a second under load before timing
     n_warm = 0
+    signals = None
     while n_warm < max(args.warmup, 3) or time.time() < warm_until:
         flush.fill_(1)
-        out = hot_path()
+        signals = hot_path()
         n_warm += 1
-        if n_warm % 16 == 0:
-            torch.cuda.synchronize()
     barrier()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -343,149 +562,159 @@ def run_ours(args):
     for i in range(args.steps):
         flush.fill_(i & 0xff)
         starts[i].record()
-        out = hot_path()
+        signals = hot_path()
         stops[i].record()
     barrier()
     wall = time.perf_counter() - wall0
     launches = eng.launches - launches0
     clocks = sampler.stop(t_region0, time.time())
-    kernel_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
-    t_dev = torch.tensor([sum(kernel_ms)], dtype=torch.float64, device=eng.device)
+    step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
+    t_dev = torch.tensor([sum(step_ms)], dtype=torch.float64, device=eng.device)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     total_ms = float(t_dev.item())
-    steps_done = args.steps * N_SETS * N_STEPS * world
-    value = steps_done / (total_ms * 1e-3)
+    points_per_step = POINTS_PER_MEMBER * M * world
+    value = args.steps * points_per_step / (total_ms * 1e-3)
+    uses_graph = any(p is not None for p in eng.plans.values())
 
-    timed_output = out.cpu().numpy() if rank == 0 else None            # compared with the cpu_baseline run below
+    # ---- one traced evaluation: device time of every launch (CUDA events on the launching streams), the gather ----
+    eng.trace = []
+    t_ref = torch.cuda.Event(enable_timing=True)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_ref.record()
+    local_rows, infos = R._set_local(eng, program, mu, sequences, counts)
+    g0.record()
+    traced = [R._finish(eng, o, info, True) for o, info in zip(local_rows, infos)]
+    g1.record()
+    barrier()
+    trace, eng.trace = eng.trace, None
+    launch_rows, kernel_sums = trace_table(trace, t_ref)
+    traced_ms = t_ref.elapsed_time(g1)
+    gather_ms = g0.elapsed_time(g1)
+    t_g = torch.tensor([gather_ms], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(t_g, op=dist.ReduceOp.MAX)
+    gather_ms = float(t_g.item())
+    del traced
 
-    # ---- end to end through the public API: host arrays in, pinned host populations out ----------------------
-    pinned = torch.empty((N_SETS, N_STEPS + 1, 2), dtype=torch.float64).pin_memory()
-    host_batch = SystemBatch(np.array(batch.energies), np.array(batch.couplings), np.array(batch.dipole_moments),
-                             np.array(batch.omega), np.array(batch.coupl_ep), (2,))
-    time_grid = np.arange(N_STEPS + 1) * DT
-    world_was = world
+    # ---- end to end through the public API: host objects in (new realisations every step), pinned host signals out ---
+    lo, hi = rank * M, (rank + 1) * M
+    pinned = [torch.empty((M, N_T1, N_T2, N_T3), dtype=torch.complex128).pin_memory() for _ in DIAGRAMS]
 
-    def e2e_once():
-        # per-rank call on this rank's own parameter sets (no gather: weak scaling, independent units)
-        res = qevolve_batch(host_batch, time_grid, dt=DT, coll_rates=params['rates'][lo:hi], device_output=True,
-                            shard=False)
-        pinned.copy_(res, non_blocking=True)
+    def e2e_once(seed):
+        fresh = c4_members(M * world, seed=seed)
+        sigs = qspectroscopy_ensemble(fresh, specs, shots=0, verbose=False, device_output=True, **kw)
+        for buf, sig in zip(pinned, sigs):                       # every rank reads back its own members: together the
+            buf.copy_(sig[lo:hi], non_blocking=True)            # complete result is in host memory once
         torch.cuda.synchronize()
 
-    e2e_once()
+    e2e_once(100)
     h2d0 = eng.h2d_bytes
+    e2e_iters = max(1, min(args.steps, 5))
     barrier()
     t0 = time.perf_counter()
-    e2e_iters = max(1, min(args.steps, 5))
-    for _ in range(e2e_iters):
-        e2e_once()
+    for k in range(e2e_iters):
+        e2e_once(101 + k)
     barrier()
-    e2e_sec = time.perf_counter() - t0
-    h2d = (eng.h2d_bytes - h2d0) // e2e_iters
-    t_e2e = torch.tensor([e2e_sec], dtype=torch.float64, device=eng.device)
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=eng.device)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = e2e_iters * N_SETS * N_STEPS * world_was / float(t_e2e.item())
+    e2e_value = e2e_iters * points_per_step / float(t_e2e.item())
+    h2d = (eng.h2d_bytes - h2d0) // e2e_iters
 
-    spectro = spectroscopy_extras(world, rank, barrier) if not args.no_spectroscopy else None
+    fp64_peak = eng.fp64_peak(5) if rank == 0 else None
+    sm_clock = (clocks.get('sm_mhz') or 1965.0) * 1e6
+    fp64_peak_all = torch.tensor([fp64_peak or 0.0], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.broadcast(fp64_peak_all, 0)
+    extras_c2 = extras_spec = None
+    c2_state = None
+    if not args.no_extras:
+        extras_c2, c2_state = collision_steps_block(eng, world, rank, barrier, float(fp64_peak_all.item()), sm_clock)
+        extras_spec = spectroscopy_extras(world, rank, barrier)
 
     if rank == 0:
-        fp64_peak = eng.fp64_peak(5)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
-        except OSError:
-            pass
-        f_step = algorithmic_flops_per_step(2, 1, block.size)
-        executed = None
-        if 'rr' in dev:
-            ex_flops, ex_instr = dev['rr'].executed_flops_per_step()
-            ex_tf = ex_flops * N_SETS * N_STEPS / (float(np.mean(kernel_ms)) * 1e-3) / 1e12
-            # FP64 pipe: 64 lanes per clock and SM; every DFMA / DMUL / DADD occupies one lane-slot
-            sm_clock = (clocks.get('sm_mhz') or 1965.0) * 1e6
-            pipe = ex_instr * N_SETS * N_STEPS / (float(np.mean(kernel_ms)) * 1e-3) / (64 * eng.sm_count * sm_clock)
-            executed = dict(flops_per_collision_step=ex_flops, fp64_instructions_per_collision_step=ex_instr,
-                            achieved=ex_tf, unit='TFLOP/s', frac_of_dfma_peak=ex_tf / fp64_peak if fp64_peak else None,
-                            fp64_pipe_utilisation_estimate=pipe,
-                            note='flops the register-resident kernel executes, counted from its operation list '
-                                 '(read-outs excluded); the SURVEY formula above counts the un-fused gate list')
-        # The BASELINE batch (4096 sets = 512 warps) leaves the GPU latency-bound; the same kernel on a 16 x larger batch
-        # of the same distribution shows its own rate (reported next to, never instead of, the BASELINE configuration).
-        saturated = None
-        if 'rr' in dev:
-            big_n = 16 * N_SETS
-            bp = c2_parameters(big_n)
-            bb = SystemBatch(bp['energies'], bp['couplings'], bp['dipole_moments'], bp['omega'], bp['coupl_ep'], (2,))
-            bprog = StepProgram(bb, DT, 1, 1, bp['rates'])
-            bdev = eng.upload_program(bprog.bind(block, fused=False), bprog)
-            b_set = torch.arange(big_n, dtype=torch.int32, device=eng.device)
-            b_src = torch.zeros(big_n, dtype=torch.int32, device=eng.device)
-            times = []
-            for rep in range(4):
-                flush.fill_(rep)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                eng.evolve(bdev, sigma0, big_n, N_STEPS, emit, obs=obs, obs_real=True, inst_set=b_set, inst_src=b_src)
-                e1.record()
-                torch.cuda.synchronize()
-                times.append(e0.elapsed_time(e1))
-            big_ms = sorted(times[1:])[1]
-            big_rate = big_n * N_STEPS / (big_ms * 1e-3)
-            saturated = dict(parameter_sets=big_n, kernel_ms_per_launch=big_ms, steps_per_s=big_rate,
-                             achieved=f_step * big_rate / 1e12, frac=f_step * big_rate / 1e12 / fp64_peak if fp64_peak else None,
-                             executed_achieved=ex_flops * big_rate / 1e12,
-                             executed_frac_of_dfma_peak=ex_flops * big_rate / 1e12 / fp64_peak if fp64_peak else None,
-                             fp64_pipe_utilisation_estimate=ex_instr * big_rate / (64 * eng.sm_count * sm_clock),
-                             note='same kernel, 16 x the BASELINE batch per GPU: enough warps to hide the latencies')
-            del bdev, b_set, b_src
-        per_launch_flops = f_step * N_SETS * N_STEPS
-        per_launch_ms = float(np.mean(kernel_ms))
-        achieved = per_launch_flops / (per_launch_ms * 1e-3) / 1e12
-        out_bytes = N_SETS * (N_STEPS + 1) * 2 * 8
-        in_bytes = bound.params.nbytes + block.size * 16
+        peaks = measured_peaks()
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
-        cpu_baseline = parity = None
+        # dominant kernel of the step = largest device time in the traced evaluation
+        dom_name = max(kernel_sums, key=lambda k: kernel_sums[k]['ms'])
+        dom = kernel_sums[dom_name]
+        dom_rows = [r for r in launch_rows if r['kernel'] == dom_name]
+        dom_tf = dom['executed_flops'] / (dom['ms'] * 1e-3) / 1e12 if dom['ms'] else 0.0
+        total_flops = sum(s['executed_flops'] for s in kernel_sums.values())
+        busy_ms = sum(s['ms'] for s in kernel_sums.values())
+        mean_step_ms = float(np.mean(step_ms))
+        traffic, traffic_source = ncu_traffic(dom_name)
+        blk = program.block(1, 1)
+        f_step = survey_flops_per_step(4, 1, blk.size, 3)
+        inst_steps = sum(r['instances'] * r['steps'] for r in dom_rows if 'instances' in r)
+        roofline = dict(
+            bound='fp64', kernel=dom_name + ' (CTA-wide register-resident kernel: t2 level of se / esa, all members)',
+            achieved=dom_tf, peak=fp64_peak, unit='TFLOP/s', frac=dom_tf / fp64_peak if fp64_peak else None,
+            traffic=traffic, traffic_source=traffic_source,
+            what='executed FP64 flops of the kernel (counted from its operation list, RRCProgram.executed_flops_per_step) '
+                 '/ its launch durations (CUDA events on the launching stream, traced evaluation of the same step)',
+            peak_source='qsx_fp64_peak DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)',
+            launches_per_step=dom['launches'], kernel_ms_per_step=dom['ms'], share_of_step=dom['ms'] / traced_ms,
+            instance_steps_per_step=inst_steps,
+            fp64_pipe_utilisation_estimate=dom['fp64_instructions'] / (dom['ms'] * 1e-3) / (64 * eng.sm_count * sm_clock) if dom['ms'] else None,
+            survey_formula=dict(flops_per_collision_step=f_step,
+                                achieved=f_step * inst_steps / (dom['ms'] * 1e-3) / 1e12 if dom['ms'] else None,
+                                note='SURVEY 8(d) counts the un-fused gate list on the (1,1) block; the kernel executes '
+                                     'fewer flops by exact algebra, so this figure can exceed the peak'),
+            whole_step=dict(executed_flops=total_flops, ms=mean_step_ms, achieved=total_flops / (mean_step_ms * 1e-3) / 1e12,
+                            frac=total_flops / (mean_step_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
+                            kernel_busy_ms_summed_over_streams=busy_ms, traced_step_ms=traced_ms,
+                            note='all launches of one evaluation (evolutions, dipoles, read-out products)'),
+            kernels={k: dict(launches=v['launches'], ms=v['ms'],
+                             tflops=v['executed_flops'] / (v['ms'] * 1e-3) / 1e12 if v['ms'] and v['executed_flops'] else None)
+                     for k, v in sorted(kernel_sums.items(), key=lambda kv: -kv[1]['ms'])},
+            hbm=dict(peak=hbm_peak, unit='GB/s', peak_source='MEASURED_PEAKS.json' if peaks else 'fallback',
+                     note='the states stay on chip during a propagation; HBM carries the snapshots between levels'))
+        cpu_baseline = parity = c2_err = None
         if world == 1:                                  # reported on rank 0 at N = 1 only
-            kept = []
-            cpu_value, cpu_threads, cpu_sec = cpu_sample(params, N_SETS, keep=kept)
-            parity = float(np.abs(timed_output - kept[0]).max())    # the timed kernel's output vs the CPU baseline's
-            cpu_baseline = dict(value=cpu_value, unit=UNIT, cores=cpu_threads, kind='port',
-                                sample='all %d parameter sets x %d steps (the whole workload of one bench step), C oracle '
-                                       'port (full-space literal gates, OpenMP), %.1f s' % (N_SETS, N_STEPS, cpu_sec))
+            rate, used, sec, what = cpu_sample()
+            cpu_baseline = dict(value=rate, unit=UNIT, cores=used, kind='port', sample=what)
+            parity = c4_parity(signals, members)
+            if c2_state is not None:
+                c2_err = c2_parity(c2_state[0], c2_state[3])
+                extras_c2['parity_max_abs_err_vs_oracle'] = c2_err
+                extras_c2['parity_sets_checked'] = 256
+        if args.trace_out:
+            json.dump(dict(launches=launch_rows, traced_step_ms=traced_ms, gather_ms=gather_ms), open(args.trace_out, 'w'), indent=1)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=total_ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-                    dtype='f64', data='synthetic', config=workload_config(world),
-                    clocks=clocks, gpu_launches=launches,
-                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(pinned.numel() * 8),
-                             api='qsextra_b200.qcomo.qevolve_batch(SystemBatch of host arrays) -> pinned host tensor'),
-                    roofline=dict(bound='fp64', kernel='rr::evolve_rr_static_kernel<0, 1> (register-resident, compile-time program)', achieved=achieved, peak=fp64_peak,
-                                  unit='TFLOP/s', frac=achieved / fp64_peak if fp64_peak else None,
-                                  traffic=18869000, traffic_source='dram__bytes_read.sum + dram__bytes_write.sum of one launch '
-                                  'in profiles/r1_c2_static_rr_kernel.md (ncu --set full); most of the 65.6 MB of read-outs is '
-                                  'still in L2 when the kernel ends',
-                                  peak_source='qsx_fp64_peak DFMA micro-benchmark measured in this run '
-                                              '(MEASURED_PEAKS.json has no FP64 figure)',
-                                  flops_per_collision_step=f_step, flops_per_launch=per_launch_flops,
-                                  kernel_ms_per_launch=per_launch_ms, executed=executed, saturated=saturated,
-                                  hbm=dict(achieved=(in_bytes + out_bytes) / (per_launch_ms * 1e-3) / 1e9, peak=hbm_peak,
-                                           unit='GB/s', algorithmic_bytes_per_launch=in_bytes + out_bytes,
-                                           peak_source='MEASURED_PEAKS.json' if peaks else 'fallback')),
-                    cpu_baseline=cpu_baseline,
-                    parity_max_abs_err_vs_oracle=parity, wall_s_timed_region=wall, spectroscopy=spectro)
-        print(json.dumps(line))
+                    dtype='f64', data='synthetic', config=workload_config(world, M),
+                    clocks=clocks, gpu_launches=launches, cuda_graph=uses_graph,
+                    collective_ms=gather_ms if world > 1 else 0.0,
+                    collective='all_gather_into_tensor of the rank-local signal rows (3 diagrams), measured in the traced '
+                               'evaluation; it is inside every timed step',
+                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d),
+                             d2h_bytes_per_step=int(sum(p.numel() for p in pinned) * 16),
+                             api='qsextra_b200.spectroscopy.qspectroscopy_ensemble(new ChromophoreSystem realisations every '
+                                 'step, FeynmanDiagram x 3) -> signals in pinned host memory (each rank its own members)'),
+                    roofline=roofline, cpu_baseline=cpu_baseline,
+                    parity_max_rel_err_vs_oracle=None if parity is None else parity['max_rel_err'], parity=parity,
+                    wall_s_timed_region=wall, collision_steps=extras_c2, spectroscopy=extras_spec)
+        print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--no-spectroscopy', action='store_true', help='skip the 2DES extras (C3 / C4 grid points per second)')
+    ap.add_argument('--members', type=int, default=8, help='disorder realisations of the C4 aggregate per GPU')
+    ap.add_argument('--no-extras', action='store_true', help='skip the C2 / C3 / single-system extras')
+    ap.add_argument('--no-spectroscopy', action='store_true', help=argparse.SUPPRESS)     # (older name of --no-extras)
+    ap.add_argument('--trace-out', default=None, help='write the per-launch device times of one evaluation to this file')
     args = ap.parse_args()
+    args.no_extras = args.no_extras or args.no_spectroscopy
     if args.impl == 'reference':
         run_reference(args)
     else:
