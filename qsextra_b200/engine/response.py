@@ -34,6 +34,7 @@ import numpy as np
 import torch
 
 from . import dist as qdist
+from . import support as qsupport
 from .program import StepProgram
 from .sectors import Block
 
@@ -208,7 +209,9 @@ class ResponsePlan:
 def plan_key(program, mu, sequences, step_counts):
     rank, size = qdist.world()
     return (_fingerprint(program), np.asarray(mu, dtype=float).tobytes(), tuple((a, b) for a, b in sequences),
-            tuple(np.asarray(c).tobytes() for c in step_counts), rank, size)
+            tuple(np.asarray(c).tobytes() for c in step_counts), rank, size,
+            tuple(os.environ.get(k) for k in ('QSX_DISABLE_BASIS', 'QSX_DISABLE_HEISENBERG', 'QSX_HEISENBERG_MIN',
+                                              'QSX_HEISENBERG_ALWAYS', 'QSX_DISABLE_RR', 'QSX_DISABLE_RRC')))
 
 
 def response_function_set(program: StepProgram, mu, sequences, step_counts, engine=None, device_output: bool = False):
@@ -355,6 +358,10 @@ def _response_local(program: StepProgram, mu, side_seq: str, direction_seq: str,
     sharded = False
     zero = False
     out = None
+    # structural support of the states of the current level (engine/support.py) and the pending basis substitution
+    support = None if continuous else qsupport.ground_support(block)
+    pending = None                                      # dict(coeff [S, n_in, d], rows_in, after_gather) once substituted
+    inst_src = None
     for level, (side, kind) in enumerate(plan[:-1]):
         # ket side: |1><0| sigma raises the ket sector; bra side: sigma |0><1| raises the bra sector
         delta = +1 if kind == 'X' or (kind == 'raise') == (side == 'k') else -1
@@ -365,16 +372,42 @@ def _response_local(program: StepProgram, mu, side_seq: str, direction_seq: str,
             break
         last = level == len(plan) - 2
         if shared is not None and not last and prefix_key(level) in shared:
-            sigma, n_global, sharded, shard_units, rows_per_unit, inst_set = shared[prefix_key(level)]
+            sigma, n_global, sharded, shard_units, rows_per_unit, inst_set, pending, support = shared[prefix_key(level)]
             block, ka, kb = new_block, nka, nkb
             continue
+        # Basis substitution (linearity).  The n_in states per parameter set that enter this level all live on the
+        # `d` elements of their structural support: when n_in clearly exceeds d, the d one-hot basis elements are
+        # propagated instead and the signal is contracted with the coefficients [n_in, d] at the end.
+        inst_src = None
+        if (pending is None and level >= 1 and support is not None and sigma.shape[0] > 0
+                and not os.environ.get('QSX_DISABLE_BASIS')):
+            sup = np.flatnonzero(support.reshape(-1))
+            local_sets = sigma.shape[0] * n_sets // n_global if sharded else n_sets
+            n_in = sigma.shape[0] // max(local_sets, 1)
+            if local_sets > 0 and n_in * 2 >= 3 * len(sup) and (n_sets > 1 or not sharded):
+                d = len(sup)
+                sup_dev = eng.to_device(sup, torch.int64)
+                coeff = sigma.reshape(local_sets, n_in, block.size).index_select(2, sup_dev).contiguous()
+                one_hot = np.zeros((d, block.size), dtype=complex)
+                one_hot[np.arange(d), sup] = 1.0
+                sigma = eng.to_device(one_hot)
+                pending = dict(coeff=coeff, n_in=n_in, d=d, after_gather=False)
+                if n_sets > 1:                          # every set propagates the same d source rows with its own tables
+                    set_ids = inst_set.reshape(local_sets, n_in)[:, 0].contiguous()
+                    inst_set = set_ids.repeat_interleave(d)
+                    inst_src = torch.arange(d, dtype=torch.int32, device=eng.device).repeat(local_sets)
+                    n_global = n_sets * d
+                else:
+                    n_global = d
         if not sharded and size > 1 and (n_global >= size or n_sets > 1):
             lo, hi = qdist.shard_bounds(n_global, rank, size)
             sigma = sigma[lo:hi].contiguous()
             if inst_set is not None:
                 inst_set = inst_set[lo:hi].contiguous()
             sharded, shard_units = True, n_global
-        n_local = sigma.shape[0]
+            if pending is not None:                     # the basis rows of ONE system are what is sharded: contract
+                pending = dict(pending, after_gather=True)                                  # after the gather
+        n_local = sigma.shape[0] if inst_src is None else int(inst_src.numel())
         emit = uniq[level]
         if n_local == 0:                                # a rank without parameter sets (more ranks than sets)
             block, ka, kb = new_block, nka, nkb
@@ -385,19 +418,25 @@ def _response_local(program: StepProgram, mu, side_seq: str, direction_seq: str,
                 rows_per_unit *= len(emit)
             continue
         sigma = eng.apply_dipole(block, new_block, 0 if side == 'k' else 1, mu_dev, sigma)
+        prev_block = block
         block, ka, kb = new_block, nka, nkb
         dev = None if last and readouts is not None else upload(block)
         sets_kw = {} if inst_set is None else dict(inst_set=inst_set)
+        if inst_src is not None:
+            sets_kw['inst_src'] = inst_src
         if level < len(plan) - 2:
             _, snap = propagate(dev, sigma, n_local, emit, snapshots=True, **sets_kw)
             sigma = snap.reshape(n_local * len(emit), block.size)
             if inst_set is not None:
                 inst_set = inst_set.repeat_interleave(len(emit))
+            inst_src = None
         elif readouts is not None:
             if ready is not None:
                 main = torch.cuda.current_stream(eng.device)
                 main.wait_event(ready)
                 readouts.record_stream(main)
+            if inst_src is not None:                    # basis rows shared by the sets: one copy per instance
+                sigma = sigma.index_select(0, inst_src.long())
             if n_sets > 1:                              # whole sets per rank, equally many chains each: batched product
                 local_sets = readouts.shape[0]
                 out = eng.readout_gemm(sigma.reshape(local_sets, n_local // local_sets, block.size).contiguous(),
@@ -411,15 +450,35 @@ def _response_local(program: StepProgram, mu, side_seq: str, direction_seq: str,
         n_global *= len(emit)
         if sharded and level < len(plan) - 2:
             rows_per_unit *= len(emit)
+        if support is not None:
+            support = qsupport.step_closure(program, block, qsupport.dipole_support(support, prev_block, block, side))
         if shared is not None and not last:
-            shared[prefix_key(level)] = (sigma, n_global, sharded, shard_units, rows_per_unit, inst_set)
+            shared[prefix_key(level)] = (sigma, n_global, sharded, shard_units, rows_per_unit, inst_set, pending, support)
 
+    if pending is not None and not pending['after_gather'] and not zero and out is not None and out.shape[0] > 0:
+        out = contract_basis(eng, out, pending)
     lead = [n_sets] if n_sets > 1 else []               # ensembles: one signal per parameter set
     info = dict(lead=lead, shape=shape, uniq_len=[len(u) for u in uniq], inverse=inverse, zero=zero, sharded=sharded,
-                shard_units=shard_units, rows_per_unit=rows_per_unit)
+                shard_units=shard_units, rows_per_unit=rows_per_unit,
+                pending=pending if pending is not None and pending['after_gather'] else None)
     if zero:
         out = torch.zeros(lead + shape, dtype=torch.complex128, device=eng.device)
     return out, info
+
+
+def contract_basis(eng, out, pending):
+    """Rows of ``out`` = (set, basis element b, later delays r) x last delay -> (set, incoming state k, r) x last delay:
+    out[s, k, r, e] = sum_b coeff[s, k, b] out[s, b, r, e]  (one batched product of the read-out kernel, K = d)."""
+    coeff = pending['coeff']                            # [S, n_in, d]
+    n_sets_local, n_in, d = coeff.shape
+    n_last = out.shape[1]
+    per_basis = out.shape[0] // (n_sets_local * d)
+    table = out.reshape(n_sets_local, d, per_basis * n_last).transpose(1, 2).contiguous()      # [S, R, d]
+    if hasattr(eng, 'readout_gemm') and eng.device.type == 'cuda':
+        full = eng.readout_gemm(coeff, table)                                                    # [S, n_in, R]
+    else:
+        full = torch.matmul(coeff, table.transpose(1, 2))
+    return full.reshape(n_sets_local * n_in * per_basis, n_last)
 
 
 def _finish(eng, out, info, device_output: bool):
@@ -429,6 +488,8 @@ def _finish(eng, out, info, device_output: bool):
         return out if device_output else out.cpu().numpy()
     if info['sharded']:
         out = qdist.all_gather_rows(out, info['shard_units'], info['rows_per_unit'])
+    if info.get('pending') is not None:                 # the sharded units were basis rows of one system
+        out = contract_basis(eng, out, info['pending'])
     skip = len(lead)
     if device_output:
         table = out.reshape(lead + uniq_len)

@@ -272,3 +272,29 @@ def test_shots_add_the_estimator_sampling_error(engine):
     assert abs((default - exact).real.std() / (sigma * 2) - 1) < 0.1
     both = qspectroscopy_set(s, [spec], **kw)                 # the set API defaults to exact
     assert np.array_equal(both[0], exact)
+
+
+def test_basis_substitution_on_the_gpu(engine, monkeypatch):
+    """4-site chain with pseudomodes, 80 t1 values: the t2 level propagates the 64 basis elements of the (0,1) block's
+    support instead of 80 chains (engine/support.py); same signal as the chain-by-chain tree and as the oracle rows."""
+    from qsextra_b200 import ChromophoreSystem
+    from qsextra_b200.spectroscopy import FeynmanDiagram, qspectroscopy_set
+    from oracle import fast
+    J = np.zeros((4, 4))
+    for i in range(3):
+        J[i, i + 1] = J[i + 1, i] = -0.01
+    s = ChromophoreSystem(energies=[1.55, 1.50, 1.46, 1.52], couplings=J, dipole_moments=[1., 0.8, -0.6, 1.1],
+                          frequencies_pseudomode=0.02, levels_pseudomode=2, couplings_ep=0.054)
+    dt = 0.15
+    delays = [(dt * 2 * np.arange(80)).tolist(), (dt * 7 * np.arange(3)).tolist(), (dt * 3 * np.arange(9)).tolist()]
+    specs = [FeynmanDiagram(lab, delays) for lab in ('gsb', 'se', 'esa')]
+    kw = dict(verbose=False, dt=dt, coll_rates=[0.2])
+    got = qspectroscopy_set(s, specs, **kw)
+    monkeypatch.setenv('QSX_DISABLE_BASIS', '1')
+    plain = qspectroscopy_set(s, specs, **kw)
+    rows = [(79, 2), (40, 1), (0, 0)]
+    for spec, a, b in zip(specs, got, plain):
+        scale = np.abs(b).max()
+        assert np.abs(a - b).max() < 1e-11 * scale
+        ref, _ = fast.response_points(s, spec, rows, dt, coll_rates=[0.2], kraus=True)
+        assert np.abs(np.array([a[i, j] for i, j in rows]) - ref).max() < 1e-10 * scale

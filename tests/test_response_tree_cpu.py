@@ -221,3 +221,94 @@ def test_ensemble_members_sharded_over_a_gloo_group(tmp_path, size, monkeypatch)
     for r in range(size):
         got = np.load(os.path.join(str(tmp_path), 'e%d.npy' % r))
         assert got.shape == want.shape and np.abs(got - want).max() < 1e-12
+
+
+# ---- basis substitution: many chains entering a level replaced by the basis of their structural support ----------
+_BASIS_DELAYS = [(0.15 * np.arange(14)).tolist(), [0., 0.3, 0.15], [0., 0.45, 0.15, 0.9]]
+
+
+def _basis_case(labels, engine, n_members=1):
+    systems = _ensemble(n_members)
+    return systems, _ensemble_signals(systems, labels, _BASIS_DELAYS, engine)
+
+
+class _CountingEngine(NumpyEngine):
+    def __init__(self):
+        super().__init__()
+        self.instances = []
+
+    def evolve(self, prog, sigma_in, n_inst, *a, **k):
+        self.instances.append(int(n_inst))
+        return super().evolve(prog, sigma_in, n_inst, *a, **k)
+
+
+@pytest.mark.parametrize('heisenberg', [False, True])
+@pytest.mark.parametrize('n_members', [1, 3])
+def test_basis_substitution_equals_chain_by_chain(heisenberg, n_members, monkeypatch):
+    """14 t1 values enter the t2 level of a dimer with pseudomodes; the (0,1) / (1,0) block they live in has a support
+    of 8 elements (the pseudomodes of the ground side stay empty): 8 basis elements are propagated instead of 14
+    chains and the signal is contracted with the coefficients.  Same numbers as the plain tree and as the oracle."""
+    monkeypatch.setenv('QSX_DISABLE_RR', '1')
+    monkeypatch.setenv('QSX_HEISENBERG_MIN', '1' if heisenberg else '1000000')
+    labels = ('gsb', 'se', 'esa')
+    with_basis = _CountingEngine()
+    systems, got = _basis_case(labels, with_basis, n_members)
+    monkeypatch.setenv('QSX_DISABLE_BASIS', '1')
+    plain = _CountingEngine()
+    _, want = _basis_case(labels, plain, n_members)
+    assert max(with_basis.instances) == 8 * 3 * n_members and max(plain.instances) == 14 * 3 * n_members or heisenberg
+    assert sum(with_basis.instances) < sum(plain.instances)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and np.abs(a - b).max() < 1e-12
+    if n_members == 1:
+        from oracle import reference_path as R
+        from qsextra_b200.spectroscopy import FeynmanDiagram
+        for lab, sig in zip(labels, got):
+            ref = R.qspectroscopy_operator(systems[0], FeynmanDiagram(lab, _BASIS_DELAYS), dt=0.15, coll_rates=[0.2])
+            assert np.abs(sig - ref).max() < 1e-10 * max(1.0, np.abs(ref).max())
+
+
+def _basis_worker(rank, size, port, out_dir, n_members):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), QSX_DISABLE_RR='1', QSX_HEISENBERG_MIN='2')
+    dist.init_process_group('gloo', rank=rank, world_size=size)
+    try:
+        _, sigs = _basis_case(('gsb', 'esa'), NumpyEngine(), n_members)
+        np.save(os.path.join(out_dir, 'b%d.npy' % rank), np.array(sigs))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('size,n_members', [(2, 1), (3, 1), (2, 3)])
+def test_basis_rows_sharded_over_a_gloo_group(tmp_path, size, n_members, monkeypatch):
+    """One system: the basis rows are the sharded units and the contraction follows the gather; an ensemble: members are
+    sharded and every rank contracts its own."""
+    monkeypatch.setenv('QSX_DISABLE_RR', '1')
+    monkeypatch.setenv('QSX_HEISENBERG_MIN', '2')
+    monkeypatch.setenv('QSX_DISABLE_BASIS', '1')
+    _, want = _basis_case(('gsb', 'esa'), NumpyEngine(), n_members)
+    monkeypatch.delenv('QSX_DISABLE_BASIS')
+    mp.spawn(_basis_worker, args=(size, _free_port(), str(tmp_path), n_members), nprocs=size, join=True)
+    for r in range(size):
+        got = np.load(os.path.join(str(tmp_path), 'b%d.npy' % r))
+        assert np.abs(got - np.array(want)).max() < 1e-12
+
+
+def test_structural_support_is_closed_under_the_step():
+    """The closure of engine/support.py contains every element the emulated step populates, and is minimal for the
+    block after the first interaction (empty pseudomodes on the ground side)."""
+    from qsextra_b200.engine import support
+    from qsextra_b200.engine.sectors import Block
+    system = _ensemble(1)[0]
+    counts, (dt_, dt_trotter, tn, _) = delay_step_counts([[0.15]], 0.15, 1)
+    program = _program_for(system, dt_, dt_trotter, tn, 1, _validate_rates(system, [0.2]))
+    ground = program.block(0, 0)
+    for (ka, kb, side), expected in (((0, 1, 'b'), 8), ((1, 0, 'k'), 8)):
+        block = Block(program.n_sites, program.n_bits, ka, kb)
+        mask = support.step_closure(program, block, support.dipole_support(support.ground_support(ground), ground, block, side))
+        assert int(mask.sum()) == expected
+        sigma = np.zeros((block.dim_a, block.dim_b), dtype=complex)
+        sigma[mask] = 1.0 + 0.5j
+        bound = program.bind(block)
+        for _ in range(12):
+            sigma = emulator.apply_step(sigma, bound, 0)
+        assert np.all(mask[np.abs(sigma) > 0])
