@@ -12,6 +12,7 @@
 // Reference semantics: qsextra/qcomo/evolution/qevolve.py:74-348 (gates), :417-427 (step loop);
 // qsextra/spectroscopy/simulation/qspectroscopy.py:65-80, :142-183 (dipoles, read-out).
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -594,6 +595,7 @@ __global__ void __launch_bounds__(256) evolve_kernel(const EvolveParams k) {
 }  // namespace (helpers above are shared with the register-resident kernel)
 #include "qsx_rr.cuh"
 #include "qsx_rrc.cuh"
+#include "qsx_rrc2.cuh"
 #include "qsx_post.cuh"
 #include "qsx_lindblad.cuh"
 namespace {
@@ -1198,7 +1200,12 @@ int32_t qsx_evolve_rrc(const qsx_rrc_args* a, void* stream) {
     int sms = 0, smem_max = 0;
     int32_t rc = device_limits(&sms, &smem_max);
     if (rc) return rc;
-    int r = rrc::launch<0>(*a, sms, smem_max, (cudaStream_t)stream);
+    // Levels with many instances run the throughput form (two CTAs per SM, qsx_rrc2.cuh) when the program is eligible;
+    // QSX_RRC_V2=0 / 1 switches it off / on for every instance count (A/B runs and tests).
+    const char* v2 = getenv("QSX_RRC_V2");
+    const bool want_v2 = v2 ? (v2[0] != '0') : (a->n_inst >= 2 * sms);
+    int r = want_v2 ? rrc2::launch<0>(*a, sms, smem_max, (cudaStream_t)stream) : 1;
+    if (r == 1) r = rrc::launch<0>(*a, sms, smem_max, (cudaStream_t)stream);
     if (r == 1) return fail(QSX_ERR_NO_PROGRAM, "no compile-time program matches this block%s");
     if (r < 0) return fail(QSX_ERR_CUDA, "CUDA error: %s", cudaGetErrorString((cudaError_t)(-r)));
     return QSX_OK;

@@ -270,10 +270,51 @@ def _set_local(eng, program, mu, sequences, step_counts):
         got = _propagate_readout(eng, program, mu, last_block, chains, uniq[-1], continuous, index)
         if got is not None:
             shared[key] = got
-    # every diagram is enqueued before any result is read back: one synchronisation at the end instead of one per diagram
-    pairs = [_response_local(program, mu, side_seq, direction_seq, step_counts, eng, shared)
-             for side_seq, direction_seq in sequences]
+    # Every diagram is enqueued before any result is read back.  On the GPU each diagram after the first runs on its own
+    # stream: levels shared between diagrams carry the event of their completion, so e.g. the cheap ground-state level of
+    # gsb fills the SMs the long single-exciton level of se / esa leaves idle in its last wave.
+    on_gpu = eng.device.type == 'cuda' and not os.environ.get('QSX_ONE_STREAM')
+    if not on_gpu or len(sequences) == 1:
+        pairs = [_response_local(program, mu, side_seq, direction_seq, step_counts, eng, shared)
+                 for side_seq, direction_seq in sequences]
+        return [p[0] for p in pairs], [p[1] for p in pairs]
+    main = torch.cuda.current_stream(eng.device)
+    streams = [main] + [eng.side_stream_of(4 + (k - 1) % 4) for k in range(1, len(sequences))]
+    for st in streams[1:]:
+        st.wait_stream(main)                            # fork before anything of this call is enqueued on main
+    shared['events'] = True                             # shared entries carry (stream, event) of their producer
+    pairs = []
+    for st, (side_seq, direction_seq) in zip(streams, sequences):
+        with torch.cuda.stream(st):
+            pair = _response_local(program, mu, side_seq, direction_seq, step_counts, eng, shared)
+            if st is not main and pair[0] is not None:
+                pair[0].record_stream(main)
+        pairs.append(pair)
+    for st in streams[1:]:
+        main.wait_stream(st)                            # join
     return [p[0] for p in pairs], [p[1] for p in pairs]
+
+
+def _publish(eng, shared, key, value, tensors):
+    """Store a level in ``shared`` together with the event that marks its completion on the producing stream."""
+    if eng.device.type == 'cuda' and shared.get('events'):
+        event = torch.cuda.Event()
+        event.record(torch.cuda.current_stream(eng.device))
+        shared[key] = (value, event, torch.cuda.current_stream(eng.device), tensors)
+    else:
+        shared[key] = (value, None, None, tensors)
+
+
+def _consume(eng, shared, key):
+    value, event, producer, tensors = shared[key]
+    if event is not None:
+        here = torch.cuda.current_stream(eng.device)
+        if here != producer:
+            here.wait_event(event)
+            for t in tensors:
+                if t is not None and t.is_cuda:
+                    t.record_stream(here)
+    return value
 
 
 def response_function(program: StepProgram, mu, side_seq: str, direction_seq: str, step_counts, engine=None,
@@ -372,7 +413,7 @@ def _response_local(program: StepProgram, mu, side_seq: str, direction_seq: str,
             break
         last = level == len(plan) - 2
         if shared is not None and not last and prefix_key(level) in shared:
-            sigma, n_global, sharded, shard_units, rows_per_unit, inst_set, pending, support = shared[prefix_key(level)]
+            sigma, n_global, sharded, shard_units, rows_per_unit, inst_set, pending, support = _consume(eng, shared, prefix_key(level))
             block, ka, kb = new_block, nka, nkb
             continue
         # Basis substitution (linearity).  The n_in states per parameter set that enter this level all live on the
@@ -453,7 +494,8 @@ def _response_local(program: StepProgram, mu, side_seq: str, direction_seq: str,
         if support is not None:
             support = qsupport.step_closure(program, block, qsupport.dipole_support(support, prev_block, block, side))
         if shared is not None and not last:
-            shared[prefix_key(level)] = (sigma, n_global, sharded, shard_units, rows_per_unit, inst_set, pending, support)
+            _publish(eng, shared, prefix_key(level), (sigma, n_global, sharded, shard_units, rows_per_unit, inst_set, pending,
+                                                      support), [sigma, inst_set, None if pending is None else pending['coeff']])
 
     if pending is not None and not pending['after_gather'] and not zero and out is not None and out.shape[0] > 0:
         out = contract_basis(eng, out, pending)

@@ -85,7 +85,7 @@ class Engine:
         """Side stream number ``index`` (a small fixed set, created once)."""
         if self._side_stream is None:
             self._side_stream = []
-        index %= 4
+        index %= 8
         while len(self._side_stream) <= index:
             self._side_stream.append(torch.cuda.Stream(device=self.device))
         return self._side_stream[index]

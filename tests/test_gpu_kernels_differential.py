@@ -91,7 +91,8 @@ def test_all_kernel_families_agree_with_emulated_operations(engine, name, system
         scale = np.abs(want).max()
         variants = [('op list', plain, False, None), ('pass program', prog.bind(blk), False, None),
                     ('register-resident, generic', plain, True, {'QSX_RR_NO_STATIC': '1', 'QSX_DISABLE_RRC': '1'}),
-                    ('register-resident, best', plain, True, None)]
+                    ('register-resident, best', plain, True, {'QSX_RRC_V2': '0'}),
+                    ('register-resident, throughput form of the CTA-wide kernel', plain, True, {'QSX_RRC_V2': '1'})]
         for label, bound, use_rr, env in variants:
             got, dev = run_engine(engine, prog, bound, sigma0, use_rr, env)
             err = np.abs(got - want).max()
@@ -177,3 +178,60 @@ def test_readout_gemm_against_numpy(engine, m, n, k):
     got = engine.readout_gemm(torch.as_tensor(a, device='cuda'), torch.as_tensor(b, device='cuda')).cpu().numpy()
     want = a @ b.T
     assert got.shape == want.shape and np.abs(got - want).max() < 1e-12 * np.sqrt(k) * max(1.0, np.abs(want).max())
+
+
+def test_throughput_form_of_the_cta_wide_kernel_with_many_instances(engine):
+    """qsx_rrc2.cuh (two CTAs per SM, folded damping scalings, shear hops) against the first form and the emulated
+    operations: 300 instances of the 4-site chain's (1,1) block with different parameter sets and shared source rows,
+    snapshots and trace read-outs at irregular steps (step 0 included: no folded scaling is pending there)."""
+    from qsextra_b200.engine.program import StepProgram, SystemBatch
+    from qsextra_b200.engine.sectors import population_observables
+    rng = np.random.default_rng(11)
+    n_sets, n_src, n_inst = 5, 7, 300
+    J = np.zeros((n_sets, 4, 4))
+    for i in range(3):
+        J[:, i, i + 1] = J[:, i + 1, i] = -0.3 + 0.02 * rng.normal(size=n_sets)
+    batch = SystemBatch(1.5 + 0.1 * rng.normal(size=(n_sets, 4)), J, np.ones((n_sets, 4)),
+                        0.3 + 0.05 * rng.normal(size=(n_sets, 1)), np.full((n_sets, 1), 0.7), (2,))
+    prog = StepProgram(batch, 0.15, 1, 1, 0.5 + 0.1 * rng.random((n_sets, 1)))
+    for ka, kb in ((1, 1), (0, 1), (1, 0)):
+        blk = prog.block(ka, kb)
+        bound = prog.bind(blk, fused=False)
+        sigma0 = rng.normal(size=(n_src, blk.size)) + 1j * rng.normal(size=(n_src, blk.size))
+        inst_set = torch.as_tensor(rng.integers(0, n_sets, n_inst), dtype=torch.int32, device=engine.device)
+        inst_src = torch.as_tensor(rng.integers(0, n_src, n_inst), dtype=torch.int32, device=engine.device)
+        emit = [0, 1, 4, 9]
+        results = {}
+        for flag in ('0', '1'):
+            os.environ['QSX_RRC_V2'] = flag
+            try:
+                dev = engine.upload_program(bound, prog)
+                assert dev.get('rrc') is not None
+                _, snap = engine.evolve(dev, engine.to_device(sigma0), n_inst, 9, emit, snapshots=True, inst_set=inst_set,
+                                        inst_src=inst_src)
+                obs = None
+                if ka == kb:
+                    obs = engine.upload_observables(*population_observables(blk), kind='populations')
+                    pops, _ = engine.evolve(dev, engine.to_device(sigma0), n_inst, 9, emit, obs=obs, obs_real=True,
+                                            inst_set=inst_set, inst_src=inst_src)
+                else:
+                    mu = np.array([1., 0.8, -0.6, 1.1])
+                    obs = engine.upload_observables(*blk.emission_observable(mu), kind='emission', mu=mu)
+                    pops, _ = engine.evolve(dev, engine.to_device(sigma0), n_inst, 9, emit, obs=obs, inst_set=inst_set,
+                                            inst_src=inst_src)
+                torch.cuda.synchronize()
+                results[flag] = (snap.cpu().numpy(), pops.cpu().numpy())
+            finally:
+                os.environ.pop('QSX_RRC_V2', None)
+        scale = np.abs(results['0'][0]).max()
+        assert np.abs(results['0'][0] - results['1'][0]).max() < 1e-12 * scale, (ka, kb)
+        assert np.abs(results['0'][1] - results['1'][1]).max() < 1e-12 * np.abs(results['0'][1]).max(), (ka, kb)
+        sets, srcs = inst_set.cpu().numpy(), inst_src.cpu().numpy()
+        for inst in (0, 151, 299):                           # the emulated operations, a few instances
+            sigma = sigma0[srcs[inst]].reshape(blk.dim_a, blk.dim_b)
+            for step in range(10):
+                if step:
+                    sigma = emulator.apply_step(sigma, bound, int(sets[inst]))
+                if step in emit:
+                    got = results['1'][0][inst, emit.index(step)].reshape(blk.dim_a, blk.dim_b)
+                    assert np.abs(got - sigma).max() < 1e-12 * scale, (ka, kb, inst, step)
