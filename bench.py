@@ -444,8 +444,8 @@ def spectroscopy_extras(world, rank, barrier):
                 qspectroscopy_set(chain, specs, verbose=False, **kw)
             sec, samples, sigs = timed(lambda: qspectroscopy_set(chain, specs, verbose=False, **kw))
             entry = dict(grid_points=POINTS_PER_MEMBER, seconds=sec, grid_points_per_s=POINTS_PER_MEMBER / sec,
-                         api='qspectroscopy_set (host objects -> NumPy signals; chains of the ONE system sharded over the '
-                             'ranks, one all-gather: strong scaling)', samples_s=samples, first_call_s=first,
+                         api='qspectroscopy_set (host objects -> NumPy signals); ONE system is latency-bound (64 basis rows on 148 SMs): '
+                             'under torchrun every rank evaluates it whole (replicas), more GPUs serve more realisations', samples_s=samples, first_call_s=first,
                          checksum=float(sum(np.abs(s_).sum() for s_ in sigs)))
 
             def pipeline():
@@ -519,7 +519,8 @@ def run_ours(args):
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        import datetime
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank), timeout=datetime.timedelta(seconds=180))
     from qsextra_b200.engine import response as R
     from qsextra_b200.engine.runtime import get_engine
     from qsextra_b200.spectroscopy import qspectroscopy_ensemble
@@ -545,13 +546,21 @@ def run_ours(args):
 
     sampler = ClockSampler(local_rank)
     sampler.wait_for_first_sample()
-    warm_until = time.time() + 0.5                  # at least W (>= 3) steps and half a second under load before timing
-    n_warm = 0
+    # at least W (>= 3) steps and half a second under load before timing; the SAME number of evaluations on every rank
+    # (each holds a collective): rank 0 decides how many extra ones fill the half second
     signals = None
-    while n_warm < max(args.warmup, 3) or time.time() < warm_until:
+    t_warm = time.time()
+    for _ in range(max(args.warmup, 3)):
         flush.fill_(1)
         signals = hot_path()
-        n_warm += 1
+    torch.cuda.synchronize()
+    per_step = (time.time() - t_warm) / max(args.warmup, 3)
+    extra = torch.tensor([int(np.ceil(max(0.0, 0.5 - (time.time() - t_warm)) / max(per_step, 1e-3)))], device=eng.device)
+    if world > 1:
+        dist.broadcast(extra, 0)
+    for _ in range(int(extra.item())):
+        flush.fill_(1)
+        signals = hot_path()
     barrier()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]

@@ -97,7 +97,7 @@ def _last_level(program, plan, uniq, rank, size):
         block = Block(program.n_sites, program.n_bits, ka, kb)
         if not block.valid():
             return None, 0
-        if not sharded and size > 1 and (n_global >= size or n_sets > 1):
+        if not sharded and size > 1 and (n_global >= size or n_sets > 1):        # (a lower bound when the tree stays unsharded)
             lo, hi = qdist.shard_bounds(n_global, rank, size)
             local, sharded = hi - lo, True
         if level < len(plan) - 2:
@@ -440,7 +440,11 @@ def _response_local(program: StepProgram, mu, side_seq: str, direction_seq: str,
                     n_global = n_sets * d
                 else:
                     n_global = d
-        if not sharded and size > 1 and (n_global >= size or n_sets > 1):
+        # Chains / basis rows of ONE system are only worth sharding when a level holds more instances than the GPU
+        # has SMs (below that every propagation is latency-bound and a rank gains nothing from holding fewer of them):
+        # otherwise every rank evaluates the whole tree and no gather is needed.  Parameter sets are always sharded.
+        shard_min = int(os.environ.get('QSX_SHARD_MIN', getattr(eng, 'sm_count', 1)))
+        if not sharded and size > 1 and (n_sets > 1 or (n_global >= size and n_global >= shard_min)):
             lo, hi = qdist.shard_bounds(n_global, rank, size)
             sigma = sigma[lo:hi].contiguous()
             if inst_set is not None:

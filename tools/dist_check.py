@@ -2,6 +2,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import warnings; warnings.simplefilter('ignore')
+os.environ['QSX_SHARD_MIN'] = '1'          # small grids: shard them anyway, the sharded path is what is checked
 import numpy as np, torch, torch.distributed as dist
 from qsextra_b200 import ChromophoreSystem
 from qsextra_b200.engine import dist as qdist
