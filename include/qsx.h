@@ -29,13 +29,20 @@
 #ifndef QSX_H
 #define QSX_H
 
+#ifdef __CUDACC_RTC__ /* run-time compilation of a kernel specialisation (engine/jit.py): no host headers */
+typedef signed char int8_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+#else
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define QSX_ABI_VERSION 17
+#define QSX_ABI_VERSION 18
 
 enum {
     QSX_OK = 0,
@@ -244,6 +251,14 @@ int32_t qsx_evolve_rrc(const qsx_rrc_args* args, void* stream);
 /* Index of the compile-time program of qsx_evolve_rrc with this signature (HOST int32 vector), or -1 when the call
  * would answer "no compile-time program matches"; lets the host plan before it enqueues anything. */
 int32_t qsx_rrc_find_program(const int32_t* signature, int32_t n_signature);
+
+/* Add a kernel specialisation compiled at run time (engine/jit.py: NVRTC on csrc/qsx_rrc.cuh + csrc/qsx_rrc2.cuh around
+ * the program's own BigProg<0> table) to the programs qsx_evolve_rrc can run: `cubin` is loaded into the current
+ * device's primary context, `kernel_name` (and `kernel2_name`, the throughput form, or NULL) are the lowered names of
+ * the kernels in it, `signature` (HOST) is what later calls are matched against.  Registering a signature twice is a
+ * no-op.  This is what opens the compile-time menu: any eligible block structure runs the register-resident kernels. */
+int32_t qsx_rrc_register(const void* cubin, int64_t cubin_bytes, const char* kernel_name, const char* kernel2_name,
+                         const int32_t* signature, int32_t n_signature);
 
 int32_t qsx_abi_version(void);
 

@@ -11,14 +11,21 @@
 //
 // Reference semantics: qsextra/qcomo/evolution/qevolve.py:74-348 (gates), :417-427 (step loop);
 // qsextra/spectroscopy/simulation/qspectroscopy.py:65-80, :142-183 (dipoles, read-out).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
 
 #include "qsx.h"
+
+#ifndef QSX_GEMM_DEFAULT
+#define QSX_GEMM_DEFAULT 2
+#endif
 
 namespace {
 
@@ -38,12 +45,7 @@ int32_t fail(int32_t code, const char* fmt, const char* detail = "") {
 // ------------------------------------------------------------------------------------------------
 // complex helpers (double2 = re, im)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
-    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
-}
-__device__ __forceinline__ double2 cmul_conj(double2 a, double2 b) {   // a * conj(b)
-    return make_double2(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -a.x * b.y));
-}
+#include "qsx_complex.cuh"
 // x*c + y*(fr + i fi)
 __device__ __forceinline__ double2 axpby(double c, double2 x, double fr, double fi, double2 y) {
     return make_double2(fma(c, x.x, fma(fr, y.x, -fi * y.y)), fma(c, x.y, fma(fr, y.y, fi * y.x)));
@@ -596,6 +598,7 @@ __global__ void __launch_bounds__(256) evolve_kernel(const EvolveParams k) {
 #include "qsx_rr.cuh"
 #include "qsx_rrc.cuh"
 #include "qsx_rrc2.cuh"
+#include "qsx_gemm.cuh"
 #include "qsx_post.cuh"
 #include "qsx_lindblad.cuh"
 namespace {
@@ -1179,13 +1182,140 @@ int32_t qsx_evolve_rr(const qsx_rr_args* a, void* stream) {
     return QSX_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Run-time specialisations of the CTA-wide kernels (engine/jit.py compiles them with NVRTC; here they are loaded and
+// launched).  The driver API is reached through cudaGetDriverEntryPoint: no link-time dependency on libcuda, so the
+// library still loads on a machine without a driver (CPU-only test runs).
+// ------------------------------------------------------------------------------------------------
+namespace jit {
+
+struct Entry {
+    std::vector<int32_t> sig;
+    CUmodule module = nullptr;
+    CUfunction first = nullptr, second = nullptr;
+    int threads = 0, exchange_elems = 0, exchange2_elems = 0, n_ops = 0, min_ctas2 = 1;
+};
+static std::vector<Entry> g_entries;
+static std::mutex g_mu;
+
+struct Driver {
+    CUresult (*moduleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*moduleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*moduleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*) = nullptr;
+    CUresult (*memcpyDtoH)(void*, CUdeviceptr, size_t) = nullptr;
+    CUresult (*funcSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+    CUresult (*launchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
+                             void**, void**) = nullptr;
+    CUresult (*occupancy)(int*, CUfunction, int, size_t) = nullptr;
+    bool ok = false;
+};
+
+static bool entry_point(const char* name, void** fn) {
+    cudaDriverEntryPointQueryResult status;
+    return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &status) == cudaSuccess &&
+           status == cudaDriverEntryPointSuccess && *fn;
+}
+
+static const Driver& driver() {
+    static Driver d;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        d.ok = entry_point("cuModuleLoadData", (void**)&d.moduleLoadData) &&
+               entry_point("cuModuleGetFunction", (void**)&d.moduleGetFunction) &&
+               entry_point("cuModuleGetGlobal", (void**)&d.moduleGetGlobal) &&
+               entry_point("cuMemcpyDtoH", (void**)&d.memcpyDtoH) &&
+               entry_point("cuFuncSetAttribute", (void**)&d.funcSetAttribute) &&
+               entry_point("cuLaunchKernel", (void**)&d.launchKernel) &&
+               entry_point("cuOccupancyMaxActiveBlocksPerMultiprocessor", (void**)&d.occupancy);
+    });
+    return d;
+}
+
+static int find(const int32_t* signature, int n) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    for (size_t e = 0; e < g_entries.size(); ++e)
+        if ((int)g_entries[e].sig.size() == n && !memcmp(g_entries[e].sig.data(), signature, n * sizeof(int32_t))) return (int)e;
+    return -1;
+}
+
+// 0: launched, 1: no registered program, < 0: CUDA driver error code (negated)
+static int launch(const qsx_rrc_args& a, bool want_second, int sms, int smem_max, cudaStream_t stream) {
+    const int idx = find(a.signature, a.n_signature);
+    if (idx < 0) return 1;
+    Entry e;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        e = g_entries[idx];
+    }
+    const Driver& d = driver();
+    const size_t p_bytes = (size_t)((a.param_stride + 1) & ~1) * sizeof(double);
+    const bool second = want_second && e.second;
+    const size_t smem = second ? (size_t)e.exchange2_elems * sizeof(double2) + p_bytes + 64 * sizeof(double2) +
+                                     (size_t)e.n_ops * sizeof(double2)
+                               : (size_t)e.exchange_elems * sizeof(double2) + p_bytes + 64 * sizeof(double2);
+    if (smem > (size_t)smem_max) return 1;
+    CUfunction fn = second ? e.second : e.first;
+    CUresult r = d.funcSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
+    if (r != CUDA_SUCCESS) return -(int)r;
+    int per_sm = 1;
+    r = d.occupancy(&per_sm, fn, e.threads, smem);
+    if (r != CUDA_SUCCESS) return -(int)r;
+    if (per_sm < 1) per_sm = 1;
+    int grid = sms * per_sm;
+    if (grid > a.n_inst) grid = a.n_inst;
+    rrc::Params k;
+    k.a = a;
+    void* params[] = {&k};
+    r = d.launchKernel(fn, grid, 1, 1, e.threads, 1, 1, (unsigned)smem, (CUstream)stream, params, nullptr);
+    return r == CUDA_SUCCESS ? 0 : -(int)r;
+}
+
+}  // namespace jit
+
+int32_t qsx_rrc_register(const void* cubin, int64_t cubin_bytes, const char* kernel_name, const char* kernel2_name,
+                         const int32_t* signature, int32_t n_signature) {
+    if (!cubin || cubin_bytes <= 0 || !kernel_name || !signature || n_signature <= 0)
+        return fail(QSX_ERR_INVALID, "qsx_rrc_register: missing argument%s");
+    if (jit::find(signature, n_signature) >= 0) return QSX_OK;              // already there
+    QSX_CUDA(cudaFree(0));                                                  // the primary context of the current device
+    const jit::Driver& d = jit::driver();
+    if (!d.ok) return fail(QSX_ERR_CUDA, "CUDA driver entry points unavailable%s");
+    jit::Entry e;
+    e.sig.assign(signature, signature + n_signature);
+    CUresult r = d.moduleLoadData(&e.module, cubin);
+    if (r != CUDA_SUCCESS) return fail(QSX_ERR_CUDA, "cuModuleLoadData failed for a run-time specialisation%s");
+    if (d.moduleGetFunction(&e.first, e.module, kernel_name) != CUDA_SUCCESS)
+        return fail(QSX_ERR_INVALID, "kernel %s not found in the cubin", kernel_name);
+    if (kernel2_name && d.moduleGetFunction(&e.second, e.module, kernel2_name) != CUDA_SUCCESS)
+        return fail(QSX_ERR_INVALID, "kernel %s not found in the cubin", kernel2_name);
+    CUdeviceptr info_ptr = 0;
+    size_t info_bytes = 0;
+    int info[6] = {0, 0, 0, 0, 0, 1};
+    if (d.moduleGetGlobal(&info_ptr, &info_bytes, e.module, "qsx_jit_info") != CUDA_SUCCESS || info_bytes < sizeof(info) ||
+        d.memcpyDtoH(info, info_ptr, sizeof(info)) != CUDA_SUCCESS)
+        return fail(QSX_ERR_INVALID, "qsx_jit_info missing from the cubin%s");
+    e.threads = info[0];
+    e.exchange_elems = info[1];
+    e.exchange2_elems = info[3];
+    e.n_ops = info[4];
+    e.min_ctas2 = info[5];
+    if (!info[2]) e.second = nullptr;
+    if (e.threads <= 0 || e.threads > 1024) return fail(QSX_ERR_INVALID, "bad thread count in qsx_jit_info%s");
+    std::lock_guard<std::mutex> lock(jit::g_mu);
+    jit::g_entries.push_back(e);
+    return QSX_OK;
+}
+
 int32_t qsx_rrc_find_program(const int32_t* signature, int32_t n_signature) {
     if (!signature || n_signature <= 0) return fail(QSX_ERR_INVALID, "missing program signature%s");
     qsx_rrc_args a;
     memset(&a, 0, sizeof(a));
     a.signature = signature;
     a.n_signature = n_signature;
-    return rrc::find<0>(a);
+    const int shipped = rrc::find<0>(a);
+    if (shipped >= 0) return shipped;
+    const int registered = jit::find(signature, n_signature);
+    return registered >= 0 ? rrc::kNumBigProgs + registered : -1;
 }
 
 int32_t qsx_evolve_rrc(const qsx_rrc_args* a, void* stream) {
@@ -1206,15 +1336,31 @@ int32_t qsx_evolve_rrc(const qsx_rrc_args* a, void* stream) {
     const bool want_v2 = v2 ? (v2[0] != '0') : (a->n_inst >= 2 * sms);
     int r = want_v2 ? rrc2::launch<0>(*a, sms, smem_max, (cudaStream_t)stream) : 1;
     if (r == 1) r = rrc::launch<0>(*a, sms, smem_max, (cudaStream_t)stream);
+    if (r == 1) {                                   // a structure specialised at run time (qsx_rrc_register)?
+        r = jit::launch(*a, want_v2, sms, smem_max, (cudaStream_t)stream);
+        if (r < 0) return fail(QSX_ERR_CUDA, "CUDA driver error while launching a run-time specialisation%s");
+    }
     if (r == 1) return fail(QSX_ERR_NO_PROGRAM, "no compile-time program matches this block%s");
     if (r < 0) return fail(QSX_ERR_CUDA, "CUDA error: %s", cudaGetErrorString((cudaError_t)(-r)));
     return QSX_OK;
 }
 
-static int readout_splits(int n_inst, int n_emit, int n_elem, int sms) {
-    const long long tiles = (long long)((n_emit + RG_TN - 1) / RG_TN) * ((n_inst + RG_TM - 1) / RG_TM);
+// Which form of the read-out product runs: 0 = first form (32 x 64 tiles, single buffer), 1 = pipelined FP64 CUDA-core
+// form, 2 = FP64 tensor-core form (qsx_gemm.cuh).  QSX_GEMM=old|simt|dmma overrides the default.
+static int gemm_form() {
+    const char* e = getenv("QSX_GEMM");
+    if (e && !strcmp(e, "old")) return 0;
+    if (e && !strcmp(e, "simt")) return 1;
+    if (e && !strcmp(e, "dmma")) return 2;
+    return QSX_GEMM_DEFAULT;
+}
+
+static int readout_splits(int form, int n_inst, int n_emit, int n_elem, int sms) {
+    const int tm = form ? gemm::TM : RG_TM, tn = form ? gemm::TN : RG_TN;
+    const long long tiles = (long long)((n_emit + tn - 1) / tn) * ((n_inst + tm - 1) / tm);
+    const long long want = (form ? 4LL : 4LL) * sms;          // CTAs to fill the GPU (two 256-thread CTAs per SM)
     int splits = 1;
-    while (splits < 16 && tiles * splits < 4LL * sms && n_elem / (splits * 2) >= 256) splits *= 2;
+    while (splits < 16 && tiles * splits < want && n_elem / (splits * 2) >= 256) splits *= 2;
     return splits;
 }
 
@@ -1223,7 +1369,12 @@ int64_t qsx_readout_gemm_batched_workspace_bytes(int32_t n_batch, int32_t n_inst
     int sms = 0, smem_max = 0;
     int32_t rc = device_limits(&sms, &smem_max);
     if (rc) return rc;
-    const int splits = readout_splits(n_batch * n_inst, n_emit, n_elem, sms);
+    // (the largest split count any form would use for these sizes, so that the scratch fits whichever runs)
+    int splits = 1;
+    for (int form = 0; form < 3; ++form) {
+        const int s = readout_splits(form, n_batch * n_inst, n_emit, n_elem, sms);
+        if (s > splits) splits = s;
+    }
     return splits > 1 ? (int64_t)splits * n_batch * n_inst * n_emit * (int64_t)sizeof(double2) : 0;
 }
 
@@ -1244,21 +1395,32 @@ int32_t qsx_readout_gemm_batched(int32_t n_batch, int32_t n_inst, int32_t n_emit
     int sms = 0, smem_max = 0;
     int32_t rc = device_limits(&sms, &smem_max);
     if (rc) return rc;
-    int splits = workspace ? readout_splits(n_batch * n_inst, n_emit, n_elem, sms) : 1;   // without scratch: no split
-    const int m_tiles = (n_inst + RG_TM - 1) / RG_TM;
-    if ((long long)m_tiles * n_batch > 65535) return fail(QSX_ERR_INVALID, "more than 2097120 chains in one call%s");
-    dim3 grid((n_emit + RG_TN - 1) / RG_TN, m_tiles * n_batch, splits);
-    int k_chunk = ((n_elem + splits - 1) / splits + RG_TK - 1) / RG_TK * RG_TK;
-    if (k_chunk < RG_TK) k_chunk = RG_TK;
+    const int form = gemm_form();
+    const int tm = form ? gemm::TM : RG_TM, tn = form ? gemm::TN : RG_TN, tk = form ? gemm::TK : RG_TK;
+    int splits = workspace ? readout_splits(form, n_batch * n_inst, n_emit, n_elem, sms) : 1;   // without scratch: no split
+    const int m_tiles = (n_inst + tm - 1) / tm;
+    if ((long long)m_tiles * n_batch > 65535) return fail(QSX_ERR_INVALID, "too many chains in one call (grid.y)%s");
+    dim3 grid((n_emit + tn - 1) / tn, m_tiles * n_batch, splits);
+    int k_chunk = ((n_elem + splits - 1) / splits + tk - 1) / tk * tk;
+    if (k_chunk < tk) k_chunk = tk;
     double2* target = splits > 1 ? reinterpret_cast<double2*>(workspace) : reinterpret_cast<double2*>(out);
-    readout_gemm_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(n_inst, n_emit, n_elem, k_chunk, m_tiles, n_batch,
-                                                                 reinterpret_cast<const double2*>(sigma),
-                                                                 reinterpret_cast<const double2*>(readout), target);
+    const double2* A = reinterpret_cast<const double2*>(sigma);
+    const double2* B = reinterpret_cast<const double2*>(readout);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (form == 1) {
+        QSX_CUDA(cudaFuncSetAttribute(gemm::simt::kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm::simt::SMEM));
+        gemm::simt::kernel<<<grid, 256, gemm::simt::SMEM, st>>>(n_inst, n_emit, n_elem, k_chunk, m_tiles, n_batch, A, B, target);
+    } else if (form == 2) {
+        QSX_CUDA(cudaFuncSetAttribute(gemm::dmma::kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm::dmma::SMEM));
+        gemm::dmma::kernel<<<grid, 256, gemm::dmma::SMEM, st>>>(n_inst, n_emit, n_elem, k_chunk, m_tiles, n_batch, A, B, target);
+    } else {
+        readout_gemm_kernel<<<grid, 128, 0, st>>>(n_inst, n_emit, n_elem, k_chunk, m_tiles, n_batch, A, B, target);
+    }
     if (splits > 1) {
         const size_t n = (size_t)n_batch * n_inst * n_emit;
         size_t blocks = (n + 255) / 256;
         if (blocks > (size_t)sms * 8) blocks = (size_t)sms * 8;
-        reduce_splits_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(n, splits, target, reinterpret_cast<double2*>(out));
+        reduce_splits_kernel<<<(int)blocks, 256, 0, st>>>(n, splits, target, reinterpret_cast<double2*>(out));
     }
     QSX_CUDA(cudaGetLastError());
     return QSX_OK;

@@ -6,13 +6,23 @@
 // double-buffered shared-memory exchange for warp bits) and amplitude damping (the (1,1) threads of a bit pair hand
 // their tile to the (0,0) threads through shared memory).  The operation list is a compile-time constant (BigProg<PID>).
 #pragma once
+#ifdef __CUDACC_RTC__            // run-time specialisation (engine/jit.py): libcu++ instead of the host's <utility>
+#include <cuda/std/utility>
+namespace qstd = cuda::std;
+#else
 #include <utility>
+namespace qstd = std;
+#endif
 
 namespace rrc {
 
 template <int PID>
 struct BigProg;
+#ifdef QSX_RRC_EXTERNAL_PROGRAMS  // names the header that defines BigProg<0> and kNumBigProgs = 1 for this unit
+#include QSX_RRC_EXTERNAL_PROGRAMS
+#else
 #include "qsx_rrc_programs.inc"
+#endif
 
 enum { OP_DIAG = 0, OP_HOPK = 1, OP_HOPB = 2, OP_ROTK = 3, OP_ROTB = 4, OP_AD = 5, OP_ADT = 6 };
 
@@ -187,7 +197,7 @@ template <int PID, int... Os>
 __device__ __forceinline__ void big_step(double2 (&v)[BigProg<PID>::NA][BigProg<PID>::NB],
                                          const double2 (&w)[BigProg<PID>::NA][BigProg<PID>::NB], const double* P,
                                          double2* xbuf, int (&which)[Geo<PID>::NGROUP], int tid,
-                                         std::integer_sequence<int, Os...>) {
+                                         qstd::integer_sequence<int, Os...>) {
     (big_op<PID, Os>(v, w, P, xbuf, which, tid), ...);
 }
 
@@ -204,7 +214,7 @@ __device__ __forceinline__ void trace_term(const double2 (&v)[BigProg<PID>::NA][
 template <int PID, int... Es>
 __device__ __forceinline__ void big_trace(const double2 (&v)[BigProg<PID>::NA][BigProg<PID>::NB],
                                           double (&re)[BigProg<PID>::NBITS], double (&im)[BigProg<PID>::NBITS],
-                                          std::integer_sequence<int, Es...>) {
+                                          qstd::integer_sequence<int, Es...>) {
     (trace_term<PID, Es>(v, re, im), ...);
 }
 
@@ -220,7 +230,7 @@ __device__ __forceinline__ int bra_bit(int tid) {
     return ((tid >> p) & 1) << Q;
 }
 template <int PID, int... Qs>
-__device__ __forceinline__ void thread_modes(int tid, int& ma, int& mb, std::integer_sequence<int, Qs...>) {
+__device__ __forceinline__ void thread_modes(int tid, int& ma, int& mb, qstd::integer_sequence<int, Qs...>) {
     ma = (ket_bit<PID, Qs>(tid) | ...);
     mb = (bra_bit<PID, Qs>(tid) | ...);
 }
@@ -237,7 +247,7 @@ __global__ void __launch_bounds__(1 << (2 * BigProg<PID>::NBITS)) evolve_rrc_ker
     double* P = reinterpret_cast<double*>(red + 64);
     const int tid = threadIdx.x;
     int ma, mb;
-    thread_modes<PID>(tid, ma, mb, std::make_integer_sequence<int, NBITS>{});
+    thread_modes<PID>(tid, ma, mb, qstd::make_integer_sequence<int, NBITS>{});
     double mu[16];
 #pragma unroll
     for (int s = 0; s < 16; ++s) mu[s] = a.mu[s];
@@ -270,14 +280,14 @@ __global__ void __launch_bounds__(1 << (2 * BigProg<PID>::NBITS)) evolve_rrc_ker
         int next_emit = a.n_emit > 0 ? a.emit_steps[0] : -1;
         int after_next = a.n_emit > 1 ? a.emit_steps[1] : -1;
         for (int step = 0; step <= a.n_steps && slot < a.n_emit; ++step) {
-            if (step) big_step<PID>(v, w, P, xbuf, which, tid, std::make_integer_sequence<int, BP::NOPS>{});
+            if (step) big_step<PID>(v, w, P, xbuf, which, tid, qstd::make_integer_sequence<int, BP::NOPS>{});
             if (step == next_emit) {
                 if (a.emit_trace) {
                     double re[NBITS], im[NBITS];                 // one pseudomode per site: NBITS = number of sites
 #pragma unroll
                     for (int s = 0; s < NBITS; ++s) re[s] = im[s] = 0.0;
                     if constexpr (BP::NEM > 0) {
-                        if (ma == mb) big_trace<PID>(v, re, im, std::make_integer_sequence<int, BP::NEM>{});
+                        if (ma == mb) big_trace<PID>(v, re, im, qstd::make_integer_sequence<int, BP::NEM>{});
                     }
 #pragma unroll
                     for (int s = 0; s < NBITS; ++s) {
@@ -321,6 +331,7 @@ __global__ void __launch_bounds__(1 << (2 * BigProg<PID>::NBITS)) evolve_rrc_ker
     }
 }
 
+#ifndef __CUDACC_RTC__
 template <int PID>
 bool matches(const qsx_rrc_args& a) {
     using BP = BigProg<PID>;
@@ -364,5 +375,7 @@ int launch(const qsx_rrc_args& a, int sms, int smem_max, cudaStream_t stream) {
         return e == cudaSuccess ? 0 : -(int)e;
     }
 }
+
+#endif  // !__CUDACC_RTC__
 
 }  // namespace rrc

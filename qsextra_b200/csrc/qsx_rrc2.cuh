@@ -15,7 +15,6 @@
 //   * shared-memory exchanges synchronise the CTA (bar.sync 0) and alternate between two buffers.
 // Forward programs only (the transposed read-out propagations are single instances: latency, not throughput).
 #pragma once
-#include <utility>
 
 namespace rrc2 {
 
@@ -158,7 +157,7 @@ __device__ __forceinline__ void op2(double2 (&v)[BigProg<PID>::NA][BigProg<PID>:
 
 template <int PID, int... Os>
 __device__ __forceinline__ void step2(double2 (&v)[BigProg<PID>::NA][BigProg<PID>::NB], const double2 g, const double* P,
-                                      const double2* H, double2* xbuf, int& cur, int tid, std::integer_sequence<int, Os...>) {
+                                      const double2* H, double2* xbuf, int& cur, int tid, qstd::integer_sequence<int, Os...>) {
     (op2<PID, Os>(v, g, P, H, xbuf, cur, tid), ...);
 }
 
@@ -177,7 +176,7 @@ __device__ __forceinline__ double damp_scale(const double* P, int tid) {
     }
 }
 template <int PID, int... Os>
-__device__ __forceinline__ double damp_scales(const double* P, int tid, std::integer_sequence<int, Os...>) {
+__device__ __forceinline__ double damp_scales(const double* P, int tid, qstd::integer_sequence<int, Os...>) {
     return (damp_scale<PID, Os>(P, tid) * ...);
 }
 
@@ -192,7 +191,7 @@ __device__ __forceinline__ void hop_entry(const double* P, double2* H) {
     }
 }
 template <int PID, int... Os>
-__device__ __forceinline__ void hop_table(const double* P, double2* H, std::integer_sequence<int, Os...>) {
+__device__ __forceinline__ void hop_table(const double* P, double2* H, qstd::integer_sequence<int, Os...>) {
     (hop_entry<PID, Os>(P, H), ...);
 }
 
@@ -209,7 +208,7 @@ __global__ void __launch_bounds__(1 << (2 * BigProg<PID>::NBITS), Geo<PID>::MIN_
     double* P = reinterpret_cast<double*>(H + BP::NOPS);
     const int tid = threadIdx.x;
     int ma, mb;
-    rrc::thread_modes<PID>(tid, ma, mb, std::make_integer_sequence<int, NBITS>{});
+    rrc::thread_modes<PID>(tid, ma, mb, qstd::make_integer_sequence<int, NBITS>{});
 
     for (int inst = blockIdx.x; inst < a.n_inst; inst += gridDim.x) {
         const int set = a.inst_set ? a.inst_set[inst] : 0;
@@ -218,10 +217,10 @@ __global__ void __launch_bounds__(1 << (2 * BigProg<PID>::NBITS), Geo<PID>::MIN_
         __syncthreads();
         for (int i = tid; i < a.param_stride; i += NT) P[i] = Pg[i];
         __syncthreads();
-        if (tid == 0) hop_table<PID>(P, H, std::make_integer_sequence<int, BP::NOPS>{});
+        if (tid == 0) hop_table<PID>(P, H, qstd::make_integer_sequence<int, BP::NOPS>{});
         const double2 g0 = cmul_conj(reinterpret_cast<const double2*>(P + 2 * NA * NB)[ma],
                                      reinterpret_cast<const double2*>(P + 2 * NA * NB + 2 * M)[mb]);
-        const double dd = damp_scales<PID>(P, tid, std::make_integer_sequence<int, BP::NOPS>{});
+        const double dd = damp_scales<PID>(P, tid, qstd::make_integer_sequence<int, BP::NOPS>{});
         const double2 g1 = make_double2(g0.x * dd, g0.y * dd);
         double2 v[NA][NB];
         {
@@ -237,7 +236,7 @@ __global__ void __launch_bounds__(1 << (2 * BigProg<PID>::NBITS), Geo<PID>::MIN_
         int next_emit = a.n_emit > 0 ? a.emit_steps[0] : -1;
         int after_next = a.n_emit > 1 ? a.emit_steps[1] : -1;
         for (int step = 0; step <= a.n_steps && slot < a.n_emit; ++step) {
-            if (step) step2<PID>(v, step == 1 ? g0 : g1, P, H, xbuf, cur, tid, std::make_integer_sequence<int, BP::NOPS>{});
+            if (step) step2<PID>(v, step == 1 ? g0 : g1, P, H, xbuf, cur, tid, qstd::make_integer_sequence<int, BP::NOPS>{});
             if (step == next_emit) {
                 const double out_scale = step ? dd : 1.0;          // the trailing damping scalings the registers lack
                 if (a.emit_trace) {
@@ -245,7 +244,7 @@ __global__ void __launch_bounds__(1 << (2 * BigProg<PID>::NBITS), Geo<PID>::MIN_
 #pragma unroll
                     for (int s = 0; s < NBITS; ++s) re[s] = im[s] = 0.0;
                     if constexpr (BP::NEM > 0) {
-                        if (ma == mb) rrc::big_trace<PID>(v, re, im, std::make_integer_sequence<int, BP::NEM>{});
+                        if (ma == mb) rrc::big_trace<PID>(v, re, im, qstd::make_integer_sequence<int, BP::NEM>{});
                     }
 #pragma unroll
                     for (int s = 0; s < NBITS; ++s) {
@@ -293,6 +292,7 @@ __global__ void __launch_bounds__(1 << (2 * BigProg<PID>::NBITS), Geo<PID>::MIN_
     }
 }
 
+#ifndef __CUDACC_RTC__
 // 0: launched, 1: no eligible compile-time program, < 0: CUDA error code (negated)
 template <int PID>
 int launch(const qsx_rrc_args& a, int sms, int smem_max, cudaStream_t stream) {
@@ -322,5 +322,7 @@ int launch(const qsx_rrc_args& a, int sms, int smem_max, cudaStream_t stream) {
         }
     }
 }
+
+#endif  // !__CUDACC_RTC__
 
 }  // namespace rrc2

@@ -11,11 +11,11 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libqsx.so')
-ABI_VERSION = 17
+ABI_VERSION = 18
 ERR_NO_PROGRAM = -4
 
 EXPORTS = ('qsx_abi_version', 'qsx_last_error', 'qsx_device_info', 'qsx_evolve_workspace_bytes', 'qsx_evolve',
-           'qsx_evolve_rr', 'qsx_bind_params', 'qsx_rr_tables', 'qsx_evolve_rrc', 'qsx_rrc_find_program', 'qsx_apply_dipole', 'qsx_readout_gemm_workspace_bytes', 'qsx_readout_gemm',
+           'qsx_evolve_rr', 'qsx_bind_params', 'qsx_rr_tables', 'qsx_evolve_rrc', 'qsx_rrc_find_program', 'qsx_rrc_register', 'qsx_apply_dipole', 'qsx_readout_gemm_workspace_bytes', 'qsx_readout_gemm',
            'qsx_readout_gemm_batched_workspace_bytes', 'qsx_readout_gemm_batched', 'qsx_rotating_frame', 'qsx_spectrum_shift',
            'qsx_lindblad_workspace_bytes', 'qsx_lindblad_evolve',
            'qsx_fp64_peak')
@@ -134,6 +134,8 @@ def load():
     lib.qsx_evolve_rrc.restype = C.c_int32
     lib.qsx_rrc_find_program.argtypes = [C.c_void_p, C.c_int32]
     lib.qsx_rrc_find_program.restype = C.c_int32
+    lib.qsx_rrc_register.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int32]
+    lib.qsx_rrc_register.restype = C.c_int32
     lib.qsx_apply_dipole.argtypes = [C.POINTER(QsxBlock), C.POINTER(QsxBlock), C.c_int32, C.c_void_p, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
     lib.qsx_apply_dipole.restype = C.c_int32

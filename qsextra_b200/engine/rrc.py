@@ -59,6 +59,33 @@ class RRCProgram:
                 flops, instr = flops + (6 * n) // 4 + (2 * n * 3) // 4, instr + (4 * n) // 4 + (2 * n * 3) // 4
         return flops, instr
 
+    def source(self, pid: int = 0, comment: str = '') -> str:
+        """The ``BigProg<pid>`` specialisation of csrc/qsx_rrc.cuh for this program (the compile-time menu of
+        csrc/qsx_rrc_programs.inc and the run-time specialisations of engine/jit.py are both written by this)."""
+        def arr(rows):
+            return '{' + ', '.join('{' + ', '.join(str(int(v)) for v in r) + '}' for r in rows) + '}'
+        sig = self.signature()
+        em = self.emission or [(0, 0, 0)]
+        lines = ['// ' + comment] if comment else []
+        lines.append('template <> struct BigProg<%d> {' % pid)
+        lines.append('    static constexpr int NA = %d, NB = %d, NBITS = %d, NOPS = %d, NEM = %d, NSIG = %d;' % (
+            self.n_a, self.n_b, self.n_bits, len(self.ops), len(self.emission), len(sig)))
+        lines.append('    static constexpr int ket_pos[%d] = {%s}, bra_pos[%d] = {%s};' % (
+            self.n_bits, ', '.join(map(str, self.ket_pos)), self.n_bits, ', '.join(map(str, self.bra_pos))))
+        lines.append('    static constexpr int ops[%d][5] = %s;' % (len(self.ops), arr(self.ops)))
+        lines.append('    static constexpr int em[%d][3] = %s;' % (len(em), arr(em)))
+        lines.append('    static constexpr int sig[%d] = {%s};' % (len(sig), ', '.join(str(int(v)) for v in sig)))
+        lines.append('};')
+        return '\n'.join(lines) + '\n'
+
+    def throughput_form_eligible(self) -> bool:
+        """Mirror of ``rrc2::Geo<PID>::eligible()``: forward program, DIAG first, dampings last, tile <= 16 elements."""
+        kinds = [op[0] for op in self.ops]
+        if self.n_a * self.n_b > 16 or not kinds or kinds[0] != OP_DIAG or OP_ADT in kinds or OP_DIAG in kinds[1:]:
+            return False
+        tail = [k == OP_AD for k in kinds[1:]]
+        return all(not (a and not b) for a, b in zip(tail, tail[1:]))
+
     def signature(self) -> np.ndarray:
         """Everything the compile-time copy must agree on, as one int32 vector."""
         sig = [self.n_a, self.n_b, self.n_bits] + list(self.ket_pos) + list(self.bra_pos) + [len(self.ops)]

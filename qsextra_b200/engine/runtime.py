@@ -59,6 +59,7 @@ class Engine:
             sm, smem, cc = C.c_int32(), C.c_int32(), C.c_int32()
             cabi.check(self.lib.qsx_device_info(C.byref(sm), C.byref(smem), C.byref(cc)))
         self.sm_count, self.smem_optin, self.cc = sm.value, smem.value, cc.value
+        self.n_shipped_rrc = 20                 # programs of csrc/qsx_rrc_programs.inc (indices below it: shipped menu)
 
     # ---- helpers --------------------------------------------------------------------------
     @contextlib.contextmanager
@@ -173,13 +174,20 @@ class Engine:
                     kind={'populations': 1, 'emission': 2}.get(kind, 0), mu=None if mu is None else np.asarray(mu, dtype=float))
 
     def has_static_rrc(self, prog: dict) -> bool:
-        """Does a compile-time program of the CTA-wide kernel exist for this uploaded program?"""
+        """Can the CTA-wide register-resident kernel run this uploaded program?  Either a compile-time program of the
+        shipped menu has its signature, or ``engine/jit.py`` specialises the kernel for it now (NVRTC; cached on disk)."""
         if prog.get('rrc') is None:
             return False
         sig = prog['rrc_signature']
         found = self.lib.qsx_rrc_find_program(C.c_void_p(sig.ctypes.data), int(sig.size))
         if found < 0:
+            from . import jit
+            if jit.ensure_registered(self.lib, prog['rrc'], sig):
+                found = self.lib.qsx_rrc_find_program(C.c_void_p(sig.ctypes.data), int(sig.size))
+        if found < 0:
             prog['rrc'] = None
+        else:
+            prog['rrc_family'] = 'shipped' if found < self.n_shipped_rrc else 'specialised at run time'
         return found >= 0
 
     def _evolve_rrc(self, prog, sigma_in, n_inst, n_steps, emit, obs, snapshots, inst_set, inst_src):
@@ -310,6 +318,8 @@ class Engine:
         if 'rr' in prog and (obs is None or obs['n'] <= cabi.RR_MAX_OBS):
             return self._evolve_rr(prog, sigma_in, n_inst, n_steps, emit, obs, obs_real, snapshots, inst_set, inst_src)
         blk_ = blk.block
+        if prog.get('rrc') is not None and 'rrc_family' not in prog:
+            self.has_static_rrc(prog)                   # (specialises the kernel for a structure outside the menu)
         rrc_serves = ((not obs_real and (obs is None or (obs.get('kind') == 2 and obs['n'] == 1))) or
                       (obs_real and obs is not None and obs.get('kind') == 1 and obs['n'] == blk_.n_sites and blk_.ka == blk_.kb))
         if prog.get('rrc') is not None and rrc_serves:

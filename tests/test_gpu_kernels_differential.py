@@ -101,8 +101,8 @@ def test_all_kernel_families_agree_with_emulated_operations(engine, name, system
     # the register-resident forms must actually have been exercised where the structure allows it
     if name in ('dimer_modes', 'dimer_markov'):
         assert any('[rr]' in s for s in seen)
-    if name in ('trimer_modes', 'chain4_modes'):
-        assert any('[rrc]' in s for s in seen)
+    if name in ('trimer_modes', 'chain4_modes', 'trimer_ring_modes', 'tetramer_ring_modes'):
+        assert any('[rrc]' in s for s in seen)          # rings: kernels specialised at run time (engine/jit.py)
 
 
 def test_parameter_sets_assembled_on_the_device_match_the_host_recipe(engine):
@@ -235,3 +235,48 @@ def test_throughput_form_of_the_cta_wide_kernel_with_many_instances(engine):
                 if step in emit:
                     got = results['1'][0][inst, emit.index(step)].reshape(blk.dim_a, blk.dim_b)
                     assert np.abs(got - sigma).max() < 1e-12 * scale, (ka, kb, inst, step)
+
+
+def test_structures_outside_the_menu_are_specialised_at_run_time(engine, tmp_path, monkeypatch):
+    """A 4-site ring and a chain with a missing bond have no compile-time program in csrc/qsx_rrc_programs.inc: the
+    CTA-wide kernels are compiled for them with NVRTC on first use (engine/jit.py), registered through the C ABI and
+    serve the forward, the throughput and the transposed form -- no silent drop to the shared-memory pass program."""
+    from qsextra_b200.engine import jit
+    from qsextra_b200.engine.program import StepProgram, SystemBatch
+    monkeypatch.setenv('QSX_JIT_CACHE', str(tmp_path))
+    rng = np.random.default_rng(21)
+    n_sets = 3
+    for label, bonds in (('ring', [(0, 1), (1, 2), (2, 3), (0, 3)]), ('broken chain', [(0, 1), (2, 3)]),
+                         ('long range', [(0, 1), (1, 2), (2, 3), (0, 2)])):
+        J = np.zeros((n_sets, 4, 4))
+        for i, j in bonds:
+            J[:, i, j] = J[:, j, i] = -0.3 + 0.03 * rng.normal(size=n_sets)
+        batch = SystemBatch(1.5 + 0.1 * rng.normal(size=(n_sets, 4)), J, np.ones((n_sets, 4)),
+                            0.3 + 0.05 * rng.normal(size=(n_sets, 1)), np.full((n_sets, 1), 0.7), (2,))
+        prog = StepProgram(batch, 0.15, 1, 1, 0.5 + 0.1 * rng.random((n_sets, 1)))
+        for ka, kb, transposed in ((1, 1, False), (2, 1, False), (2, 1, True)):
+            blk = prog.block(ka, kb)
+            plain = prog.bind(blk, fused=False)
+            bound = plain.transposed() if transposed else plain
+            n_inst = 5
+            sigma0 = rng.normal(size=(n_inst, blk.size)) + 1j * rng.normal(size=(n_inst, blk.size))
+            inst_set = torch.as_tensor(rng.integers(0, n_sets, n_inst), dtype=torch.int32, device=engine.device)
+            for v2 in ('0', '1'):
+                monkeypatch.setenv('QSX_RRC_V2', v2)
+                dev = engine.upload_program(bound, prog)
+                assert dev.get('rrc') is not None, label
+                assert engine.has_static_rrc(dev) and dev['rrc_family'] == 'specialised at run time', (label, ka, kb)
+                _, snap = engine.evolve(dev, engine.to_device(sigma0), n_inst, 3, [0, 1, 3], snapshots=True, inst_set=inst_set)
+                torch.cuda.synchronize()
+                assert dev.get('rrc') is not None                   # the specialised kernel ran (no hand-over)
+                got = snap.cpu().numpy()
+                for inst in range(n_inst):
+                    sigma = sigma0[inst].reshape(blk.dim_a, blk.dim_b)
+                    for step in range(4):
+                        if step:
+                            sigma = emulator.apply_step(sigma, bound, int(inst_set[inst]))
+                        if step in (0, 1, 3):
+                            err = np.abs(got[inst, [0, 1, 3].index(step)].reshape(blk.dim_a, blk.dim_b) - sigma).max()
+                            assert err < 1e-12 * np.abs(sigma0).max(), (label, ka, kb, transposed, v2, inst, step, err)
+    assert len([f for f in os.listdir(str(tmp_path)) if f.endswith('.cubin')]) >= 6          # cached on disk
+    monkeypatch.delenv('QSX_RRC_V2')
