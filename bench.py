@@ -657,7 +657,7 @@ def run_ours(args):
         traffic, traffic_source = ncu_traffic(dom_name)
         blk = program.block(1, 1)
         f_step = survey_flops_per_step(4, 1, blk.size, 3)
-        inst_steps = sum(r['instances'] * r['steps'] for r in dom_rows if 'instances' in r)
+        inst_steps = sum(r['instances'] * r['steps'] for r in dom_rows if r.get('steps') is not None)
         roofline = dict(
             bound='fp64', kernel=dom_name + ' (CTA-wide register-resident kernel: t2 level of se / esa, all members)',
             achieved=dom_tf, peak=fp64_peak, unit='TFLOP/s', frac=dom_tf / fp64_peak if fp64_peak else None,

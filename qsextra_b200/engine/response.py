@@ -338,6 +338,18 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
 
 def _response_local(program: StepProgram, mu, side_seq: str, direction_seq: str, step_counts, eng,
                     shared: dict | None = None):
+    """``_response_tree`` with the caller's current stream restored whatever happens inside (the tree may move to a
+    branch stream half way)."""
+    home = torch.cuda.current_stream(eng.device) if eng.device.type == 'cuda' else None
+    try:
+        return _response_tree(program, mu, side_seq, direction_seq, step_counts, eng, shared)
+    finally:
+        if home is not None and torch.cuda.current_stream(eng.device) != home:
+            torch.cuda.set_stream(home)
+
+
+def _response_tree(program: StepProgram, mu, side_seq: str, direction_seq: str, step_counts, eng,
+                   shared: dict | None = None):
     """Enqueue the tree of one diagram; -> (rank-local signal rows, bookkeeping for ``_finish``: gather over the
     ranks, caller's delay order, host copy).  Arguments as ``response_function``."""
     n_sites = program.n_sites
@@ -385,6 +397,11 @@ def _response_local(program: StepProgram, mu, side_seq: str, direction_seq: str,
             if shared is not None:
                 shared[readout_key] = got
 
+    on_cuda = eng.device.type == 'cuda'
+    home = torch.cuda.current_stream(eng.device) if on_cuda else None     # the stream this diagram was given
+    start_event = base_sets = None                      # fork point of the branch stream; parameter-set ids at level 0
+    branch = None                                       # stream the basis rows continue on (see the substitution)
+
     ka = kb = 0
     block = program.block(0, 0)
     n_sets = n_parameter_sets(program)
@@ -394,6 +411,12 @@ def _response_local(program: StepProgram, mu, side_seq: str, direction_seq: str,
     ground[:, 0] = 1.0                                  # |g><g|, pseudomodes and ancilla in |0>
     sigma = eng.to_device(ground)
     inst_set = torch.arange(n_sets, dtype=torch.int32, device=eng.device) if n_sets > 1 else None
+    if n_sets > 1:                                      # the sets this rank holds (parameter sets are sharded first)
+        set_lo, set_hi = qdist.shard_bounds(n_sets, rank, size) if size > 1 else (0, n_sets)
+        base_sets = torch.arange(set_lo, set_hi, dtype=torch.int32, device=eng.device)
+    if on_cuda and not os.environ.get('QSX_ONE_STREAM'):
+        start_event = torch.cuda.Event()                # fork point: everything a branch stream needs exists by now
+        start_event.record(home)
     n_global = n_sets                                   # instances across all ranks at the current level
     shard_units, rows_per_unit = 0, 1                   # units split over ranks, and rows each has grown into
     sharded = False
@@ -413,7 +436,8 @@ def _response_local(program: StepProgram, mu, side_seq: str, direction_seq: str,
             break
         last = level == len(plan) - 2
         if shared is not None and not last and prefix_key(level) in shared:
-            sigma, n_global, sharded, shard_units, rows_per_unit, inst_set, pending, support = _consume(eng, shared, prefix_key(level))
+            (sigma, n_global, sharded, shard_units, rows_per_unit, inst_set, pending,
+             support) = _consume(eng, shared, prefix_key(level))
             block, ka, kb = new_block, nka, nkb
             continue
         # Basis substitution (linearity).  The n_in states per parameter set that enter this level all live on the
@@ -429,13 +453,25 @@ def _response_local(program: StepProgram, mu, side_seq: str, direction_seq: str,
                 d = len(sup)
                 sup_dev = eng.to_device(sup, torch.int64)
                 coeff = sigma.reshape(local_sets, n_in, block.size).index_select(2, sup_dev).contiguous()
+                coeff_ready = None
+                if start_event is not None:
+                    # The basis rows do not depend on the earlier levels (only the coefficients do): they continue on
+                    # their own stream, forked at the entry of this diagram, and run beside the earlier levels; the
+                    # contraction at the end waits for the coefficients.
+                    coeff_ready = torch.cuda.Event()
+                    coeff_ready.record(torch.cuda.current_stream(eng.device))
+                    eng._branches = getattr(eng, '_branches', 0) + 1
+                    branch = eng.side_stream_of(8 + eng._branches % 4)
+                    branch.wait_event(start_event)
+                    torch.cuda.set_stream(branch)
+                    if base_sets is not None:
+                        base_sets.record_stream(branch)
                 one_hot = np.zeros((d, block.size), dtype=complex)
                 one_hot[np.arange(d), sup] = 1.0
                 sigma = eng.to_device(one_hot)
-                pending = dict(coeff=coeff, n_in=n_in, d=d, after_gather=False)
+                pending = dict(coeff=coeff, n_in=n_in, d=d, after_gather=False, ready=coeff_ready)
                 if n_sets > 1:                          # every set propagates the same d source rows with its own tables
-                    set_ids = inst_set.reshape(local_sets, n_in)[:, 0].contiguous()
-                    inst_set = set_ids.repeat_interleave(d)
+                    inst_set = base_sets.repeat_interleave(d)
                     inst_src = torch.arange(d, dtype=torch.int32, device=eng.device).repeat(local_sets)
                     n_global = n_sets * d
                 else:
@@ -503,6 +539,11 @@ def _response_local(program: StepProgram, mu, side_seq: str, direction_seq: str,
 
     if pending is not None and not pending['after_gather'] and not zero and out is not None and out.shape[0] > 0:
         out = contract_basis(eng, out, pending)
+    if branch is not None:                              # back to the diagram's own stream, which joins the branch
+        torch.cuda.set_stream(home)
+        home.wait_stream(branch)
+        if out is not None and out.is_cuda:
+            out.record_stream(home)
     lead = [n_sets] if n_sets > 1 else []               # ensembles: one signal per parameter set
     info = dict(lead=lead, shape=shape, uniq_len=[len(u) for u in uniq], inverse=inverse, zero=zero, sharded=sharded,
                 shard_units=shard_units, rows_per_unit=rows_per_unit,
@@ -516,6 +557,10 @@ def contract_basis(eng, out, pending):
     """Rows of ``out`` = (set, basis element b, later delays r) x last delay -> (set, incoming state k, r) x last delay:
     out[s, k, r, e] = sum_b coeff[s, k, b] out[s, b, r, e]  (one batched product of the read-out kernel, K = d)."""
     coeff = pending['coeff']                            # [S, n_in, d]
+    if pending.get('ready') is not None and coeff.is_cuda:
+        here = torch.cuda.current_stream(eng.device)
+        here.wait_event(pending['ready'])
+        coeff.record_stream(here)
     n_sets_local, n_in, d = coeff.shape
     n_last = out.shape[1]
     per_basis = out.shape[0] // (n_sets_local * d)

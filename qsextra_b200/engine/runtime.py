@@ -86,7 +86,7 @@ class Engine:
         """Side stream number ``index`` (a small fixed set, created once)."""
         if self._side_stream is None:
             self._side_stream = []
-        index %= 8
+        index %= 12
         while len(self._side_stream) <= index:
             self._side_stream.append(torch.cuda.Stream(device=self.device))
         return self._side_stream[index]
