@@ -12,7 +12,8 @@
 //     dampings end the step, so all of them fold into g of the NEXT step's diagonal multiply (the state kept in
 //     registers lacks the trailing scalings; emissions and snapshots multiply by the per-thread scalar on the way out);
 //   * exciton hops as three shears (tan(theta/2), sin(theta), tan(theta/2)): 6 FMA per pair instead of 4 MUL + 4 FMA;
-//   * shared-memory exchanges synchronise the CTA (bar.sync 0) and alternate between two buffers.
+//   * the bra rotations over warp bits share ONE exchange round (they touch different columns and commute with the
+//     ket side), dampings inside a warp need no CTA barrier: four CTA barriers per step instead of seven.
 // Forward programs only (the transposed read-out propagations are single instances: latency, not throughput).
 #pragma once
 
@@ -34,32 +35,53 @@ struct Geo {
     using BP = BigProg<PID>;
     static constexpr int NA = BP::NA, NB = BP::NB, NBITS = BP::NBITS, M = 1 << NBITS, NT = 1 << (2 * NBITS);
     static constexpr int E = NA * NB * NT, DB = NB * M;
-    static constexpr int popc(int v) { return v == 0 ? 0 : (v & 1) + popc(v >> 1); }
-    // forward program of the expected shape: DIAG first, dampings last, nothing transposed, tile of at most 16 elements
+    static __host__ __device__ constexpr int popc(int v) { return v == 0 ? 0 : (v & 1) + popc(v >> 1); }
+    // Forward program of the expected shape: DIAG first, then hops and pseudomode rotations, dampings last; nothing
+    // transposed; a tile of at most 16 elements; ket rotations exchange over lane bits (warp shuffles).
     static constexpr bool eligible() {
         if (NA * NB > 16 || BP::ops[0][0] != OP_DIAG) return false;
         bool in_tail = false;
         for (int o = 1; o < BP::NOPS; ++o) {
             const int kind = BP::ops[o][0];
             if (kind == OP_ADT || kind == OP_DIAG) return false;
+            if (kind == OP_ROTK && BP::ket_pos[BP::ops[o][1]] >= 5) return false;
+            if (kind == OP_ROTB && BP::bra_pos[BP::ops[o][1]] >= 5)      // one exchange round: disjoint columns only
+                for (int q = 1; q < o; ++q)
+                    if (BP::ops[q][0] == OP_ROTB && BP::bra_pos[BP::ops[q][1]] >= 5 && (BP::ops[q][3] & BP::ops[o][3])) return false;
             if (kind == OP_AD) in_tail = true;
             else if (in_tail) return false;
         }
         return true;
     }
-    static constexpr int buffer_elems() {
-        int need = NA * NB * (NT / 4);
-        for (int o = 0; o < BP::NOPS; ++o) {
-            const int kind = BP::ops[o][0], bit = BP::ops[o][1], mask = BP::ops[o][3];
-            if (kind == OP_ROTK && BP::ket_pos[bit] >= 5 && popc(mask) * NB * NT > need) need = popc(mask) * NB * NT;
-            if (kind == OP_ROTB && BP::bra_pos[bit] >= 5 && popc(mask) * NA * NT > need) need = popc(mask) * NA * NT;
-        }
-        return need;
+    // Shared-memory exchanges of one step and their buffers (complex elements):
+    //   R  all bra rotations over warp bits, written together and separated from their reads by ONE CTA barrier
+    //      (they act on different columns of the tile and commute with every ket-side operation);
+    //   A  dampings whose two thread bits are lane bits: the exchange stays inside a warp (__syncwarp);
+    //   B, C  the other dampings, alternating, one CTA barrier each.
+    // A buffer is rewritten only after a CTA barrier that every reader of its previous contents has passed.
+    static __host__ __device__ constexpr bool rotb_warp(int o) { return BP::ops[o][0] == OP_ROTB && BP::bra_pos[BP::ops[o][1]] >= 5; }
+    static __host__ __device__ constexpr int rotb_offset(int upto) {
+        int off = 0;
+        for (int o = 0; o < upto; ++o)
+            if (rotb_warp(o)) off += popc(BP::ops[o][3]) * NA * NT;
+        return off;
     }
-    static constexpr int BUF = buffer_elems();
+    static __host__ __device__ constexpr int ad_hi(int o) {
+        const int pa = BP::ket_pos[BP::ops[o][1]], pb = BP::bra_pos[BP::ops[o][1]];
+        return pa > pb ? pa : pb;
+    }
+    static __host__ __device__ constexpr int ad_rank(int upto) {            // dampings over a warp bit before operation `upto`
+        int n = 0;
+        for (int o = 0; o < upto; ++o)
+            if (BP::ops[o][0] == OP_AD && ad_hi(o) >= 5) ++n;
+        return n;
+    }
+    static constexpr int R_ELEMS = rotb_offset(BP::NOPS);
+    static constexpr int AD_ELEMS = NA * NB * (NT / 4);
+    static constexpr int BUF = R_ELEMS + 3 * AD_ELEMS;                     // R | A | B | C
     static constexpr int MIN_CTAS = NT >= 256 ? 2 : (512 / NT > 8 ? 8 : 512 / NT);
     static constexpr size_t smem_bytes(int p_doubles) {
-        return (size_t)2 * BUF * sizeof(double2) + (size_t)((p_doubles + 1) & ~1) * sizeof(double) +
+        return (size_t)BUF * sizeof(double2) + (size_t)((p_doubles + 1) & ~1) * sizeof(double) +
                64 * sizeof(double2) + (size_t)BP::NOPS * sizeof(double2);
     }
 };
@@ -74,9 +96,11 @@ __device__ __forceinline__ void pair_shear(double2& x, double2& y, double th, do
     x.y = fma(-th, y.x, x.y);
 }
 
+// Phase 1 of a step, in program order: diagonal multiply, hops of both sides, ket rotations and the bra rotations over
+// lane bits (shuffles); the bra rotations over warp bits are deferred to phase 2 (they commute with all of these).
 template <int PID, int O>
-__device__ __forceinline__ void op2(double2 (&v)[BigProg<PID>::NA][BigProg<PID>::NB], const double2 g, const double* P,
-                                    const double2* H, double2* xbuf, int& cur, int tid) {
+__device__ __forceinline__ void op_first(double2 (&v)[BigProg<PID>::NA][BigProg<PID>::NB], const double2 g, const double* P,
+                                         const double2* H, double2* xbuf, int tid) {
     using BP = BigProg<PID>;
     using G = Geo<PID>;
     constexpr int NA = G::NA, NB = G::NB, NT = G::NT;
@@ -98,8 +122,8 @@ __device__ __forceinline__ void op2(double2 (&v)[BigProg<PID>::NA][BigProg<PID>:
     } else if constexpr (kind == OP_ROTK || kind == OP_ROTB) {
         constexpr bool ket = kind == OP_ROTK;
         constexpr int pos = ket ? BP::ket_pos[a] : BP::bra_pos[a];
-        const double t = ket ? P[slot + 1] : -P[slot + 1];
         if constexpr (pos < 5) {
+            const double t = ket ? P[slot + 1] : -P[slot + 1];
 #pragma unroll
             for (int i = 0; i < NA; ++i)
 #pragma unroll
@@ -110,37 +134,72 @@ __device__ __forceinline__ void op2(double2 (&v)[BigProg<PID>::NA][BigProg<PID>:
                         p.y = __shfl_xor_sync(0xffffffffu, v[i][j].y, 1 << pos);
                         rrc::tan_one(v[i][j], p, t);
                     }
-        } else {
-            double2* buf = xbuf + cur * G::BUF;
-            int e = 0;
-#pragma unroll
-            for (int i = 0; i < NA; ++i)
-#pragma unroll
-                for (int j = 0; j < NB; ++j)
-                    if ((mask >> (ket ? i : j)) & 1) buf[(e++) * NT + tid] = v[i][j];
-            __syncthreads();
-            e = 0;
-#pragma unroll
-            for (int i = 0; i < NA; ++i)
-#pragma unroll
-                for (int j = 0; j < NB; ++j)
-                    if ((mask >> (ket ? i : j)) & 1) rrc::tan_one(v[i][j], buf[(e++) * NT + (tid ^ (1 << pos))], t);
-            cur ^= 1;
         }
-    } else {   // OP_AD without its scalings: the (1,1) threads of the bit pair hand sin^2(phi) x tile to the (0,0) threads
+    }
+}
+
+// Phase 2a (after EVERY ket-side operation and lane-bit rotation of the step: what is written must be the state the
+// partner's rotation acts on): the bra rotations over warp bits write their columns into R.
+template <int PID, int O>
+__device__ __forceinline__ void op_rotb_write(const double2 (&v)[BigProg<PID>::NA][BigProg<PID>::NB], double2* xbuf, int tid) {
+    using BP = BigProg<PID>;
+    using G = Geo<PID>;
+    if constexpr (G::rotb_warp(O)) {
+        constexpr int NA = G::NA, NB = G::NB, NT = G::NT, mask = BP::ops[O][3];
+        double2* buf = xbuf + G::rotb_offset(O);
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < NA; ++i)
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+                if ((mask >> j) & 1) buf[(e++) * NT + tid] = v[i][j];
+    }
+}
+
+// Phase 2b (after the CTA barrier): the bra rotations over warp bits read their partners' columns from R.
+template <int PID, int O>
+__device__ __forceinline__ void op_rotb_read(double2 (&v)[BigProg<PID>::NA][BigProg<PID>::NB], const double* P,
+                                             const double2* xbuf, int tid) {
+    using BP = BigProg<PID>;
+    using G = Geo<PID>;
+    if constexpr (G::rotb_warp(O)) {
+        constexpr int NA = G::NA, NB = G::NB, NT = G::NT;
+        constexpr int a = BP::ops[O][1], mask = BP::ops[O][3], slot = BP::ops[O][4], pos = BP::bra_pos[a];
+        const double t = -P[slot + 1];
+        const double2* buf = xbuf + G::rotb_offset(O);
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < NA; ++i)
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+                if ((mask >> j) & 1) rrc::tan_one(v[i][j], buf[(e++) * NT + (tid ^ (1 << pos))], t);
+    }
+}
+
+// Phase 3: dampings without their scalings -- the (1,1) threads of the bit pair hand their tile to the (0,0) threads,
+// which add sin^2(phi) times it.
+template <int PID, int O>
+__device__ __forceinline__ void op_damp(double2 (&v)[BigProg<PID>::NA][BigProg<PID>::NB], const double* P, double2* xbuf,
+                                        int tid) {
+    using BP = BigProg<PID>;
+    using G = Geo<PID>;
+    if constexpr (BP::ops[O][0] == OP_AD) {
+        constexpr int NA = G::NA, NB = G::NB, NT = G::NT;
+        constexpr int a = BP::ops[O][1], slot = BP::ops[O][4];
         constexpr int pa = BP::ket_pos[a], pb = BP::bra_pos[a];
         constexpr int hi = pa > pb ? pa : pb, lo = pa > pb ? pb : pa;
+        constexpr int which = hi < 5 ? 0 : 1 + (G::ad_rank(O) & 1);          // A | B, C alternating
         const double ss = P[slot + 1];                                        // sin^2 phi
         const int la = (tid >> pa) & 1, lb = (tid >> pb) & 1;
         const int cid = rrc::remove_bit(rrc::remove_bit(tid, hi), lo);
-        double2* buf = xbuf + cur * G::BUF;
+        double2* buf = xbuf + G::R_ELEMS + which * G::AD_ELEMS;
         if (la & lb) {
 #pragma unroll
             for (int i = 0; i < NA; ++i)
 #pragma unroll
                 for (int j = 0; j < NB; ++j) buf[(i * NB + j) * (NT / 4) + cid] = v[i][j];
         }
-        __syncthreads();
+        if constexpr (hi < 5) __syncwarp(); else __syncthreads();
         if (!(la | lb)) {
 #pragma unroll
             for (int i = 0; i < NA; ++i)
@@ -151,14 +210,20 @@ __device__ __forceinline__ void op2(double2 (&v)[BigProg<PID>::NA][BigProg<PID>:
                     v[i][j].y = fma(ss, p.y, v[i][j].y);
                 }
         }
-        cur ^= 1;
+        if constexpr (hi < 5) __syncwarp();              // the warp's region is rewritten by this warp only
     }
 }
 
 template <int PID, int... Os>
 __device__ __forceinline__ void step2(double2 (&v)[BigProg<PID>::NA][BigProg<PID>::NB], const double2 g, const double* P,
-                                      const double2* H, double2* xbuf, int& cur, int tid, qstd::integer_sequence<int, Os...>) {
-    (op2<PID, Os>(v, g, P, H, xbuf, cur, tid), ...);
+                                      const double2* H, double2* xbuf, int tid, qstd::integer_sequence<int, Os...>) {
+    (op_first<PID, Os>(v, g, P, H, xbuf, tid), ...);
+    if constexpr (Geo<PID>::R_ELEMS > 0) {
+        (op_rotb_write<PID, Os>(v, xbuf, tid), ...);
+        __syncthreads();
+        (op_rotb_read<PID, Os>(v, P, xbuf, tid), ...);
+    }
+    (op_damp<PID, Os>(v, P, xbuf, tid), ...);
 }
 
 // per-thread product of the folded damping scalings: 1, cos, cos, cos^2 for (a_q, b_q) = (0,0), (0,1), (1,0), (1,1)
@@ -203,7 +268,7 @@ __global__ void __launch_bounds__(1 << (2 * BigProg<PID>::NBITS), Geo<PID>::MIN_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const qsx_rrc_args& a = k.a;
     double2* xbuf = reinterpret_cast<double2*>(smem_raw);
-    double2* red = xbuf + 2 * G::BUF;
+    double2* red = xbuf + G::BUF;
     double2* H = red + 64;
     double* P = reinterpret_cast<double*>(H + BP::NOPS);
     const int tid = threadIdx.x;
@@ -231,12 +296,11 @@ __global__ void __launch_bounds__(1 << (2 * BigProg<PID>::NBITS), Geo<PID>::MIN_
                 for (int j = 0; j < NB; ++j) v[i][j] = sin[(size_t)((i << NBITS) | ma) * DB + ((j << NBITS) | mb)];
         }
         __syncthreads();
-        int cur = 0;
         int slot = 0;
         int next_emit = a.n_emit > 0 ? a.emit_steps[0] : -1;
         int after_next = a.n_emit > 1 ? a.emit_steps[1] : -1;
         for (int step = 0; step <= a.n_steps && slot < a.n_emit; ++step) {
-            if (step) step2<PID>(v, step == 1 ? g0 : g1, P, H, xbuf, cur, tid, qstd::make_integer_sequence<int, BP::NOPS>{});
+            if (step) step2<PID>(v, step == 1 ? g0 : g1, P, H, xbuf, tid, qstd::make_integer_sequence<int, BP::NOPS>{});
             if (step == next_emit) {
                 const double out_scale = step ? dd : 1.0;          // the trailing damping scalings the registers lack
                 if (a.emit_trace) {

@@ -37,7 +37,7 @@ UNIT = '''#define QSX_RRC_EXTERNAL_PROGRAMS "qsx_jit_program.inc"
 #include "qsx_rrc2.cuh"
 // what the host needs to size a launch: threads, exchange-buffer elements of the two forms, operations
 extern "C" __constant__ int qsx_jit_info[6] = {rrc::Geo<0>::NT, 2 * rrc::Geo<0>::NGROUP * rrc::Geo<0>::BUF,
-                                               %(eligible)d, 2 * rrc2::Geo<0>::BUF, rrc::BigProg<0>::NOPS,
+                                               %(eligible)d, rrc2::Geo<0>::BUF, rrc::BigProg<0>::NOPS,
                                                rrc2::Geo<0>::MIN_CTAS};
 template __global__ void rrc::evolve_rrc_kernel<0>(const rrc::Params);
 %(second)s

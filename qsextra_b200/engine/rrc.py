@@ -81,6 +81,14 @@ class RRCProgram:
     def throughput_form_eligible(self) -> bool:
         """Mirror of ``rrc2::Geo<PID>::eligible()``: forward program, DIAG first, dampings last, tile <= 16 elements."""
         kinds = [op[0] for op in self.ops]
+        if any(op[0] == OP_ROTK and self.ket_pos[op[1]] >= 5 for op in self.ops):
+            return False
+        seen = 0                                        # bra rotations over warp bits share one exchange round
+        for op in self.ops:
+            if op[0] == OP_ROTB and self.bra_pos[op[1]] >= 5:
+                if seen & op[3]:
+                    return False
+                seen |= op[3]
         if self.n_a * self.n_b > 16 or not kinds or kinds[0] != OP_DIAG or OP_ADT in kinds or OP_DIAG in kinds[1:]:
             return False
         tail = [k == OP_AD for k in kinds[1:]]
