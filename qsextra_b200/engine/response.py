@@ -106,7 +106,7 @@ def _last_level(program, plan, uniq, rank, size):
     return block, local if sharded else n_global
 
 
-def _propagate_readout(eng, program, mu, last_block, chains, emit, continuous, stream_index):
+def _propagate_readout(eng, program, mu, last_block, chains, emit, continuous, stream_index, fork_event=None):
     """Enqueue the propagation of the emission read-out of ``last_block`` on a side stream, if the Heisenberg picture
     is planned for this level.  -> (read-outs [n_emit, E] on the device, completion event | None) or None."""
     n_sets = n_parameter_sets(program)
@@ -128,8 +128,11 @@ def _propagate_readout(eng, program, mu, last_block, chains, emit, continuous, s
     np.add.at(readout, np.asarray(idx[ptr[0]:ptr[1]]), np.asarray(w[ptr[0]:ptr[1]]))
     on_gpu = eng.device.type == 'cuda'                   # (the CPU stand-in of the tests has no streams)
     side_stream = eng.side_stream_of(stream_index) if on_gpu else None
-    if on_gpu:
-        side_stream.wait_stream(torch.cuda.current_stream(eng.device))
+    if on_gpu:                                          # fork: after the caller's fork point if it has one (so that the
+        if fork_event is not None:                      # propagation does not queue behind kernels enqueued since),
+            side_stream.wait_event(fork_event)          # else after everything on the current stream
+        else:
+            side_stream.wait_stream(torch.cuda.current_stream(eng.device))
     readouts = None
     with (torch.cuda.stream(side_stream) if on_gpu else contextlib.nullcontext()):
         start = eng.to_device(readout.reshape(1, -1))
@@ -266,30 +269,61 @@ def _set_local(eng, program, mu, sequences, step_counts):
             pending.append((key, (last_block, chains)))
     # longest first: the block size orders the propagation times
     pending.sort(key=lambda item: -(item[1][0].size if item[1][0] is not None else 0))
-    for index, (key, (last_block, chains)) in enumerate(pending):
-        got = _propagate_readout(eng, program, mu, last_block, chains, uniq[-1], continuous, index)
-        if got is not None:
-            shared[key] = got
-    # Every diagram is enqueued before any result is read back.  On the GPU each diagram after the first runs on its own
-    # stream: levels shared between diagrams carry the event of their completion, so e.g. the cheap ground-state level of
-    # gsb fills the SMs the long single-exciton level of se / esa leaves idle in its last wave.
     on_gpu = eng.device.type == 'cuda' and not os.environ.get('QSX_ONE_STREAM')
+
+    fork = None
+    if on_gpu:
+        fork = torch.cuda.Event()
+        fork.record(torch.cuda.current_stream(eng.device))
+
+    def start_readouts(items, first_index):
+        for index, (key, (last_block, chains)) in enumerate(items):
+            got = _propagate_readout(eng, program, mu, last_block, chains, uniq[-1], continuous, first_index + index, fork)
+            if got is not None:
+                shared[key] = got
+
     if not on_gpu or len(sequences) == 1:
+        start_readouts(pending, 0)
         pairs = [_response_local(program, mu, side_seq, direction_seq, step_counts, eng, shared)
                  for side_seq, direction_seq in sequences]
         return [p[0] for p in pairs], [p[1] for p in pairs]
+
+    # Order of enqueueing on the GPU (it decides how early the long kernels start when the host is the slower side):
+    # the longest read-out propagation, then the forward levels of the heaviest diagram (largest block before its last
+    # delay), then the other read-outs and diagrams.  Each diagram after the first runs on its own stream; levels shared
+    # between diagrams carry the event of their completion, so e.g. the cheap ground-state level of gsb fills the SMs the
+    # long single-exciton level of se / esa leaves idle in its last wave.
+    def weight(seq):
+        ka = kb = 0
+        heavy = 0
+        for side, kind in interaction_plan(*seq)[:-2]:
+            delta = +1 if kind == 'X' or (kind == 'raise') == (side == 'k') else -1
+            ka, kb = (ka + delta, kb) if side == 'k' else (ka, kb + delta)
+            blk = Block(program.n_sites, program.n_bits, ka, kb)
+            heavy = max(heavy, blk.size if blk.valid() else 0)
+        return heavy
+
+    order = sorted(range(len(sequences)), key=lambda k: -weight(sequences[k]))
     main = torch.cuda.current_stream(eng.device)
     streams = [main] + [eng.side_stream_of(4 + (k - 1) % 4) for k in range(1, len(sequences))]
     for st in streams[1:]:
         st.wait_stream(main)                            # fork before anything of this call is enqueued on main
     shared['events'] = True                             # shared entries carry (stream, event) of their producer
-    pairs = []
-    for st, (side_seq, direction_seq) in zip(streams, sequences):
+    start_readouts(pending[:1], 0)
+    pairs = [None] * len(sequences)
+    for position, (st, k) in enumerate(zip(streams, order)):
+        side_seq, direction_seq = sequences[k]
         with torch.cuda.stream(st):
-            pair = _response_local(program, mu, side_seq, direction_seq, step_counts, eng, shared)
+            if position == 0 and len(pending) > 1:
+                # the first diagram's early levels before the remaining read-outs (which only the products at the very
+                # end need): its tree is entered with the read-outs it will find in `shared` later, so split the call
+                pair = _response_local(program, mu, side_seq, direction_seq, step_counts, eng, shared,
+                                       before_last=lambda: start_readouts(pending[1:], 1))
+            else:
+                pair = _response_local(program, mu, side_seq, direction_seq, step_counts, eng, shared)
             if st is not main and pair[0] is not None:
                 pair[0].record_stream(main)
-        pairs.append(pair)
+        pairs[k] = pair
     for st in streams[1:]:
         main.wait_stream(st)                            # join
     return [p[0] for p in pairs], [p[1] for p in pairs]
@@ -337,19 +371,19 @@ def response_function(program: StepProgram, mu, side_seq: str, direction_seq: st
 
 
 def _response_local(program: StepProgram, mu, side_seq: str, direction_seq: str, step_counts, eng,
-                    shared: dict | None = None):
+                    shared: dict | None = None, before_last=None):
     """``_response_tree`` with the caller's current stream restored whatever happens inside (the tree may move to a
     branch stream half way)."""
     home = torch.cuda.current_stream(eng.device) if eng.device.type == 'cuda' else None
     try:
-        return _response_tree(program, mu, side_seq, direction_seq, step_counts, eng, shared)
+        return _response_tree(program, mu, side_seq, direction_seq, step_counts, eng, shared, before_last)
     finally:
         if home is not None and torch.cuda.current_stream(eng.device) != home:
             torch.cuda.set_stream(home)
 
 
 def _response_tree(program: StepProgram, mu, side_seq: str, direction_seq: str, step_counts, eng,
-                   shared: dict | None = None):
+                   shared: dict | None = None, before_last=None):
     """Enqueue the tree of one diagram; -> (rank-local signal rows, bookkeeping for ``_finish``: gather over the
     ranks, caller's delay order, host copy).  Arguments as ``response_function``."""
     n_sites = program.n_sites
@@ -388,14 +422,17 @@ def _response_tree(program: StepProgram, mu, side_seq: str, direction_seq: str, 
     readouts = ready = None                             # propagated read-outs and the CUDA event of their completion
     last_block, chains = _last_level(program, plan, uniq, rank, size)
     readout_key = ('readouts', last_block, uniq[-1].tobytes())
-    if shared is not None and readout_key in shared:
-        readouts, ready = shared[readout_key]
-    else:
+
+    def find_readouts():
+        if shared is not None and readout_key in shared:
+            return shared[readout_key]
         got = _propagate_readout(eng, program, mu, last_block, chains, uniq[-1], continuous, 0)
-        if got is not None:
-            readouts, ready = got
-            if shared is not None:
-                shared[readout_key] = got
+        if got is not None and shared is not None:
+            shared[readout_key] = got
+        return got if got is not None else (None, None)
+
+    if before_last is None:                             # (else: looked up when the last level is reached)
+        readouts, ready = find_readouts()
 
     on_cuda = eng.device.type == 'cuda'
     home = torch.cuda.current_stream(eng.device) if on_cuda else None     # the stream this diagram was given
@@ -435,6 +472,10 @@ def _response_tree(program: StepProgram, mu, side_seq: str, direction_seq: str, 
             zero = True
             break
         last = level == len(plan) - 2
+        if last and before_last is not None:            # the caller's deferred work (other read-outs), then ours
+            before_last()
+            before_last = None
+            readouts, ready = find_readouts()
         if shared is not None and not last and prefix_key(level) in shared:
             (sigma, n_global, sharded, shard_units, rows_per_unit, inst_set, pending,
              support) = _consume(eng, shared, prefix_key(level))
