@@ -85,11 +85,11 @@ def n_parameter_sets(program) -> int:
 
 
 def _last_level(program, plan, uniq, rank, size):
-    """(block of the last delay or None if a sector is empty, chains this rank holds there) -- the bookkeeping of
-    ``response_function`` without any propagation."""
+    """(block of the last delay or None if a sector is empty, chains PER PARAMETER SET that enter it, over all ranks)
+    -- the bookkeeping of ``response_function`` without any propagation.  Rank-independent on purpose: every rank must
+    take the same decisions from it (Heisenberg picture or not, and with it whether the last level is sharded)."""
     ka = kb = 0
-    n_sets = n_parameter_sets(program)
-    n_global, local, sharded = n_sets, n_sets, False
+    chains = 1
     block = None
     for level, (side, kind) in enumerate(plan[:-1]):
         delta = +1 if kind == 'X' or (kind == 'raise') == (side == 'k') else -1
@@ -97,13 +97,9 @@ def _last_level(program, plan, uniq, rank, size):
         block = Block(program.n_sites, program.n_bits, ka, kb)
         if not block.valid():
             return None, 0
-        if not sharded and size > 1 and (n_global >= size or n_sets > 1):        # (a lower bound when the tree stays unsharded)
-            lo, hi = qdist.shard_bounds(n_global, rank, size)
-            local, sharded = hi - lo, True
         if level < len(plan) - 2:
-            n_global *= len(uniq[level])
-            local *= len(uniq[level])
-    return block, local if sharded else n_global
+            chains *= len(uniq[level])
+    return block, chains
 
 
 def _propagate_readout(eng, program, mu, last_block, chains, emit, continuous, stream_index, fork_event=None):
@@ -114,7 +110,7 @@ def _propagate_readout(eng, program, mu, last_block, chains, emit, continuous, s
     local_sets = set_hi - set_lo
     if local_sets == 0:
         return None                                     # more ranks than parameter sets: nothing to do on this one
-    if (last_block is None or chains // local_sets < int(os.environ.get('QSX_HEISENBERG_MIN', '8'))
+    if (last_block is None or chains < int(os.environ.get('QSX_HEISENBERG_MIN', '8'))
             or os.environ.get('QSX_DISABLE_HEISENBERG')):
         return None
     back = None
@@ -148,7 +144,7 @@ def _propagate_readout(eng, program, mu, last_block, chains, emit, continuous, s
             # the fused forward passes: then it only pays once the chains outnumber the SMs.
             fast = (bool(os.environ.get('QSX_HEISENBERG_ALWAYS')) or
                     getattr(eng, 'has_static_rrc', lambda p: True)(dev_back))
-            if fast or chains >= 4 * getattr(eng, 'sm_count', 1):
+            if fast or chains * n_sets >= 4 * getattr(eng, 'sm_count', 1):
                 if n_sets > 1:                          # one read-out per parameter set of this rank, same start
                     sets = torch.arange(set_lo, set_hi, dtype=torch.int32, device=eng.device)
                     _, readouts = eng.evolve(dev_back, start, local_sets, int(emit.max()), emit, snapshots=True,
@@ -521,7 +517,8 @@ def _response_tree(program: StepProgram, mu, side_seq: str, direction_seq: str, 
         # has SMs (below that every propagation is latency-bound and a rank gains nothing from holding fewer of them):
         # otherwise every rank evaluates the whole tree and no gather is needed.  Parameter sets are always sharded.
         shard_min = int(os.environ.get('QSX_SHARD_MIN', getattr(eng, 'sm_count', 1)))
-        if not sharded and size > 1 and (n_sets > 1 or (n_global >= size and n_global >= shard_min)):
+        worth_it = not (last and readouts is not None) or 'QSX_SHARD_MIN' in os.environ    # (a product only: not worth it)
+        if not sharded and size > 1 and (n_sets > 1 or (n_global >= size and n_global >= shard_min and worth_it)):
             lo, hi = qdist.shard_bounds(n_global, rank, size)
             sigma = sigma[lo:hi].contiguous()
             if inst_set is not None:
@@ -588,7 +585,8 @@ def _response_tree(program: StepProgram, mu, side_seq: str, direction_seq: str, 
     lead = [n_sets] if n_sets > 1 else []               # ensembles: one signal per parameter set
     info = dict(lead=lead, shape=shape, uniq_len=[len(u) for u in uniq], inverse=inverse, zero=zero, sharded=sharded,
                 shard_units=shard_units, rows_per_unit=rows_per_unit,
-                pending=pending if pending is not None and pending['after_gather'] else None)
+                # (contracted in _finish, after the streams of the tree have joined: no event to wait for there)
+                pending=dict(pending, ready=None) if pending is not None and pending['after_gather'] else None)
     if zero:
         out = torch.zeros(lead + shape, dtype=torch.complex128, device=eng.device)
     return out, info
