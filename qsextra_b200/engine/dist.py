@@ -5,12 +5,31 @@ step: every rank evolves a contiguous slice of the units and one all-gather asse
 """
 from __future__ import annotations
 
+import contextlib
+import threading
+
 import torch
 import torch.distributed as dist
 
+_LOCAL = threading.local()
+
+
+@contextlib.contextmanager
+def local_only():
+    """Inside: ``world()`` answers (0, 1).  For work whose units were split over the ranks by the CALLER (an ensemble whose
+    members each rank lowered for itself): the tree must not split them again; the caller gathers afterwards."""
+    previous = getattr(_LOCAL, 'on', False)
+    _LOCAL.on = True
+    try:
+        yield
+    finally:
+        _LOCAL.on = previous
+
 
 def world():
-    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised or inside ``local_only()``."""
+    if getattr(_LOCAL, 'on', False):
+        return 0, 1
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1

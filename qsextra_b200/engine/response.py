@@ -181,17 +181,17 @@ class ResponsePlan:
         self.graph, self.local, self.infos, self.uploads, self.launches = graph, local, infos, uploads, launches
 
     @classmethod
-    def build(cls, eng, program, mu, sequences, step_counts):
+    def build(cls, eng, program, mu, sequences, step_counts, global_sets=None):
         """Warm pass (fills the upload memo, loads modules, sizes the allocator), then the captured pass."""
         eng._memo = {}
         try:
-            _set_local(eng, program, mu, sequences, step_counts)
+            _tree(eng, program, mu, sequences, step_counts, global_sets)
             torch.cuda.synchronize(eng.device)
             before = eng.launches
             graph = torch.cuda.CUDAGraph()
             eng._capturing = True
             with torch.cuda.graph(graph):
-                local, infos = _set_local(eng, program, mu, sequences, step_counts)
+                local, infos = _tree(eng, program, mu, sequences, step_counts, global_sets)
             return cls(graph, local, infos, eng._memo, eng.launches - before)
         finally:
             eng._memo, eng._capturing = None, False
@@ -213,20 +213,26 @@ def plan_key(program, mu, sequences, step_counts):
                                               'QSX_HEISENBERG_ALWAYS', 'QSX_DISABLE_RR', 'QSX_DISABLE_RRC')))
 
 
-def response_function_set(program: StepProgram, mu, sequences, step_counts, engine=None, device_output: bool = False):
+def response_function_set(program: StepProgram, mu, sequences, step_counts, engine=None, device_output: bool = False,
+                          global_sets: int | None = None):
     """Several diagrams ``sequences = [(side_seq, direction_seq), ...]`` of the same system on the same delay grid (the
     contributions of one 2-D spectrum).  All distinct read-out propagations are enqueued first, each on its own side
     stream, so the longest one (the two-exciton block of esa) runs while the shorter diagrams are evaluated; the delay
     levels the diagrams have in common are computed once (``shared`` of ``response_function``).  -> list of signals.
 
     The second evaluation of the same content on a GPU builds a ``ResponsePlan`` (CUDA graph); later ones replay it
-    (``QSX_DISABLE_GRAPH`` switches this off)."""
+    (``QSX_DISABLE_GRAPH`` switches this off).
+
+    ``global_sets``: the parameter sets of ``program`` are THIS RANK's contiguous share (``dist.shard_bounds``) of an
+    ensemble of that many members which the caller split over the ranks before lowering anything (so that no rank
+    computes tables for members it does not hold); the tree then runs without further sharding and one all-gather per
+    diagram assembles all members' signals on every rank."""
     from .runtime import get_engine
     eng = engine or get_engine()
     continuous = bool(getattr(program, 'continuous', False))
     on_gpu = eng.device.type == 'cuda'
     if on_gpu and not continuous and not os.environ.get('QSX_DISABLE_GRAPH') and hasattr(eng, 'plans'):
-        key = plan_key(program, mu, sequences, step_counts)
+        key = plan_key(program, mu, sequences, step_counts) + (global_sets,)
         plan = eng.plans.get(key)
         if plan is None and key not in eng.plans:
             seen = eng.plan_seen[key] = eng.plan_seen.get(key, 0) + 1
@@ -234,7 +240,7 @@ def response_function_set(program: StepProgram, mu, sequences, step_counts, engi
                 eng.plan_seen.clear()
             if seen >= 2:
                 try:
-                    plan = ResponsePlan.build(eng, program, mu, sequences, step_counts)
+                    plan = ResponsePlan.build(eng, program, mu, sequences, step_counts, global_sets)
                 except Exception as exc:                  # not capturable (e.g. the streaming path synchronises): stay eager
                     import warnings
                     warnings.warn('response tree not captured in a CUDA graph: {!r}'.format(exc))
@@ -244,8 +250,37 @@ def response_function_set(program: StepProgram, mu, sequences, step_counts, engi
                 eng.plans[key] = plan
         if plan is not None:
             return plan.run(eng, device_output)
-    local, infos = _set_local(eng, program, mu, sequences, step_counts)
+    local, infos = _tree(eng, program, mu, sequences, step_counts, global_sets)
     return [_finish(eng, out, info, device_output) for out, info in zip(local, infos)]
+
+
+def _tree(eng, program, mu, sequences, step_counts, global_sets=None):
+    """``_set_local``, or -- for an ensemble the caller already split over the ranks -- ``_set_local`` without any
+    sharding inside, with the bookkeeping ``_finish`` needs to gather the members of all ranks."""
+    if global_sets is None or qdist.world()[1] == 1:
+        return _set_local(eng, program, mu, sequences, step_counts)
+    with qdist.local_only():
+        local, infos = _set_local(eng, program, mu, sequences, step_counts)
+    local_sets = n_parameter_sets(program)
+    out_rows = []
+    for out, info in zip(local, infos):
+        if info['zero']:
+            out = torch.zeros([global_sets] + info['shape'], dtype=torch.complex128, device=eng.device)
+        else:
+            info.update(sharded=True, shard_units=global_sets, rows_per_unit=out.shape[0] // local_sets)
+        info['lead'] = [global_sets]
+        out_rows.append(out)
+    return out_rows, infos
+
+
+def empty_share(eng, sequences, step_counts, global_sets):
+    """What a rank WITHOUT members contributes to the gathers of a pre-split ensemble: no rows, the same bookkeeping."""
+    uniq, inverse = _unique_delays(step_counts, False)
+    rows_per_unit = int(np.prod([len(u) for u in uniq[:-1]])) if len(uniq) > 1 else 1
+    info = dict(lead=[global_sets], shape=[len(c) for c in step_counts], uniq_len=[len(u) for u in uniq], inverse=inverse,
+                zero=False, sharded=True, shard_units=global_sets, rows_per_unit=rows_per_unit, pending=None)
+    empty = torch.zeros((0, len(uniq[-1])), dtype=torch.complex128, device=eng.device)
+    return [empty for _ in sequences], [dict(info) for _ in sequences]
 
 
 def _set_local(eng, program, mu, sequences, step_counts):

@@ -293,9 +293,11 @@ def qspectroscopy_set(system: ChromophoreSystem | ExcitonicSystem,
     return signals
 
 
-def ensemble_program(systems, spectroscopies, **qevolve_kwds):
+def ensemble_program(systems, spectroscopies, members=None, **qevolve_kwds):
     """Checks of ``qspectroscopy_ensemble`` and the objects its evaluation is made of:
-    -> (StepProgram over all members, dipole moments, [(side_seq, direction_seq)], step counts per delay)."""
+    -> (StepProgram over the members, dipole moments, [(side_seq, direction_seq)], step counts per delay).
+    ``members = (lo, hi)``: every system is checked, but only the members lo .. hi-1 are lowered (the share of one rank;
+    ``None`` when the share is empty)."""
     from ...engine.program import StepProgram, SystemBatch
     systems, spectroscopies = list(systems), list(spectroscopies)
     for s_ in systems:
@@ -331,8 +333,14 @@ def ensemble_program(systems, spectroscopies, **qevolve_kwds):
         if type(systems[0]) is ExcitonicSystem:
             rates = rates.reshape(B)
     counts, (dt, dt_trotter, trotter_number, _) = delay_step_counts(delays, qevolve_kwds['dt'], qevolve_kwds.get('Trotter_number', 1))
-    program = StepProgram(SystemBatch.from_systems(systems), dt, trotter_number, qevolve_kwds.get('Trotter_order', 1), rates,
-                          dt_trotter=dt_trotter)
+    if members is not None:
+        lo, hi = members
+        systems = systems[lo:hi]
+        rates = None if rates is None else rates[lo:hi]
+    program = None
+    if systems:
+        program = StepProgram(SystemBatch.from_systems(systems), dt, trotter_number, qevolve_kwds.get('Trotter_order', 1),
+                              rates, dt_trotter=dt_trotter)
     return program, mu, [(sp.side_seq, sp.direction_seq) for sp in spectroscopies], counts
 
 
@@ -365,10 +373,23 @@ def qspectroscopy_ensemble(systems,
         warnings.warn("Pseudomodes not specified. Executing the dynamics with system as an ExcitonicSystem.")
         return qspectroscopy_ensemble([s_.extract_ExcitonicSystem() for s_ in systems], spectroscopies, shots, verbose,
                                       device_output, average, seed, **qevolve_kwds)
-    program, mu, sequences, counts = ensemble_program(systems, spectroscopies, **qevolve_kwds)
+    from ...engine import dist as qdist
+    from ...engine.response import _finish, empty_share
     B = len(systems)
-    signals = response_function_set(program, mu, sequences, counts, device_output=device_output)
-    if B == 1:                                          # a one-member ensemble still carries the ensemble axis
+    rank, size = qdist.world()
+    if size > 1:                                        # every rank lowers and uploads its own members only
+        share = qdist.shard_bounds(B, rank, size)
+        program, mu, sequences, counts = ensemble_program(systems, spectroscopies, members=share, **qevolve_kwds)
+        if program is None:                             # more ranks than members: this one only joins the gathers
+            from ...engine.runtime import get_engine
+            eng = get_engine()
+            signals = [_finish(eng, out, info, device_output) for out, info in zip(*empty_share(eng, sequences, counts, B))]
+        else:
+            signals = response_function_set(program, mu, sequences, counts, device_output=device_output, global_sets=B)
+    else:
+        program, mu, sequences, counts = ensemble_program(systems, spectroscopies, **qevolve_kwds)
+        signals = response_function_set(program, mu, sequences, counts, device_output=device_output)
+    if B == 1 and size == 1:                            # a one-member ensemble still carries the ensemble axis
         signals = [sig[None] for sig in signals]
     if shots:                                           # every member is its own set of estimator runs
         signals = [add_estimator_noise(sig, a, b, mu, shots, None if seed is None else seed + k)

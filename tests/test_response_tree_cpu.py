@@ -312,3 +312,43 @@ def test_structural_support_is_closed_under_the_step():
         for _ in range(12):
             sigma = emulator.apply_step(sigma, bound, 0)
         assert np.all(mask[np.abs(sigma) > 0])
+
+
+# ---- ensembles split by the caller: every rank lowers its own members, the tree runs unsharded, one gather --------
+def _presplit_worker(rank, size, port, out_dir, n_members):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), QSX_DISABLE_RR='1', QSX_HEISENBERG_MIN='2')
+    dist.init_process_group('gloo', rank=rank, world_size=size)
+    try:
+        from qsextra_b200.engine import dist as qdist
+        from qsextra_b200.engine.program import StepProgram, SystemBatch
+        from qsextra_b200.engine.response import _finish, empty_share, response_function_set
+        from qsextra_b200.spectroscopy import FeynmanDiagram
+        systems = _ensemble(n_members)
+        lo, hi = qdist.shard_bounds(n_members, rank, size)
+        diagrams = [FeynmanDiagram(lab, _BASIS_DELAYS) for lab in ('gsb', 'esa')]
+        sequences = [(d.side_seq, d.direction_seq) for d in diagrams]
+        counts, (dt_, dt_trotter, tn, _) = delay_step_counts(diagrams[0].delay_time, 0.15, 1)
+        engine = NumpyEngine()
+        if hi > lo:
+            rates = np.array([[0.2 + 0.01 * b] for b in range(n_members)])[lo:hi]
+            program = StepProgram(SystemBatch.from_systems(systems[lo:hi]), dt_, tn, 1, rates, dt_trotter=dt_trotter)
+            mu = np.asarray(systems[0].dipole_moments, dtype=float)
+            sigs = response_function_set(program, mu, sequences, counts, engine=engine, global_sets=n_members)
+        else:
+            sigs = [_finish(engine, out, info, False) for out, info in zip(*empty_share(engine, sequences, counts, n_members))]
+        np.save(os.path.join(out_dir, 'p%d.npy' % rank), np.array(sigs))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('size,n_members', [(2, 3), (4, 3), (2, 2)])
+def test_ensemble_split_by_the_caller(tmp_path, size, n_members, monkeypatch):
+    """``global_sets``: ranks hold 2 + 1 members, 1 + 1 + 1 + 0 members (one rank only joins the gathers) or one member
+    each (a one-set program locally); every rank ends up with all members' signals."""
+    monkeypatch.setenv('QSX_DISABLE_RR', '1')
+    monkeypatch.setenv('QSX_HEISENBERG_MIN', '2')
+    want = np.array(_ensemble_signals(_ensemble(n_members), ('gsb', 'esa'), _BASIS_DELAYS, NumpyEngine()))
+    mp.spawn(_presplit_worker, args=(size, _free_port(), str(tmp_path), n_members), nprocs=size, join=True)
+    for r in range(size):
+        got = np.load(os.path.join(str(tmp_path), 'p%d.npy' % r))
+        assert got.shape == want.shape and np.abs(got - want).max() < 1e-12
