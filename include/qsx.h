@@ -42,7 +42,7 @@ typedef long long int64_t;
 extern "C" {
 #endif
 
-#define QSX_ABI_VERSION 18
+#define QSX_ABI_VERSION 19
 
 enum {
     QSX_OK = 0,
@@ -251,6 +251,34 @@ int32_t qsx_evolve_rrc(const qsx_rrc_args* args, void* stream);
 /* Index of the compile-time program of qsx_evolve_rrc with this signature (HOST int32 vector), or -1 when the call
  * would answer "no compile-time program matches"; lets the host plan before it enqueues anything. */
 int32_t qsx_rrc_find_program(const int32_t* signature, int32_t n_signature);
+
+/* Host-side lowering of one propagation step into the operation list of qsx_evolve, for callers that are not Python
+ * (the Python binding lowers in qsextra_b200/engine/program.py and covers more: d > 2 pseudomodes, Suzuki formulas,
+ * batches of parameter sets).  Model family: N sites, W two-level pseudomodes per site (0: an excitonic system),
+ * order-1 Trotter formula, `trotter_number` Trotter steps of dt / trotter_number followed by one collision round
+ * (pseudomode damping with coll_rates[k], or dephasing with coll_rates[0] when n_modes == 0; NULL: no collisions).
+ * Reference: qsextra/qcomo/evolution/qevolve.py:74-105, :197-253, :264-348, :419-422.  Everything is HOST memory; the
+ * caller uploads `ops`, `params` (one parameter set, stride n_params) and the block tables and fills qsx_evolve_args. */
+typedef struct qsx_system_desc {
+    int32_t n_sites;
+    int32_t n_modes;
+    const double* energies;     /* [N] */
+    const double* couplings;    /* [N*N] symmetric, zero diagonal */
+    const double* omega;        /* [W] pseudomode frequencies, or NULL when n_modes == 0 */
+    const double* coupl_ep;     /* [W] exciton-pseudomode couplings, or NULL */
+    const double* coll_rates;   /* [W] damping rates / [1] dephasing rate / NULL */
+    double dt;                  /* collision step */
+    int32_t trotter_number;
+} qsx_system_desc;
+
+/* Sizes of the program of the (ka, kb) exciton-number block: operations, doubles per parameter set, configurations per
+ * side and pseudomode qubits (block dimensions nA << n_bits, nB << n_bits).  Output pointers may be NULL. */
+int32_t qsx_step_program_size(const qsx_system_desc* sys, int32_t ka, int32_t kb, int32_t* n_ops, int32_t* n_params,
+                              int32_t* n_a, int32_t* n_b, int32_t* n_bits);
+
+/* Fill ops [n_ops], params [n_params], cfg_a [nA], cfg_b [nB], rank_a / rank_b [2^N] (the tables of qsx_block). */
+int32_t qsx_step_program_build(const qsx_system_desc* sys, int32_t ka, int32_t kb, qsx_op* ops, double* params,
+                               int32_t* cfg_a, int32_t* cfg_b, int32_t* rank_a, int32_t* rank_b);
 
 /* Add a kernel specialisation compiled at run time (engine/jit.py: NVRTC on csrc/qsx_rrc.cuh + csrc/qsx_rrc2.cuh around
  * the program's own BigProg<0> table) to the programs qsx_evolve_rrc can run: `cubin` is loaded into the current

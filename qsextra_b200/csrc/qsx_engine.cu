@@ -1272,6 +1272,8 @@ static int launch(const qsx_rrc_args& a, bool want_second, int sms, int smem_max
 
 }  // namespace jit
 
+#include "qsx_builder.cuh"
+
 int32_t qsx_rrc_register(const void* cubin, int64_t cubin_bytes, const char* kernel_name, const char* kernel2_name,
                          const int32_t* signature, int32_t n_signature) {
     if (!cubin || cubin_bytes <= 0 || !kernel_name || !signature || n_signature <= 0)

@@ -11,11 +11,11 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libqsx.so')
-ABI_VERSION = 18
+ABI_VERSION = 19
 ERR_NO_PROGRAM = -4
 
 EXPORTS = ('qsx_abi_version', 'qsx_last_error', 'qsx_device_info', 'qsx_evolve_workspace_bytes', 'qsx_evolve',
-           'qsx_evolve_rr', 'qsx_bind_params', 'qsx_rr_tables', 'qsx_evolve_rrc', 'qsx_rrc_find_program', 'qsx_rrc_register', 'qsx_apply_dipole', 'qsx_readout_gemm_workspace_bytes', 'qsx_readout_gemm',
+           'qsx_evolve_rr', 'qsx_bind_params', 'qsx_rr_tables', 'qsx_evolve_rrc', 'qsx_rrc_find_program', 'qsx_rrc_register', 'qsx_step_program_size', 'qsx_step_program_build', 'qsx_apply_dipole', 'qsx_readout_gemm_workspace_bytes', 'qsx_readout_gemm',
            'qsx_readout_gemm_batched_workspace_bytes', 'qsx_readout_gemm_batched', 'qsx_rotating_frame', 'qsx_spectrum_shift',
            'qsx_lindblad_workspace_bytes', 'qsx_lindblad_evolve',
            'qsx_fp64_peak')
@@ -24,6 +24,12 @@ RR_MAX_OPS, RR_MAX_OBS, RR_MAX_ENTRIES = 24, 8, 4
 
 class QsxError(RuntimeError):
     pass
+
+
+class QsxSystemDesc(C.Structure):
+    _fields_ = [('n_sites', C.c_int32), ('n_modes', C.c_int32), ('energies', C.c_void_p), ('couplings', C.c_void_p),
+                ('omega', C.c_void_p), ('coupl_ep', C.c_void_p), ('coll_rates', C.c_void_p), ('dt', C.c_double),
+                ('trotter_number', C.c_int32)]
 
 
 class QsxOp(C.Structure):
@@ -136,6 +142,10 @@ def load():
     lib.qsx_rrc_find_program.restype = C.c_int32
     lib.qsx_rrc_register.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int32]
     lib.qsx_rrc_register.restype = C.c_int32
+    lib.qsx_step_program_size.argtypes = [C.POINTER(QsxSystemDesc), C.c_int32, C.c_int32] + [C.POINTER(C.c_int32)] * 5
+    lib.qsx_step_program_size.restype = C.c_int32
+    lib.qsx_step_program_build.argtypes = [C.POINTER(QsxSystemDesc), C.c_int32, C.c_int32] + [C.c_void_p] * 6
+    lib.qsx_step_program_build.restype = C.c_int32
     lib.qsx_apply_dipole.argtypes = [C.POINTER(QsxBlock), C.POINTER(QsxBlock), C.c_int32, C.c_void_p, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
     lib.qsx_apply_dipole.restype = C.c_int32

@@ -298,3 +298,27 @@ def test_basis_substitution_on_the_gpu(engine, monkeypatch):
         assert np.abs(a - b).max() < 1e-11 * scale
         ref, _ = fast.response_points(s, spec, rows, dt, coll_rates=[0.2], kraus=True)
         assert np.abs(np.array([a[i, j] for i, j in rows]) - ref).max() < 1e-10 * scale
+
+
+def test_qsx_evolve_driven_by_the_c_program_builder(engine):
+    """A caller that is not Python: the step program comes from qsx_step_program_build (C, host side) instead of
+    engine/program.py, goes to qsx_evolve as it is, and the populations equal the oracle's."""
+    from test_cabi import c_built_program
+    from qsextra_b200 import ChromophoreSystem
+    from qsextra_b200.engine.sectors import population_observables
+    s = ChromophoreSystem(energies=[1.55, 1.46], couplings=-0.01, dipole_moments=[1., 1.], frequencies_pseudomode=0.02,
+                          levels_pseudomode=2, couplings_ep=0.054)
+    s.set_state('localized excitation', 0)
+    dt = 0.1 / 0.658212
+    steps = np.arange(0, 61, 10)
+    want = R.qevolve_exact(s, steps * dt, dt=dt, coll_rates=[0.2])['populations']
+    from qsextra_b200.qcomo.evolution.qevolve import _program_for, _validate_rates
+    blk = _program_for(s, dt, dt, 1, 1, _validate_rates(s, [0.2])).block(1, 1)
+    ops, params, cfg_a, cfg_b, n_bits = c_built_program(s, 1, 1, dt, [0.2], 1)
+    dev = dict(block=engine.device_block(blk), ops=engine.to_device(ops, torch.int32), params=engine.to_device(params[None, :]),
+               n_ops=len(ops), stride=len(params), n_sets=1, n_passes=0, team=0, bound=None)
+    sigma0 = np.zeros((1, blk.size), dtype=complex)
+    sigma0[0, 0] = 1.0                                   # |site 0 excited, modes 0><same|
+    obs = engine.upload_observables(*population_observables(blk), kind='populations')
+    got, _ = engine.evolve(dev, engine.to_device(sigma0), 1, int(steps.max()), steps, obs=obs, obs_real=True)
+    assert np.abs(got.cpu().numpy()[0] - want).max() < 1e-10
