@@ -303,6 +303,7 @@ def test_basis_substitution_on_the_gpu(engine, monkeypatch):
 def test_qsx_evolve_driven_by_the_c_program_builder(engine):
     """A caller that is not Python: the step program comes from qsx_step_program_build (C, host side) instead of
     engine/program.py, goes to qsx_evolve as it is, and the populations equal the oracle's."""
+    import torch
     from test_cabi import c_built_program
     from qsextra_b200 import ChromophoreSystem
     from qsextra_b200.engine.sectors import population_observables
