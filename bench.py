@@ -676,7 +676,7 @@ def run_ours(args):
             what='executed FP64 flops of the kernel (counted from its operation list, RRCProgram.executed_flops_per_step) '
                  '/ its launch durations (CUDA events on the launching stream, traced evaluation of the same step)',
             peak_source='qsx_fp64_peak DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)',
-            launches_per_step=dom['launches'], kernel_ms_per_step=dom['ms'], share_of_step=dom['ms'] / traced_ms,
+            launches_per_step=dom['launches'], kernel_ms_per_step=dom['ms'], share_of_step=dom['ms'] / mean_step_ms,
             instance_steps_per_step=inst_steps,
             fp64_pipe_utilisation_estimate=dom['fp64_instructions'] / (dom['ms'] * 1e-3) / (64 * eng.sm_count * sm_clock) if dom['ms'] else None,
             survey_formula=dict(flops_per_collision_step=f_step,
