@@ -598,6 +598,7 @@ __global__ void __launch_bounds__(256) evolve_kernel(const EvolveParams k) {
 #include "qsx_rr.cuh"
 #include "qsx_rrc.cuh"
 #include "qsx_rrc2.cuh"
+#include "qsx_rrc3.cuh"
 #include "qsx_gemm.cuh"
 #include "qsx_post.cuh"
 #include "qsx_lindblad.cuh"
@@ -1336,7 +1337,12 @@ int32_t qsx_evolve_rrc(const qsx_rrc_args* a, void* stream) {
     // QSX_RRC_V2=0 / 1 switches it off / on for every instance count (A/B runs and tests).
     const char* v2 = getenv("QSX_RRC_V2");
     const bool want_v2 = v2 ? (v2[0] != '0') : (a->n_inst >= 2 * sms);
-    int r = want_v2 ? rrc2::launch<0>(*a, sms, smem_max, (cudaStream_t)stream) : 1;
+    // Among those, levels that emit rarely run the third form (damping diagonalised by a change of coordinates that is
+    // undone around every emission, qsx_rrc3.cuh); QSX_RRC_V3=0 / 1 likewise.
+    const char* v3 = getenv("QSX_RRC_V3");
+    const bool want_v3 = v3 ? (v3[0] != '0') : (want_v2 && (long long)a->n_emit * 8 <= (long long)a->n_steps + 8);
+    int r = want_v3 ? rrc3::launch<0>(*a, sms, smem_max, (cudaStream_t)stream) : 1;
+    if (r == 1 && want_v2) r = rrc2::launch<0>(*a, sms, smem_max, (cudaStream_t)stream);
     if (r == 1) r = rrc::launch<0>(*a, sms, smem_max, (cudaStream_t)stream);
     if (r == 1) {                                   // a structure specialised at run time (qsx_rrc_register)?
         r = jit::launch(*a, want_v2, sms, smem_max, (cudaStream_t)stream);

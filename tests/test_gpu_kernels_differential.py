@@ -91,8 +91,9 @@ def test_all_kernel_families_agree_with_emulated_operations(engine, name, system
         scale = np.abs(want).max()
         variants = [('op list', plain, False, None), ('pass program', prog.bind(blk), False, None),
                     ('register-resident, generic', plain, True, {'QSX_RR_NO_STATIC': '1', 'QSX_DISABLE_RRC': '1'}),
-                    ('register-resident, best', plain, True, {'QSX_RRC_V2': '0'}),
-                    ('register-resident, throughput form of the CTA-wide kernel', plain, True, {'QSX_RRC_V2': '1'})]
+                    ('register-resident, best', plain, True, {'QSX_RRC_V2': '0', 'QSX_RRC_V3': '0'}),
+                    ('register-resident, throughput form of the CTA-wide kernel', plain, True, {'QSX_RRC_V2': '1', 'QSX_RRC_V3': '0'}),
+                    ('register-resident, damping-diagonal form of the CTA-wide kernel', plain, True, {'QSX_RRC_V2': '1', 'QSX_RRC_V3': '1'})]
         for label, bound, use_rr, env in variants:
             got, dev = run_engine(engine, prog, bound, sigma0, use_rr, env)
             err = np.abs(got - want).max()
@@ -181,7 +182,8 @@ def test_readout_gemm_against_numpy(engine, m, n, k):
 
 
 def test_throughput_form_of_the_cta_wide_kernel_with_many_instances(engine):
-    """qsx_rrc2.cuh (two CTAs per SM, folded damping scalings, shear hops) against the first form and the emulated
+    """qsx_rrc2.cuh (two CTAs per SM, folded damping scalings, shear hops) and qsx_rrc3.cuh (damping diagonalised by a
+    change of coordinates that is undone around every emission) against the first form and the emulated
     operations: 300 instances of the 4-site chain's (1,1) block with different parameter sets and shared source rows,
     snapshots and trace read-outs at irregular steps (step 0 included: no folded scaling is pending there)."""
     from qsextra_b200.engine.program import StepProgram, SystemBatch
@@ -202,8 +204,9 @@ def test_throughput_form_of_the_cta_wide_kernel_with_many_instances(engine):
         inst_src = torch.as_tensor(rng.integers(0, n_src, n_inst), dtype=torch.int32, device=engine.device)
         emit = [0, 1, 4, 9]
         results = {}
-        for flag in ('0', '1'):
-            os.environ['QSX_RRC_V2'] = flag
+        for flag, v3 in (('0', '0'), ('1', '0'), ('3', '1')):
+            os.environ['QSX_RRC_V2'] = '0' if flag == '0' else '1'
+            os.environ['QSX_RRC_V3'] = v3
             try:
                 dev = engine.upload_program(bound, prog)
                 assert dev.get('rrc') is not None
@@ -223,9 +226,11 @@ def test_throughput_form_of_the_cta_wide_kernel_with_many_instances(engine):
                 results[flag] = (snap.cpu().numpy(), pops.cpu().numpy())
             finally:
                 os.environ.pop('QSX_RRC_V2', None)
+                os.environ.pop('QSX_RRC_V3', None)
         scale = np.abs(results['0'][0]).max()
-        assert np.abs(results['0'][0] - results['1'][0]).max() < 1e-12 * scale, (ka, kb)
-        assert np.abs(results['0'][1] - results['1'][1]).max() < 1e-12 * np.abs(results['0'][1]).max(), (ka, kb)
+        for flag in ('1', '3'):
+            assert np.abs(results['0'][0] - results[flag][0]).max() < 1e-12 * scale, (ka, kb, flag)
+            assert np.abs(results['0'][1] - results[flag][1]).max() < 1e-12 * np.abs(results['0'][1]).max(), (ka, kb, flag)
         sets, srcs = inst_set.cpu().numpy(), inst_src.cpu().numpy()
         for inst in (0, 151, 299):                           # the emulated operations, a few instances
             sigma = sigma0[srcs[inst]].reshape(blk.dim_a, blk.dim_b)
@@ -233,8 +238,9 @@ def test_throughput_form_of_the_cta_wide_kernel_with_many_instances(engine):
                 if step:
                     sigma = emulator.apply_step(sigma, bound, int(sets[inst]))
                 if step in emit:
-                    got = results['1'][0][inst, emit.index(step)].reshape(blk.dim_a, blk.dim_b)
-                    assert np.abs(got - sigma).max() < 1e-12 * scale, (ka, kb, inst, step)
+                    for flag in ('1', '3'):
+                        got = results[flag][0][inst, emit.index(step)].reshape(blk.dim_a, blk.dim_b)
+                        assert np.abs(got - sigma).max() < 1e-12 * scale, (ka, kb, flag, inst, step)
 
 
 def test_structures_outside_the_menu_are_specialised_at_run_time(engine, tmp_path, monkeypatch):
