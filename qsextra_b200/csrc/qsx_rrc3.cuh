@@ -127,13 +127,17 @@ __device__ __forceinline__ void op_first(double2 (&v)[BigProg<PID>::NA][BigProg<
     } else if constexpr (kind == OP_ROTK) {
         constexpr int pk = BP::ket_pos[a], pb = BP::bra_pos[a];
         if constexpr (G::k_deferred(O)) {
-            double2* buf = kbuf + G::k_offset(O);
-            int e = 0;
+            // only the threads with the partner bit CLEAR need the value across it, so only those with the bit SET
+            // write (a warp bit: whole warps write, whole warps read)
+            if ((tid >> pb) & 1) {
+                double2* buf = kbuf + G::k_offset(O);
+                int e = 0;
 #pragma unroll
-            for (int i = 0; i < NA; ++i)
+                for (int i = 0; i < NA; ++i)
 #pragma unroll
-                for (int j = 0; j < NB; ++j)
-                    if ((mask >> i) & 1) buf[(e++) * NT + tid] = v[i][j];
+                    for (int j = 0; j < NB; ++j)
+                        if ((mask >> i) & 1) buf[(e++) * NT + tid] = v[i][j];
+            }
         } else {
             const double t = P[slot + 1];
             const int la = (tid >> pk) & 1, lb = (tid >> pb) & 1;
@@ -176,9 +180,12 @@ __device__ __forceinline__ void op_k_deferred(double2 (&v)[BigProg<PID>::NA][Big
             for (int j = 0; j < NB; ++j)
                 if ((mask >> i) & 1) {
                     double2 p = shfl_xor2(v[i][j], 1 << pk);
-                    const double2 q = buf[(e++) * NT + (tid ^ (1 << pb))];
-                    p.x = fma(w, q.x, p.x);
-                    p.y = fma(w, q.y, p.y);
+                    if (!lb) {
+                        const double2 q = buf[e * NT + (tid ^ (1 << pb))];
+                        p.x = fma(w, q.x, p.x);
+                        p.y = fma(w, q.y, p.y);
+                    }
+                    ++e;
                     rrc::tan_one(v[i][j], p, t);
                 }
     }
