@@ -230,6 +230,14 @@ def ncu_traffic(kernel_key):
     return (hit.get('dram_bytes_per_launch'), hit.get('source')) if hit else (None, None)
 
 
+def ncu_capture(kernel_key):
+    """Everything profiles/ncu_traffic.json holds about a kernel (per-instance figures of its committed ncu capture)."""
+    try:
+        return json.load(open(os.path.join(REPO, 'profiles', 'ncu_traffic.json'))).get(kernel_key) or {}
+    except (OSError, ValueError):
+        return {}
+
+
 def survey_flops_per_step(n_sites, n_modes, stored_elements, n_bonds):
     """F_step = E (6 n_Z + 12 n_R + 2.5 n_AD) for the d = 2 pseudomode step (un-fused gate list)."""
     n_z = n_sites + n_sites * n_modes
@@ -665,14 +673,30 @@ def run_ours(args):
         total_flops = sum(s['executed_flops'] for s in kernel_sums.values())
         busy_ms = sum(s['ms'] for s in kernel_sums.values())
         mean_step_ms = float(np.mean(step_ms))
-        traffic, traffic_source = ncu_traffic(dom_name)
+        capture = ncu_capture(dom_name)
+        dom_instances = sum(r['instances'] for r in dom_rows) / max(1, dom['launches'])
+        traffic = traffic_source = data_pipe = None
+        if capture.get('dram_bytes_per_instance'):
+            traffic, traffic_source = int(capture['dram_bytes_per_instance'] * dom_instances), capture.get('source')
+        if capture.get('lsu_wavefronts_per_instance_step') and dom['ms']:
+            # the pipe that bounds this kernel: one wavefront of warp shuffles / shared-memory accesses per SM and clock
+            per = capture['lsu_wavefronts_per_instance_step']
+            rate = per * sum(r['instances'] * r['steps'] for r in dom_rows if r.get('steps') is not None) / (dom['ms'] * 1e-3)
+            peak_rate = eng.sm_count * sm_clock
+            data_pipe = dict(bound='shared-memory / shuffle data pipe (l1tex__data_pipe_lsu_wavefronts)', achieved=rate / 1e9,
+                             peak=peak_rate / 1e9, unit='Gwavefronts/s', frac=rate / peak_rate,
+                             wavefronts_per_instance_step=per,
+                             ncu_pct_of_peak_sustained_elapsed=capture.get('lsu_data_pipe_pct_of_elapsed_cycles'),
+                             note='wavefronts per instance-step from the committed ncu capture of this kernel x the instance-steps '
+                                  'of this run / its device time here; peak = 1 wavefront per SM and clock at the sampled SM '
+                                  'clock.  This, not FP64 issue, is what the kernel runs against (profiles/r2_c4_rrc3_kernel.md)')
         blk = program.block(1, 1)
         f_step = survey_flops_per_step(4, 1, blk.size, 3)
         inst_steps = sum(r['instances'] * r['steps'] for r in dom_rows if r.get('steps') is not None)
         roofline = dict(
             bound='fp64', kernel=dom_name + ' (CTA-wide register-resident kernel: t2 level of se / esa, all members)',
             achieved=dom_tf, peak=fp64_peak, unit='TFLOP/s', frac=dom_tf / fp64_peak if fp64_peak else None,
-            traffic=traffic, traffic_source=traffic_source,
+            traffic=traffic, traffic_source=traffic_source, data_pipe=data_pipe,
             what='executed FP64 flops of the kernel (counted from its operation list, RRCProgram.executed_flops_per_step) '
                  '/ its launch durations (CUDA events on the launching stream, traced evaluation of the same step)',
             peak_source='qsx_fp64_peak DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)',
@@ -708,8 +732,9 @@ def run_ours(args):
                     dtype='f64', data='synthetic', config=workload_config(world, M),
                     clocks=clocks, gpu_launches=launches, cuda_graph=uses_graph,
                     collective_ms=gather_ms if world > 1 else 0.0,
-                    collective='all_gather_into_tensor of the rank-local signal rows (3 diagrams) + reshaping, timed alone on the rows '
-                               'of the traced evaluation (smallest of five, max over ranks); it is inside every timed step',
+                    collective='all_gather_into_tensor of the rank-local signal rows (one per diagram, equal shares gathered '
+                               'straight into the result) + reshaping, timed alone on the rows of the traced evaluation (smallest '
+                               'of five, max over ranks); it is inside every timed step',
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d),
                              d2h_bytes_per_step=int(sum(p.numel() for p in pinned) * 16),
                              api='qsextra_b200.spectroscopy.qspectroscopy_ensemble(new ChromophoreSystem realisations every '

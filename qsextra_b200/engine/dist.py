@@ -46,13 +46,22 @@ def shard_bounds(n_units: int, rank: int | None = None, size: int | None = None)
 
 def all_gather_rows(local: torch.Tensor, n_units: int, rows_per_unit: int = 1) -> torch.Tensor:
     """Concatenate the row-slices of all ranks into [n_units * rows_per_unit, ...].  Rank r holds the rows of the
-    units ``shard_bounds(n_units, r)``, ``rows_per_unit`` consecutive rows each.  A single collective: slices are
-    padded to the largest slice so ``all_gather_into_tensor`` applies."""
+    units ``shard_bounds(n_units, r)``, ``rows_per_unit`` consecutive rows each.  A single collective: equal slices
+    are gathered straight into the result, unequal ones are padded to the largest slice so that
+    ``all_gather_into_tensor`` applies."""
     rank, size = world()
     if size == 1:
         return local
     rows = [tuple(v * rows_per_unit for v in shard_bounds(n_units, r, size)) for r in range(size)]
     width = max(hi - lo for lo, hi in rows)
+    if all(hi - lo == width for lo, hi in rows):        # equal shares: no padding, no reassembly
+        source = local.contiguous()
+        gathered = local.new_empty((size * width,) + tuple(local.shape[1:]))
+        if source.is_complex():
+            dist.all_gather_into_tensor(torch.view_as_real(gathered), torch.view_as_real(source))
+        else:
+            dist.all_gather_into_tensor(gathered, source)
+        return gathered
     padded = local.new_zeros((width,) + tuple(local.shape[1:]))
     padded[:local.shape[0]] = local
     gathered = local.new_empty((size * width,) + tuple(local.shape[1:]))
