@@ -625,6 +625,19 @@ def run_ours(args):
         dist.all_reduce(t_g, op=dist.ReduceOp.MAX)
     gather_ms = float(t_g.item())
     del traced
+    # ... and one evaluation with every launch on ONE stream: the duration of each kernel running alone (in the step the
+    # kernels of different streams share the SMs, which stretches each of them)
+    os.environ['QSX_ONE_STREAM'] = '1'
+    eng.trace = []
+    t_alone = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_alone.record()
+    alone_rows, alone_infos = R._tree(eng, program, mu, sequences, counts, global_sets)
+    barrier()
+    os.environ.pop('QSX_ONE_STREAM')
+    alone_trace, eng.trace = eng.trace, None
+    _, alone_sums = trace_table(alone_trace, t_alone)
+    del alone_rows, alone_infos
 
     # ---- end to end through the public API: host objects in (new realisations every step), pinned host signals out ---
     lo, hi = rank * M, (rank + 1) * M
@@ -632,10 +645,9 @@ def run_ours(args):
 
     def e2e_once(seed):
         fresh = c4_members(M * world, seed=seed)
-        sigs = qspectroscopy_ensemble(fresh, specs, shots=0, verbose=False, device_output=True, **kw)
-        for buf, sig in zip(pinned, sigs):                       # every rank reads back its own members: together the
-            buf.copy_(sig[lo:hi], non_blocking=True)            # complete result is in host memory once
-        torch.cuda.synchronize()
+        # every rank reads back its own members (together the complete result is in host memory once); the copy of a
+        # diagram starts when the diagram is complete, beside the diagrams that still run; returns after the copies
+        qspectroscopy_ensemble(fresh, specs, shots=0, verbose=False, device_output=True, host_out=pinned, **kw)
 
     e2e_once(100)
     h2d0 = eng.h2d_bytes
@@ -690,13 +702,21 @@ def run_ours(args):
                              note='wavefronts per instance-step from the committed ncu capture of this kernel x the instance-steps '
                                   'of this run / its device time here; peak = 1 wavefront per SM and clock at the sampled SM '
                                   'clock.  This, not FP64 issue, is what the kernel runs against (profiles/r2_c4_rrc3_kernel.md)')
+        alone = None
+        if alone_sums.get(dom_name, {}).get('ms'):
+            a_ms = alone_sums[dom_name]['ms']
+            alone = dict(kernel_ms_per_step=a_ms, achieved=dom['executed_flops'] / (a_ms * 1e-3) / 1e12,
+                         frac=dom['executed_flops'] / (a_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
+                         data_pipe_frac=None if data_pipe is None else data_pipe['frac'] * dom['ms'] / a_ms,
+                         note='the same launches with the whole evaluation on one stream (no other kernel shares the SMs): '
+                              'what ncu measures; the figures above are taken inside the multi-stream step')
         blk = program.block(1, 1)
         f_step = survey_flops_per_step(4, 1, blk.size, 3)
         inst_steps = sum(r['instances'] * r['steps'] for r in dom_rows if r.get('steps') is not None)
         roofline = dict(
             bound='fp64', kernel=dom_name + ' (CTA-wide register-resident kernel: t2 level of se / esa, all members)',
             achieved=dom_tf, peak=fp64_peak, unit='TFLOP/s', frac=dom_tf / fp64_peak if fp64_peak else None,
-            traffic=traffic, traffic_source=traffic_source, data_pipe=data_pipe,
+            traffic=traffic, traffic_source=traffic_source, data_pipe=data_pipe, alone=alone,
             what='executed FP64 flops of the kernel (counted from its operation list, RRCProgram.executed_flops_per_step) '
                  '/ its launch durations (CUDA events on the launching stream, traced evaluation of the same step)',
             peak_source='qsx_fp64_peak DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)',
@@ -738,7 +758,8 @@ def run_ours(args):
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d),
                              d2h_bytes_per_step=int(sum(p.numel() for p in pinned) * 16),
                              api='qsextra_b200.spectroscopy.qspectroscopy_ensemble(new ChromophoreSystem realisations every '
-                                 'step, FeynmanDiagram x 3) -> signals in pinned host memory (each rank its own members)'),
+                                 'step, FeynmanDiagram x 3, host_out = pinned tensors) -> signals in pinned host memory (each '
+                                 'rank its own members)'),
                     roofline=roofline, cpu_baseline=cpu_baseline,
                     parity_max_rel_err_vs_oracle=None if parity is None else parity['max_rel_err'], parity=parity,
                     wall_s_timed_region=wall, collision_steps=extras_c2, spectroscopy=extras_spec)

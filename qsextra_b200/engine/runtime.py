@@ -88,7 +88,11 @@ class Engine:
             self._side_stream = []
         index %= 12
         while len(self._side_stream) <= index:
-            self._side_stream.append(torch.cuda.Stream(device=self.device))
+            # streams 0-3 carry the read-out propagations: a few CTAs that walk every step alone and are needed at the
+            # very end -- they must not queue behind a level that fills every SM, hence the higher priority (inside a
+            # captured response plan the kernel nodes inherit it)
+            priority = -1 if len(self._side_stream) < 4 and not os.environ.get('QSX_FLAT_PRIORITIES') else 0
+            self._side_stream.append(torch.cuda.Stream(device=self.device, priority=priority))
         return self._side_stream[index]
 
     def device_block(self, block: Block) -> DeviceBlock:

@@ -351,6 +351,7 @@ def qspectroscopy_ensemble(systems,
                            device_output: bool = False,
                            average: bool = False,
                            seed: int | None = None,
+                           host_out=None,
                            **qevolve_kwds,
                            ) -> list:
     """The diagrams ``spectroscopies`` for an ENSEMBLE of systems in one batched evaluation (new API: the reference
@@ -363,7 +364,13 @@ def qspectroscopy_ensemble(systems,
     level is one batched product (``engine.response``).  Under ``torch.distributed`` the MEMBERS are sharded over the
     ranks (contiguous slices) and one all-gather assembles the result on every rank.
     Returns one array per diagram with a leading ensemble axis, ``[len(systems), *grid]`` (``average=True``: the
-    ensemble mean, ``[*grid]``)."""
+    ensemble mean, ``[*grid]``).
+
+    ``host_out``: one pinned complex128 CPU tensor per diagram, shaped ``[members of THIS rank, *grid]`` (all members
+    without ``torch.distributed``).  The exact signals (before any estimator noise) of the rank's own members are
+    copied into them while the evaluation still runs -- each diagram as soon as it is complete, so that only the last
+    diagram's copy is left at the end -- and the call returns after the copies have finished.  Together with
+    ``device_output=True`` this is the fastest way to get the result into host memory."""
     systems, spectroscopies = list(systems), list(spectroscopies)
     if not systems or not spectroscopies:
         return []
@@ -372,11 +379,16 @@ def qspectroscopy_ensemble(systems,
             _validate_system(s_)
         warnings.warn("Pseudomodes not specified. Executing the dynamics with system as an ExcitonicSystem.")
         return qspectroscopy_ensemble([s_.extract_ExcitonicSystem() for s_ in systems], spectroscopies, shots, verbose,
-                                      device_output, average, seed, **qevolve_kwds)
+                                      device_output, average, seed, host_out, **qevolve_kwds)
     from ...engine import dist as qdist
-    from ...engine.response import _finish, empty_share
+    from ...engine.response import HostRows, _finish, empty_share
     B = len(systems)
     rank, size = qdist.world()
+    rows = None
+    if host_out is not None:
+        if len(host_out) != len(spectroscopies):
+            raise ValueError('host_out needs one tensor per diagram')
+        rows = HostRows(host_out)
     if size > 1:                                        # every rank lowers and uploads its own members only
         share = qdist.shard_bounds(B, rank, size)
         program, mu, sequences, counts = ensemble_program(systems, spectroscopies, members=share, **qevolve_kwds)
@@ -385,12 +397,23 @@ def qspectroscopy_ensemble(systems,
             eng = get_engine()
             signals = [_finish(eng, out, info, device_output) for out, info in zip(*empty_share(eng, sequences, counts, B))]
         else:
-            signals = response_function_set(program, mu, sequences, counts, device_output=device_output, global_sets=B)
+            signals = response_function_set(program, mu, sequences, counts, device_output=device_output, global_sets=B,
+                                            host_out=rows)
     else:
         program, mu, sequences, counts = ensemble_program(systems, spectroscopies, **qevolve_kwds)
-        signals = response_function_set(program, mu, sequences, counts, device_output=device_output)
+        signals = response_function_set(program, mu, sequences, counts, device_output=device_output, host_out=rows)
     if B == 1 and size == 1:                            # a one-member ensemble still carries the ensemble axis
         signals = [sig[None] for sig in signals]
+    if rows is not None:
+        import torch
+        lo, hi = qdist.shard_bounds(B, rank, size)
+        for k, (target, done) in enumerate(zip(rows.tensors, rows.copied)):
+            if target is not None and not done:         # (not copied on the way: from the finished signal)
+                mine = signals[k][lo:hi]
+                target.copy_(mine if isinstance(mine, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(mine)),
+                             non_blocking=True)
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
     if shots:                                           # every member is its own set of estimator runs
         signals = [add_estimator_noise(sig, a, b, mu, shots, None if seed is None else seed + k)
                    for k, ((a, b), sig) in enumerate(zip(sequences, signals))]

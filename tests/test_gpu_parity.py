@@ -323,3 +323,26 @@ def test_qsx_evolve_driven_by_the_c_program_builder(engine):
     obs = engine.upload_observables(*population_observables(blk), kind='populations')
     got, _ = engine.evolve(dev, engine.to_device(sigma0), 1, int(steps.max()), steps, obs=obs, obs_real=True)
     assert np.abs(got.cpu().numpy()[0] - want).max() < 1e-10
+
+
+def test_ensemble_signals_copied_to_pinned_host_memory_on_the_way(engine):
+    """``qspectroscopy_ensemble(host_out=...)``: every diagram's rows leave for the pinned host tensors as soon as the
+    diagram is complete (ascending delays), or from the finished signal (unsorted delays: the rows are not the caller's
+    grid yet).  Both must equal the returned signals; eager evaluation, captured plan and replay alike."""
+    import torch
+    from qsextra_b200 import ChromophoreSystem
+    from qsextra_b200.spectroscopy import FeynmanDiagram, qspectroscopy_ensemble
+    rng = np.random.default_rng(5)
+    members = [ChromophoreSystem(energies=(np.array([1.55, 1.50, 1.46]) + 0.01 * rng.normal(size=3)).tolist(),
+                                 couplings=[[0, -.01, 0], [-.01, 0, -.01], [0, -.01, 0]], dipole_moments=[1., 0.8, 1.1],
+                                 frequencies_pseudomode=0.02, levels_pseudomode=2, couplings_ep=0.054) for _ in range(5)]
+    dt = 0.15
+    kw = dict(verbose=False, dt=dt, coll_rates=[0.2])
+    for t2 in ([0., 3 * dt], [3 * dt, 0.]):
+        delays = [(dt * np.arange(12)).tolist(), t2, (2 * dt * np.arange(9)).tolist()]
+        specs = [FeynmanDiagram(lab, delays) for lab in ('gsb', 'se', 'esa')]
+        for _ in range(3):
+            pinned = [torch.zeros((5, 12, 2, 9), dtype=torch.complex128).pin_memory() for _ in specs]
+            signals = qspectroscopy_ensemble(members, specs, host_out=pinned, **kw)
+            for got, want in zip(pinned, signals):
+                assert np.abs(want).max() > 0 and np.array_equal(got.numpy(), want)
