@@ -44,3 +44,4 @@ for s in (102, 103, 104):
     once(s, log=True)
 cProfile.run('once(105)', '/tmp/ens.prof')
 pstats.Stats('/tmp/ens.prof').sort_stats('tottime').print_stats(30)
+pstats.Stats('/tmp/ens.prof').sort_stats('cumtime').print_stats('qsextra_b200|bench', 45)
