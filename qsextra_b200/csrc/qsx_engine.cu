@@ -1337,10 +1337,12 @@ int32_t qsx_evolve_rrc(const qsx_rrc_args* a, void* stream) {
     // QSX_RRC_V2=0 / 1 switches it off / on for every instance count (A/B runs and tests).
     const char* v2 = getenv("QSX_RRC_V2");
     const bool want_v2 = v2 ? (v2[0] != '0') : (a->n_inst >= 2 * sms);
-    // Among those, levels that emit rarely run the third form (damping diagonalised by a change of coordinates that is
-    // undone around every emission, qsx_rrc3.cuh); QSX_RRC_V3=0 / 1 likewise.
+    // Levels that emit rarely run the third form (damping diagonalised by a change of coordinates that is undone
+    // around every emission, qsx_rrc3.cuh) whatever their instance count: alone on an SM it also walks a step in fewer
+    // cycles than the first form (64 x 64 block: 4.3 k against 5.6 k, 16 x 64: 0.86 k against 1.58 k, tools/rrc_latency.py);
+    // QSX_RRC_V3=0 / 1 switches it off / on for every emission schedule.
     const char* v3 = getenv("QSX_RRC_V3");
-    const bool want_v3 = v3 ? (v3[0] != '0') : (want_v2 && (long long)a->n_emit * 8 <= (long long)a->n_steps + 8);
+    const bool want_v3 = v3 ? (v3[0] != '0') : ((long long)a->n_emit * 8 <= (long long)a->n_steps + 8);
     int r = want_v3 ? rrc3::launch<0>(*a, sms, smem_max, (cudaStream_t)stream) : 1;
     if (r == 1 && want_v2) r = rrc2::launch<0>(*a, sms, smem_max, (cudaStream_t)stream);
     if (r == 1) r = rrc::launch<0>(*a, sms, smem_max, (cudaStream_t)stream);

@@ -228,7 +228,8 @@ class HostRows:
 def _copy_local_rows(host_out, k, out, info):
     """Start the copy of diagram k's rank-local signal rows into ``host_out.tensors[k]`` on the current stream.  Only rows
     that already are the caller's grid (ascending distinct delays, nothing left to contract) can go out this early."""
-    if host_out is None or host_out.tensors[k] is None or out is None or not out.is_cuda:
+    if (host_out is None or host_out.tensors[k] is None or out is None or not out.is_cuda
+            or os.environ.get('QSX_DISABLE_EARLY_COPY')):
         return
     plain = all(len(inv) == n and np.array_equal(inv, np.arange(n)) for inv, n in zip(info['inverse'], info['uniq_len']))
     target = host_out.tensors[k]
