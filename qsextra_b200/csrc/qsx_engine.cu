@@ -599,6 +599,7 @@ __global__ void __launch_bounds__(256) evolve_kernel(const EvolveParams k) {
 #include "qsx_rrc.cuh"
 #include "qsx_rrc2.cuh"
 #include "qsx_rrc3.cuh"
+#include "qsx_rrc3t.cuh"
 #include "qsx_gemm.cuh"
 #include "qsx_post.cuh"
 #include "qsx_lindblad.cuh"
@@ -1344,6 +1345,7 @@ int32_t qsx_evolve_rrc(const qsx_rrc_args* a, void* stream) {
     const char* v3 = getenv("QSX_RRC_V3");
     const bool want_v3 = v3 ? (v3[0] != '0') : ((long long)a->n_emit * 8 <= (long long)a->n_steps + 8);
     int r = want_v3 ? rrc3::launch<0>(*a, sms, smem_max, (cudaStream_t)stream) : 1;
+    if (r == 1 && want_v3) r = rrc3t::launch<0>(*a, sms, smem_max, (cudaStream_t)stream);    // (transposed steps)
     if (r == 1 && want_v2) r = rrc2::launch<0>(*a, sms, smem_max, (cudaStream_t)stream);
     if (r == 1) r = rrc::launch<0>(*a, sms, smem_max, (cudaStream_t)stream);
     if (r == 1) {                                   // a structure specialised at run time (qsx_rrc_register)?

@@ -194,6 +194,11 @@ def build(program: StepProgram, bound: BoundProgram) -> RRCProgram | None:
     params[:, n_w + 2 * (1 << nb):shift] = np.ascontiguousarray(gm_b).view(np.float64)
     for op in ops:
         op[4] += shift if op[0] != OP_DIAG else 0
+    # the damping-diagonal forms divide by the product of the damping cosines at emissions: keep them away from
+    # collisions that empty a pseudomode (almost) completely in one step (the general kernel serves those)
+    damp_cos = [params[:, op[4]] for op in ops if op[0] == OP_AD]
+    if damp_cos and float(np.min(np.abs(damp_cos))) < 1e-3:
+        return None
     if transposed:
         ops = [[OP_ADT if op[0] == OP_AD else op[0]] + op[1:] for op in reversed(ops)]
     emission = []

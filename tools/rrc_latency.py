@@ -31,3 +31,28 @@ for ka, kb in ((1, 1), (0, 1), (1, 0)):
                 ref = out
             print('(%d,%d) %3d instances  %-12s %.3f ms = %.0f SM-cycles per step   max |diff to first form| %.2e' % (
                 ka, kb, n_inst, label, ms, ms * 1e-3 * 1.965e9 / 1500, float((out - ref).abs().max())))
+
+# transposed steps (the read-out propagations of the Heisenberg picture): one instance per member, an emission every 15
+# steps; first form against the damping-diagonal form for transposed programs (qsx_rrc3t.cuh)
+for ka, kb in ((1, 0), (0, 1), (2, 1)):
+    block = program.block(ka, kb)
+    dev = eng.upload_program(program.bind(block, fused=False).transposed(), program)
+    rng = np.random.default_rng(1)
+    for n_inst in (1, 8):
+        sigma = eng.to_device(rng.normal(size=(n_inst, block.size)) + 1j * rng.normal(size=(n_inst, block.size)))
+        emit = eng.to_device(np.arange(0, 1906, 15), torch.int32)
+        ref = None
+        for label, v3 in (('first form', '0'), ('damping-diagonal', '1')):
+            os.environ['QSX_RRC_V2'], os.environ['QSX_RRC_V3'] = '0', v3
+            run = lambda: eng.evolve(dev, sigma, n_inst, 1905, emit, snapshots=True)[1]
+            out = run(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                out = run()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            if ref is None:
+                ref = out
+            print('(%d,%d) transposed %d instance(s)  %-17s %.3f ms = %.0f SM-cycles per step   max |diff| %.2e of %.2e' % (
+                ka, kb, n_inst, label, ms, ms * 1e-3 * 1.965e9 / 1905, float((out - ref).abs().max()), float(ref.abs().max())))
