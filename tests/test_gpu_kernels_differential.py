@@ -243,6 +243,53 @@ def test_throughput_form_of_the_cta_wide_kernel_with_many_instances(engine):
                         assert np.abs(got - sigma).max() < 1e-12 * scale, (ka, kb, flag, inst, step)
 
 
+def test_damping_diagonal_form_of_the_transposed_steps(engine):
+    """qsx_rrc3t.cuh (read-out propagations: z(1,1) = W(1,1) - W(0,0) per damped pseudomode, dampings folded into the
+    diagonal multiply that ends the step, transform undone and redone around every emission) against the first form
+    and the emulated transposed operations: the (1,0), (0,1) blocks (ket rotations on disjoint rows: one shared round)
+    and the two-exciton block (2,1) (every row belongs to two ket rotations: one round per rotation), several parameter
+    sets, snapshots at irregular steps including step 0 and consecutive steps."""
+    from qsextra_b200.engine.program import StepProgram, SystemBatch
+    rng = np.random.default_rng(17)
+    n_sets, n_inst = 4, 9
+    J = np.zeros((n_sets, 4, 4))
+    for i in range(3):
+        J[:, i, i + 1] = J[:, i + 1, i] = -0.3 + 0.02 * rng.normal(size=n_sets)
+    batch = SystemBatch(1.5 + 0.1 * rng.normal(size=(n_sets, 4)), J, np.ones((n_sets, 4)),
+                        0.3 + 0.05 * rng.normal(size=(n_sets, 1)), np.full((n_sets, 1), 0.7), (2,))
+    prog = StepProgram(batch, 0.15, 1, 1, 0.5 + 0.1 * rng.random((n_sets, 1)))
+    emit = [0, 1, 2, 7, 12]
+    for ka, kb in ((1, 0), (0, 1), (2, 1)):
+        blk = prog.block(ka, kb)
+        bound = prog.bind(blk, fused=False).transposed()
+        sigma0 = rng.normal(size=(n_inst, blk.size)) + 1j * rng.normal(size=(n_inst, blk.size))
+        inst_set = torch.as_tensor(rng.integers(0, n_sets, n_inst), dtype=torch.int32, device=engine.device)
+        results = {}
+        for v3 in ('0', '1'):
+            os.environ['QSX_RRC_V2'], os.environ['QSX_RRC_V3'] = '0', v3
+            try:
+                dev = engine.upload_program(bound, prog)
+                assert dev.get('rrc') is not None
+                _, snap = engine.evolve(dev, engine.to_device(sigma0), n_inst, 12, emit, snapshots=True, inst_set=inst_set)
+                torch.cuda.synchronize()
+                assert dev.get('rrc') is not None
+                results[v3] = snap.cpu().numpy()
+            finally:
+                os.environ.pop('QSX_RRC_V2', None)
+                os.environ.pop('QSX_RRC_V3', None)
+        scale = np.abs(results['0']).max()
+        assert np.abs(results['0'] - results['1']).max() < 1e-12 * scale, (ka, kb)
+        sets = inst_set.cpu().numpy()
+        for inst in (0, 4, 8):
+            sigma = sigma0[inst].reshape(blk.dim_a, blk.dim_b)
+            for step in range(13):
+                if step:
+                    sigma = emulator.apply_step(sigma, bound, int(sets[inst]))
+                if step in emit:
+                    got = results['1'][inst, emit.index(step)].reshape(blk.dim_a, blk.dim_b)
+                    assert np.abs(got - sigma).max() < 1e-12 * scale, (ka, kb, inst, step)
+
+
 def test_structures_outside_the_menu_are_specialised_at_run_time(engine, tmp_path, monkeypatch):
     """A 4-site ring and a chain with a missing bond have no compile-time program in csrc/qsx_rrc_programs.inc: the
     CTA-wide kernels are compiled for them with NVRTC on first use (engine/jit.py), registered through the C ABI and
