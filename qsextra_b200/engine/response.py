@@ -212,7 +212,8 @@ def plan_key(program, mu, sequences, step_counts):
     return (_fingerprint(program), np.asarray(mu, dtype=float).tobytes(), tuple((a, b) for a, b in sequences),
             tuple(np.asarray(c).tobytes() for c in step_counts), rank, size,
             tuple(os.environ.get(k) for k in ('QSX_DISABLE_BASIS', 'QSX_DISABLE_HEISENBERG', 'QSX_HEISENBERG_MIN',
-                                              'QSX_HEISENBERG_ALWAYS', 'QSX_DISABLE_RR', 'QSX_DISABLE_RRC')))
+                                              'QSX_HEISENBERG_ALWAYS', 'QSX_DISABLE_RR', 'QSX_DISABLE_RRC',
+                                              'QSX_DISABLE_PULLBACK')))
 
 
 class HostRows:
@@ -611,7 +612,14 @@ def _response_tree(program: StepProgram, mu, side_seq: str, direction_seq: str, 
             if sharded and level < len(plan) - 2:
                 rows_per_unit *= len(emit)
             continue
-        sigma = eng.apply_dipole(block, new_block, 0 if side == 'k' else 1, mu_dev, sigma)
+        # Last interaction before a product with propagated read-outs: <W, O sigma> = <O^T W, sigma>.  When the interaction
+        # ENLARGES the block (esa: 64 x 64 -> 96 x 64) the transposed dipole is applied to the few read-outs instead of the
+        # many chains -- the collective operator between two sector blocks is real, and its transpose is the same operator
+        # with the blocks exchanged -- and the product runs over the smaller block (QSX_DISABLE_PULLBACK: the chains).
+        pull_back = (last and readouts is not None and new_block.size > block.size and not continuous
+                     and not os.environ.get('QSX_DISABLE_PULLBACK'))
+        if not pull_back:
+            sigma = eng.apply_dipole(block, new_block, 0 if side == 'k' else 1, mu_dev, sigma)
         prev_block = block
         block, ka, kb = new_block, nka, nkb
         dev = None if last and readouts is not None else upload(block)
@@ -631,12 +639,18 @@ def _response_tree(program: StepProgram, mu, side_seq: str, direction_seq: str, 
                 readouts.record_stream(main)
             if inst_src is not None:                    # basis rows shared by the sets: one copy per instance
                 sigma = sigma.index_select(0, inst_src.long())
+            weights, width = readouts, block.size
+            if pull_back:
+                width = prev_block.size
+                weights = eng.apply_dipole(block, prev_block, 0 if side == 'k' else 1, mu_dev,
+                                           readouts.reshape(-1, block.size).contiguous()).reshape(
+                                               tuple(readouts.shape[:-1]) + (width,))
             if n_sets > 1:                              # whole sets per rank, equally many chains each: batched product
-                local_sets = readouts.shape[0]
-                out = eng.readout_gemm(sigma.reshape(local_sets, n_local // local_sets, block.size).contiguous(),
-                                       readouts.contiguous()).reshape(n_local, len(emit))
+                local_sets = weights.shape[0]
+                out = eng.readout_gemm(sigma.reshape(local_sets, n_local // local_sets, width).contiguous(),
+                                       weights.contiguous()).reshape(n_local, len(emit))
             else:
-                out = eng.readout_gemm(sigma.reshape(n_local, block.size).contiguous(), readouts.contiguous())
+                out = eng.readout_gemm(sigma.reshape(n_local, width).contiguous(), weights.contiguous())
         else:
             obs = eng.upload_observables(*block.emission_observable(np.asarray(mu, dtype=float)), kind='emission', mu=mu)
             out, _ = propagate(dev, sigma, n_local, emit, obs=obs, **sets_kw)
