@@ -42,7 +42,7 @@ typedef long long int64_t;
 extern "C" {
 #endif
 
-#define QSX_ABI_VERSION 19
+#define QSX_ABI_VERSION 20
 
 enum {
     QSX_OK = 0,
@@ -244,6 +244,12 @@ typedef struct qsx_rrc_args {
     double mu[16];
     double* out_obs;             /* DEVICE [n_inst][n_emit] complex128 / [n_inst][n_emit][n_sites] float64, or NULL */
     double* out_snap;            /* DEVICE [n_inst][n_emit][DA*DB] complex128, logical order, or NULL */
+    int32_t* progress;           /* DEVICE [n_inst + 1] ZEROED before the call, or NULL.  With it, a launch that only writes
+                                  * snapshots and holds more instances than the GPU keeps resident is scheduled by SEGMENTS
+                                  * (the steps between two emissions): CTAs claim (instance, segment) pairs in order and
+                                  * continue an instance from its last snapshot, so the last round of instances no longer
+                                  * leaves SMs idle.  Same results; [i] counts the emissions of instance i done, [n_inst]
+                                  * is the claim counter. */
 } qsx_rrc_args;
 
 int32_t qsx_evolve_rrc(const qsx_rrc_args* args, void* stream);

@@ -437,6 +437,102 @@ __global__ void __launch_bounds__(1 << (2 * BigProg<PID>::NBITS), Geo<PID>::MIN_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same propagation scheduled by SEGMENTS (the steps between two emissions) for launches that only write snapshots
+// and hold more instances than the GPU keeps resident.  With one CTA per instance from start to end, 512 instances on
+// 296 resident CTAs take two full rounds although the second round is only 73 % full.  Here the CTAs claim
+// (instance, segment) pairs from one counter, in the order segment-major / instance-minor, and continue an instance
+// from the snapshot its previous segment left in `out_snap` (the transform to the damping-diagonal coordinates is
+// applied at every emission anyway, so a reload costs one pass over 64 KiB): every CTA ends up with the same number of
+// segments.  A claimed pair waits for `progress[inst]` to reach its segment; pairs are claimed in dependency order by
+// CTAs that are RUNNING, so the oldest unfinished pair never waits for a CTA that has not started (no deadlock when
+// other kernels keep some SMs busy).  Same arithmetic per segment as the kernel above.
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int PID>
+__global__ void __launch_bounds__(1 << (2 * BigProg<PID>::NBITS), Geo<PID>::MIN_CTAS) evolve_rrc3_segments_kernel(const Params k) {
+    using BP = BigProg<PID>;
+    using G = Geo<PID>;
+    constexpr int NA = G::NA, NB = G::NB, NBITS = G::NBITS, M = G::M, NT = G::NT, DB = G::DB, E = G::E;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int claimed;
+    const qsx_rrc_args& a = k.a;
+    double2* xbuf = reinterpret_cast<double2*>(smem_raw);
+    double2* red = xbuf + G::BUF;
+    double2* H = red + 64;
+    double* P = reinterpret_cast<double*>(H + BP::NOPS);
+    double2* shift_buf = xbuf + G::K_ELEMS;
+    const int tid = threadIdx.x;
+    int ma, mb;
+    rrc::thread_modes<PID>(tid, ma, mb, qstd::make_integer_sequence<int, NBITS>{});
+    constexpr auto all_ops = qstd::make_integer_sequence<int, BP::NOPS>{};
+    int* progress = a.progress;
+    int* counter = a.progress + a.n_inst;
+    const long long n_pairs = (long long)a.n_inst * a.n_emit;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) claimed = atomicAdd(counter, 1);
+        __syncthreads();
+        const int pair = claimed;
+        if (pair >= n_pairs) break;
+        const int inst = pair % a.n_inst, seg = pair / a.n_inst;
+        const int set = a.inst_set ? a.inst_set[inst] : 0;
+        const int src = a.inst_src ? a.inst_src[inst] : inst;
+        const double* Pg = a.params + (size_t)set * a.param_stride;
+        for (int i = tid; i < a.param_stride; i += NT) P[i] = Pg[i];
+        if (seg > 0 && tid == 0)
+            while (ld_acquire(progress + inst) < seg) __nanosleep(256);
+        __syncthreads();
+        if (tid == 0) rrc2::hop_table<PID>(P, H, all_ops);
+        const double2 g0 = cmul_conj(reinterpret_cast<const double2*>(P + 2 * NA * NB)[ma],
+                                     reinterpret_cast<const double2*>(P + 2 * NA * NB + 2 * M)[mb]);
+        const double dd = rrc2::damp_scales<PID>(P, tid, all_ops);
+        const double2 g1 = make_double2(g0.x * dd, g0.y * dd);
+        double2* snaps = reinterpret_cast<double2*>(a.out_snap) + (size_t)inst * a.n_emit * E;
+        double2 v[NA][NB];
+        {
+            // (written by another SM a moment ago: read through L2)
+            const double2* from = seg == 0 ? reinterpret_cast<const double2*>(a.sigma_in) + (size_t)src * E
+                                           : snaps + (size_t)(seg - 1) * E;
+#pragma unroll
+            for (int i = 0; i < NA; ++i)
+#pragma unroll
+                for (int j = 0; j < NB; ++j) v[i][j] = __ldcg(from + (size_t)((i << NBITS) | ma) * DB + ((j << NBITS) | mb));
+        }
+        pair_shifts<PID>(v, +1.0, shift_buf, tid, all_ops);     // sigma -> u = T sigma
+        __syncthreads();
+        const int first = seg == 0 ? 0 : a.emit_steps[seg - 1], last = a.emit_steps[seg];
+        for (int step = first + 1; step <= last; ++step) step3<PID>(v, step == first + 1 ? g0 : g1, P, H, xbuf, tid, all_ops);
+        const double out_scale = last > first ? dd : 1.0;       // the pending damping scalings, then T^-1
+#pragma unroll
+        for (int i = 0; i < NA; ++i)
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                v[i][j].x *= out_scale;
+                v[i][j].y *= out_scale;
+            }
+        pair_shifts<PID>(v, -1.0, shift_buf, tid, all_ops);
+        {
+            double2* dst = snaps + (size_t)seg * E;
+#pragma unroll
+            for (int i = 0; i < NA; ++i)
+#pragma unroll
+                for (int j = 0; j < NB; ++j) dst[(size_t)((i << NBITS) | ma) * DB + ((j << NBITS) | mb)] = v[i][j];
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release(progress + inst, seg + 1);
+    }
+}
+
 #ifndef __CUDACC_RTC__
 // 0: launched, 1: no eligible compile-time program, < 0: CUDA error code (negated)
 template <int PID>
@@ -458,9 +554,17 @@ int launch(const qsx_rrc_args& a, int sms, int smem_max, cudaStream_t stream) {
             if (e != cudaSuccess) return -(int)e;
             if (per_sm < 1) per_sm = 1;
             int grid = sms * per_sm;
-            if (grid > a.n_inst) grid = a.n_inst;
             Params k;
             k.a = a;
+            if (a.progress && a.out_snap && !a.emit_trace && a.n_emit > 1 && a.n_inst > grid) {
+                // more instances than resident CTAs and nothing but snapshots to write: schedule by segments
+                e = cudaFuncSetAttribute(evolve_rrc3_segments_kernel<PID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return -(int)e;
+                evolve_rrc3_segments_kernel<PID><<<grid, G::NT, smem, stream>>>(k);
+                e = cudaGetLastError();
+                return e == cudaSuccess ? 0 : -(int)e;
+            }
+            if (grid > a.n_inst) grid = a.n_inst;
             evolve_rrc3_kernel<PID><<<grid, G::NT, smem, stream>>>(k);
             e = cudaGetLastError();
             return e == cudaSuccess ? 0 : -(int)e;

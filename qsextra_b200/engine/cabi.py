@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libqsx.so')
-ABI_VERSION = 19
+ABI_VERSION = 20
 ERR_NO_PROGRAM = -4
 
 EXPORTS = ('qsx_abi_version', 'qsx_last_error', 'qsx_device_info', 'qsx_evolve_workspace_bytes', 'qsx_evolve',
@@ -88,7 +88,7 @@ class QsxRRCArgs(C.Structure):
                 ('n_inst', C.c_int32), ('inst_set', C.c_void_p), ('inst_src', C.c_void_p), ('sigma_in', C.c_void_p),
                 ('n_steps', C.c_int32), ('n_emit', C.c_int32), ('emit_steps', C.c_void_p),
                 ('emit_trace', C.c_int32), ('mu', C.c_double * 16),
-                ('out_obs', C.c_void_p), ('out_snap', C.c_void_p)]
+                ('out_obs', C.c_void_p), ('out_snap', C.c_void_p), ('progress', C.c_void_p)]
 
 
 _lib = None

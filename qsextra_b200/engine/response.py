@@ -376,10 +376,11 @@ def _set_local(eng, program, mu, sequences, step_counts, host_out=None):
     for st in streams[1:]:
         st.wait_stream(main)                            # fork before anything of this call is enqueued on main
     shared['events'] = True                             # shared entries carry (stream, event) of their producer
-    # The longest read-out goes first even when the forward level of the heaviest diagram takes longer (an ensemble):
-    # its few CTAs must be resident BEFORE that level fills every SM with CTAs that stay for the whole launch -- enqueued
-    # after it, the read-out waits for the first of them to retire (measured: 22.3 ms instead of 21.6 ms end to end).
-    early = 1
+    # Read-outs before forward levels: their few CTAs must be resident BEFORE a level fills every SM with CTAs that stay
+    # for the whole launch -- enqueued after it, a read-out waits for the first of them to retire.  One system: only the
+    # longest read-out first (it is the critical path, the others fit in later).  An ensemble: all of them (its long
+    # level is scheduled by segments and leaves no gap until it ends).
+    early = len(pending) if n_parameter_sets(program) >= 4 else 1
     start_readouts(pending[:early], 0)
     pairs = [None] * len(sequences)
     for position, (st, k) in enumerate(zip(streams, order)):

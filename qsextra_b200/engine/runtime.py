@@ -162,12 +162,17 @@ class Engine:
                        hops=self.to_device(bound.hops if len(bound.hops) else np.zeros(4, np.int32), torch.int32),
                        n_tile_ints=int(len(bound.tiles)), n_hop_ints=int(len(bound.hops)))
         dev.update(rr_entries)
-        if program is not None and use_rr and not rr_entries and not os.environ.get('QSX_DISABLE_RRC'):
+        # The CTA-wide kernel serves the blocks the register-resident small-block kernel cannot -- and the ground-state
+        # block (no exciton on either side) next to it: its step is the diagonal multiply and the dampings only, which
+        # the damping-diagonal form reduces to ONE complex multiply per element and step (see ``evolve``).
+        no_exciton = bound.block.ka == 0 and bound.block.kb == 0
+        if program is not None and use_rr and (not rr_entries or no_exciton) and not os.environ.get('QSX_DISABLE_RRC'):
             from . import rrc as rrc_mod
             big = rrc_mod.build(program, bound)
             if big is not None:
                 dev.update(rrc=big, rrc_params=self.to_device(big.params, torch.float64),
-                           rrc_signature=np.ascontiguousarray(big.signature()))
+                           rrc_signature=np.ascontiguousarray(big.signature()),
+                           rrc_diagonal=all(op[0] in (rrc_mod.OP_DIAG, rrc_mod.OP_AD) for op in big.ops))
         return dev
 
     def upload_observables(self, ptr, idx, w, kind: str | None = None, mu=None):
@@ -220,9 +225,14 @@ class Engine:
                 args.mu[i] = float(m)
             out_obs = torch.empty((n_inst, n_emit, 1), dtype=torch.complex128, device=self.device)
             args.out_obs = out_obs.data_ptr()
+        progress = None
         if snapshots:
             out_snap = torch.empty((n_inst, n_emit, E), dtype=torch.complex128, device=self.device)
             args.out_snap = out_snap.data_ptr()
+            if obs is None and n_inst > 2 * self.sm_count and not os.environ.get('QSX_DISABLE_SEGMENTS'):
+                # more instances than the GPU keeps resident: let the kernel schedule (instance, segment) pairs
+                progress = torch.zeros(n_inst + 1, dtype=torch.int32, device=self.device)
+                args.progress = progress.data_ptr()
         ex_flops, ex_instr = big.executed_flops_per_step()
         with torch.cuda.device(self.device), self.span(
                 'evolve_rrc ({},{}) {}x{}{}'.format(big.block.ka, big.block.kb, big.block.dim_a, big.block.dim_b,
@@ -320,6 +330,22 @@ class Engine:
         n_emit = int(emit.numel())
         assert sigma_in.dtype == torch.complex128 and sigma_in.is_contiguous() and sigma_in.numel() % E == 0
         if 'rr' in prog and (obs is None or obs['n'] <= cabi.RR_MAX_OBS):
+            # a step of diagonal multiply + dampings (ground-state block), snapshots at a few steps only: the
+            # damping-diagonal form of the CTA-wide kernel walks it with one complex multiply per element and step
+            diagonal = (prog.get('rrc') is not None and prog.get('rrc_diagonal') and obs is None and snapshots
+                        and n_emit * 8 <= int(n_steps) + 8 and not os.environ.get('QSX_DISABLE_DIAGONAL_RRC'))
+            done = None
+            if diagonal:
+                if 'rrc_shipped' not in prog:           # (shipped programs only: that form is not specialised at run time)
+                    sig = prog['rrc_signature']
+                    found = self.lib.qsx_rrc_find_program(C.c_void_p(sig.ctypes.data), int(sig.size))
+                    prog['rrc_shipped'] = 0 <= found < self.n_shipped_rrc
+                if prog['rrc_shipped']:
+                    done = self._evolve_rrc(prog, sigma_in, n_inst, n_steps, emit, obs, snapshots, inst_set, inst_src)
+                    if done is None:
+                        prog['rrc_shipped'] = False
+            if done is not None:
+                return done
             return self._evolve_rr(prog, sigma_in, n_inst, n_steps, emit, obs, obs_real, snapshots, inst_set, inst_src)
         blk_ = blk.block
         if prog.get('rrc') is not None and 'rrc_family' not in prog:

@@ -33,7 +33,7 @@ def test_struct_layout_matches_header(tmp_path):
     struct with the ctypes mirrors."""
     pairs = [('qsx_op', cabi.QsxOp, 'flags'), ('qsx_pass', cabi.QsxPass, 'f'), ('qsx_block', cabi.QsxBlock, 'rankB'),
              ('qsx_evolve_args', cabi.QsxEvolveArgs, 'hops'), ('qsx_rr_op', cabi.QsxRROp, 'aux1'),
-             ('qsx_rr_args', cabi.QsxRRArgs, 'out_snap'), ('qsx_rrc_args', cabi.QsxRRCArgs, 'out_snap'),
+             ('qsx_rr_args', cabi.QsxRRArgs, 'out_snap'), ('qsx_rrc_args', cabi.QsxRRCArgs, 'progress'),
              ('qsx_rr_tables_args', cabi.QsxRRTablesArgs, 'out'), ('qsx_lindblad_args', cabi.QsxLindbladArgs, 'workspace'),
              ('qsx_frame_args', cabi.QsxFrameArgs, 'out'), ('qsx_system_desc', cabi.QsxSystemDesc, 'trotter_number')]
     body = ''.join('printf("%zu %zu\\n", sizeof({0}), offsetof({0}, {1}));'.format(c_name, last) for c_name, _, last in pairs)

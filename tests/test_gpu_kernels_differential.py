@@ -243,6 +243,46 @@ def test_throughput_form_of_the_cta_wide_kernel_with_many_instances(engine):
                         assert np.abs(got - sigma).max() < 1e-12 * scale, (ka, kb, flag, inst, step)
 
 
+def test_segment_scheduling_of_the_damping_diagonal_form(engine, monkeypatch):
+    """With more instances than resident CTAs and nothing but snapshots to write, qsx_rrc3.cuh lets its CTAs claim
+    (instance, segment) pairs and continue an instance from the snapshot of its previous segment (qsx_rrc_args.progress).
+    Same snapshots as one CTA per instance from start to end: 700 instances of the (1,1) and (0,1) blocks, different
+    parameter sets, shared source rows, irregular emission steps with and without step 0."""
+    from qsextra_b200.engine.program import StepProgram, SystemBatch
+    rng = np.random.default_rng(23)
+    n_sets, n_src, n_inst = 5, 7, 700
+    J = np.zeros((n_sets, 4, 4))
+    for i in range(3):
+        J[:, i, i + 1] = J[:, i + 1, i] = -0.3 + 0.02 * rng.normal(size=n_sets)
+    batch = SystemBatch(1.5 + 0.1 * rng.normal(size=(n_sets, 4)), J, np.ones((n_sets, 4)),
+                        0.3 + 0.05 * rng.normal(size=(n_sets, 1)), np.full((n_sets, 1), 0.7), (2,))
+    prog = StepProgram(batch, 0.15, 1, 1, 0.5 + 0.1 * rng.random((n_sets, 1)))
+    monkeypatch.setenv('QSX_RRC_V2', '1')
+    monkeypatch.setenv('QSX_RRC_V3', '1')
+    for ka, kb in ((1, 1), (0, 1)):
+        blk = prog.block(ka, kb)
+        bound = prog.bind(blk, fused=False)
+        sigma0 = rng.normal(size=(n_src, blk.size)) + 1j * rng.normal(size=(n_src, blk.size))
+        inst_set = torch.as_tensor(rng.integers(0, n_sets, n_inst), dtype=torch.int32, device=engine.device)
+        inst_src = torch.as_tensor(rng.integers(0, n_src, n_inst), dtype=torch.int32, device=engine.device)
+        for emit in ([0, 3, 4, 9, 17], [2, 5, 17]):
+            snaps = {}
+            for mode in ('segments', 'whole instances'):
+                if mode == 'whole instances':
+                    monkeypatch.setenv('QSX_DISABLE_SEGMENTS', '1')
+                else:
+                    monkeypatch.delenv('QSX_DISABLE_SEGMENTS', raising=False)
+                dev = engine.upload_program(bound, prog)
+                _, snap = engine.evolve(dev, engine.to_device(sigma0), n_inst, 17, emit, snapshots=True, inst_set=inst_set,
+                                        inst_src=inst_src)
+                torch.cuda.synchronize()
+                assert dev.get('rrc') is not None
+                snaps[mode] = snap.cpu().numpy()
+            scale = np.abs(snaps['whole instances']).max()
+            assert np.abs(snaps['segments'] - snaps['whole instances']).max() < 1e-12 * scale, (ka, kb, emit)
+    monkeypatch.delenv('QSX_DISABLE_SEGMENTS', raising=False)
+
+
 def test_damping_diagonal_form_of_the_transposed_steps(engine):
     """qsx_rrc3t.cuh (read-out propagations: z(1,1) = W(1,1) - W(0,0) per damped pseudomode, dampings folded into the
     diagonal multiply that ends the step, transform undone and redone around every emission) against the first form
