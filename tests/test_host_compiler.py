@@ -225,3 +225,22 @@ def test_transposed_program_propagates_the_read_out(sysdef, kw, blocks):
             s3 = emulator.apply_step(s3, fwd)
             w3 = emulator.apply_step(w3, bwd)
         assert abs(np.sum(w * s3) - np.sum(w3 * sigma)) < 1e-12 * np.abs(w).sum()
+
+
+def test_cta_wide_programs_refuse_collisions_that_empty_a_pseudomode():
+    """The damping-diagonal forms of the CTA-wide kernel divide by the product of the damping cosines at emissions
+    (csrc/qsx_rrc3.cuh, qsx_rrc3t.cuh): engine/rrc.py hands blocks whose collision (almost) empties a pseudomode in one
+    step to the general kernel instead (cos phi < 1e-3), and keeps ordinary rates."""
+    from qsextra_b200.engine import rrc as RRC
+    from qsextra_b200.engine.program import StepProgram, SystemBatch
+    J = np.zeros((1, 4, 4))
+    for i in range(3):
+        J[0, i, i + 1] = J[0, i + 1, i] = -0.3
+    batch = SystemBatch(np.full((1, 4), 1.5), J, np.ones((1, 4)), np.full((1, 1), 0.3), np.full((1, 1), 0.7), (2,))
+    # (the collision angle is sqrt(rate dt): pi / 2 moves the whole excitation of the pseudomode out in one step)
+    for rate, served in ((0.5, True), (30.0, True), ((np.pi / 2) ** 2 / 0.15, False)):
+        prog = StepProgram(batch, 0.15, 1, 1, np.full((1, 1), rate))
+        for ka, kb in ((1, 1), (0, 1)):
+            bound = prog.bind(prog.block(ka, kb), fused=False)
+            assert (RRC.build(prog, bound) is not None) == served, (rate, ka, kb)
+            assert (RRC.build(prog, bound.transposed()) is not None) == served, (rate, ka, kb)
