@@ -33,7 +33,7 @@ def _worker(rank, size, port, n_units, rows_per_unit, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('size,n_units,rows', [(2, 7, 1), (2, 5, 4), (3, 4, 2), (2, 1, 3)])
+@pytest.mark.parametrize('size,n_units,rows', [(2, 7, 1), (2, 5, 4), (3, 4, 2), (2, 1, 3), (2, 8, 3), (3, 6, 1)])   # (the last two: equal shares, gathered straight into the result)
 def test_shard_and_gather(tmp_path, size, n_units, rows):
     mp.spawn(_worker, args=(size, _free_port(), n_units, rows, str(tmp_path)), nprocs=size, join=True)
     bounds = []
